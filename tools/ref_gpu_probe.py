@@ -1,0 +1,150 @@
+#!/usr/bin/env python
+"""Golden-vector generator: run the REFERENCE's own Numba-CUDA kernels on a real GPU.
+
+Test infrastructure only. Imports ``process_functional`` from ``$REF_DIR`` (default
+/root/reference; on a gpurun box the two reference .py files are handed over outside
+the repo, under /tmp) with a stub ``tensorflow`` module, launches the reference
+kernels one by one with the launch geometry of disparity_compute_by_gpu
+(process_functional.py:1093-1267) on seeded synthetic inputs, and writes every
+intermediate (cost volumes, penalties, S volumes, WTA maps, L-R flags, filled and
+median-filtered maps) to ``.npz`` files. Those files, copied to tests/golden/, pin the
+CPU oracle to the real reference on real hardware.
+
+Usage: python tools/ref_gpu_probe.py --out gpurun_out/golden [--time-c2]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+
+def import_reference(ref_dir: str):
+    sys.modules.setdefault("tensorflow", types.ModuleType("tensorflow"))
+    sys.path.insert(0, ref_dir)
+    import numba.cuda as nbcuda
+
+    nbcuda.select_device = lambda idx: None  # reference pins visible device 1 (:1095)
+    import process_functional as pf  # noqa: E402
+
+    return pf, nbcuda
+
+
+def run_case(pf, cuda, imagel, imager, fl, fr, per_path: bool):
+    """Re-issue the launches of disparity_compute_by_gpu, keeping intermediates."""
+    rows, cols = imagel.shape
+    out = {}
+    d_imagel, d_imager = cuda.to_device(imagel), cuda.to_device(imager)
+    d_fl, d_fr = cuda.to_device(fl), cuda.to_device(fr)
+    d_cl = cuda.to_device(np.ones([rows, cols, 128], np.float32))
+    d_cr = cuda.to_device(np.ones([rows, cols, 128], np.float32))
+    d_sl = cuda.to_device(np.zeros([rows, cols, 128], np.float32))
+    d_sr = cuda.to_device(np.zeros([rows, cols, 128], np.float32))
+    d_dl = cuda.to_device(np.zeros([rows, cols], np.float32))
+    d_dr = cuda.to_device(np.zeros([rows, cols], np.float32))
+    g32 = ((cols + 31) // 32, (rows + 31) // 32)
+    pf.compute_cost_volume_kernel[g32, (32, 32)](d_fl, d_fr, d_cl, d_cr)
+    out["CL"], out["CR"] = d_cl.copy_to_host(), d_cr.copy_to_host()
+
+    d_pl = cuda.to_device(np.zeros([rows, cols, 16], np.float32))
+    d_pr = cuda.to_device(np.zeros([rows, cols, 16], np.float32))
+    pf.sgm_penelty_kernel[g32, (32, 32)](d_imagel, d_imager, d_pl, d_pr, 2.3, 55.9, 30, 4)
+    out["PL"], out["PR"] = d_pl.copy_to_host(), d_pr.copy_to_host()
+
+    grow, gcol = (rows + 7) // 8, (cols + 7) // 8
+    seq = [("UpToDown", gcol), ("DownToUp", gcol), ("LeftToRight", grow), ("RightToLeft", grow),
+           ("UpToDownAndLeftToRight", gcol), ("DownToUpAndLeftToRight", gcol),
+           ("UpToDownAndRightToLeft", gcol), ("DownToUpAndRightToLeft", gcol)]
+    for i, (name, grid) in enumerate(seq):
+        getattr(pf, f"SGM_{name}_kernel")[grid, 256](d_cl, d_cr, d_sl, d_sr, d_pl, d_pr)
+        if per_path:
+            out[f"SL_after{i + 1}"], out[f"SR_after{i + 1}"] = d_sl.copy_to_host(), d_sr.copy_to_host()
+    out["SL"], out["SR"] = d_sl.copy_to_host(), d_sr.copy_to_host()
+
+    pf.WTA_and_SupixelRefinement_kernel[g32, (32, 32)](d_sl, d_sr, d_dl, d_dr)
+    out["dl_wta"], out["dr_wta"] = d_dl.copy_to_host(), d_dr.copy_to_host()
+
+    d_fll = cuda.to_device(np.zeros([rows, cols], np.uint8))
+    d_flr = cuda.to_device(np.zeros([rows, cols], np.uint8))
+    d_dla = cuda.to_device(np.full([rows, cols], -7.0, np.float32))  # reference: uninitialised
+    d_dra = cuda.to_device(np.full([rows, cols], -7.0, np.float32))
+    pf.is_error_match_kernel[g32, (32, 32)](d_dl, d_dr, d_fll, d_flr)
+    out["flag_l"], out["flag_r"] = d_fll.copy_to_host(), d_flr.copy_to_host()
+    pf.LRC_kernel[g32, (32, 32)](d_dl, d_dr, d_fll, d_flr, d_dla, d_dra)
+    out["dl_fill"] = d_dla.copy_to_host()
+    out["dr_fill_untouched"] = np.array(bool(np.all(d_dra.copy_to_host() == -7.0)))
+    g16 = ((cols - 4 + 15) // 16, (rows - 4 + 15) // 16)
+    pf.Median_Filter_kernel[g16, (16, 16)](d_dla, d_dra, d_dl, d_dr)
+    out["dl_final"] = d_dl.copy_to_host()
+    cuda.synchronize()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref-dir", default=os.environ.get("REF_DIR", "/root/reference"))
+    ap.add_argument("--out", default="gpurun_out/golden")
+    ap.add_argument("--time-c2", action="store_true", help="also time the reference kernels at 695x555")
+    args = ap.parse_args()
+    os.makedirs(args.out, exist_ok=True)
+
+    from scenedepthestimation_b200 import synthetic as syn
+
+    pf, cuda = import_reference(args.ref_dir)
+    info = {"numba": __import__("numba").__version__, "device": str(cuda.get_current_device().name),
+            "cc": list(cuda.get_current_device().compute_capability)}
+    print(info, flush=True)
+
+    cases = {
+        # name: (H, W, kind, per_path)
+        "tiny_6x10": (6, 10, "noise", True),
+        "tex_20x48": (20, 48, "tex", False),
+        "tall_40x24": (40, 24, "noise", False),
+        "wide_9x300": (9, 300, "tex", False),
+    }
+    for idx, (name, (H, W, kind, per_path)) in enumerate(cases.items()):
+        seed = 4200 + idx
+        if kind == "tex":
+            il, ir, _ = syn.textured_pair(H, W, 128, seed)
+            fl, fr, _ = syn.correlated_features(H, W, 128, 64, seed)
+        else:
+            il, ir = syn.noise_pair(H, W, seed)
+            fl, fr = syn.unit_features(H, W, 64, seed)
+        out = run_case(pf, cuda, il, ir, fl, fr, per_path)
+        # end-to-end through the reference's own orchestrator as a cross-check
+        dl, dr, _ = pf.disparity_compute_by_gpu(il, ir, fl, fr, np.zeros([7], np.float32))
+        out["dl_e2e"] = dl
+        out["e2e_equals_stepwise"] = np.array(bool(np.array_equal(dl, out["dl_final"])))
+        np.savez_compressed(os.path.join(args.out, f"ref_{name}.npz"), imagel=il, imager=ir, fl=fl, fr=fr,
+                            seed=np.array(seed), **out)
+        print(name, "ok; e2e==stepwise:", bool(out["e2e_equals_stepwise"]),
+              "flagged:", int(out["flag_l"].sum()), flush=True)
+
+    if args.time_c2:
+        W, H, D = syn.CONFIGS["c2"]
+        il, ir, _ = syn.textured_pair(H, W, D, 1001)
+        fl, fr, _ = syn.correlated_features(H, W, D, 64, 1001)
+        ts = []
+        for it in range(4):
+            cuda.synchronize()
+            t0 = time.perf_counter()
+            dl, dr, _ = pf.disparity_compute_by_gpu(il, ir, fl, fr, np.zeros([7], np.float32))
+            cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        info["c2_ref_numba_seconds"] = ts
+        np.savez_compressed(os.path.join(args.out, "ref_c2_dl.npz"), dl=dl.astype(np.uint8))
+        print("reference numba kernels on this GPU, c2 wall seconds per call:", ts, flush=True)
+    with open(os.path.join(args.out, "probe_info.json"), "w") as f:
+        json.dump(info, f)
+
+
+if __name__ == "__main__":
+    main()
