@@ -1,0 +1,166 @@
+/*
+ * mccnn_b200 — C ABI of the B200-native MC-CNN stereo-matching hot path.
+ *
+ * Drop-in boundary for WHDY/SceneDepthEstimation's hot path. The reference has no FFI
+ * layer: the path sits behind Python functions and Numba-CUDA launch objects, so every
+ * entry point below names the reference function / kernel launch it replaces
+ * (file:line relative to the reference root). The Python shim in
+ * scenedepthestimation_b200/ binds these with ctypes and keeps the reference's
+ * signatures.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / numba types.
+ *  - Every pointer is a DEVICE pointer unless the name ends in _host. The caller owns all
+ *    memory, including scratch: sizes come from the *_workspace_bytes queries. Nothing is
+ *    allocated or freed behind the caller's back.
+ *  - Every launch entry takes a cudaStream_t (passed as void*) and is asynchronous.
+ *  - Return value: 0 on success, a positive cudaError_t, or a negative MCCNN_E* argument
+ *    error. mccnn_last_error() returns a thread-local message. There is no CPU fallback.
+ *  - Volumes are fp32 [H][W][Dp] with the disparity innermost and pitch
+ *    Dp = mccnn_disp_pitch(D) (D rounded up to a multiple of 4; pad entries undefined).
+ *    Feature maps are fp32 [H][W][64]. Images are u8 [H][W]. Disparity maps are fp32 [H][W]
+ *    holding integer values, as in the reference.
+ */
+#ifndef MCCNN_B200_H
+#define MCCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCCNN_ABI_VERSION 1
+#define MCCNN_FEATURES 64 /* num_of_feature_maps: hard-coded 64 in the reference (process_functional.py:128) */
+
+enum {
+    MCCNN_OK = 0,
+    MCCNN_EINVAL = -1,    /* bad size / null pointer / unsupported D */
+    MCCNN_EALIGN = -2,    /* pointer not 16-byte aligned */
+    MCCNN_EWORKSPACE = -3 /* workspace too small */
+};
+
+/* SGM arithmetic: MCCNN_SGM_EXACT reproduces the reference bit for bit (fp64 path state, fp32 S
+ * rounded once per path in launch order, process_functional.py:265-343, 1166-1202). */
+enum { MCCNN_SGM_EXACT = 0 };
+
+typedef struct {
+    float P1;       /* 2.3   process_functional.py:1141 (stored as fp32, :149) */
+    float P2;       /* 55.9  :1142 */
+    float P1_red;   /* fp32(2.3 / 4)   :141 */
+    float P2_red;   /* fp32(55.9 / 4)  :142 */
+    int threshold;  /* 30    :1143 */
+} mccnn_sgm_params;
+
+const char* mccnn_last_error(void);
+int mccnn_abi_version(void);
+/* Fills p with the reference's constants (process_functional.py:1141-1144). */
+void mccnn_default_sgm_params(mccnn_sgm_params* p);
+/* Pitch (in floats) of the disparity axis of a volume with D disparities. */
+int mccnn_disp_pitch(int D);
+/* 1 if the library was built with kernels for the device's architecture (sm_100a). */
+int mccnn_device_supported(int device);
+
+/* ---- pre-processing ------------------------------------------------------------------------
+ * Replaces match_single.py:34-43 (standardise with population std) + process_functional.py:13-19
+ * (zero-pad by `pad` = (patch-1)/2 on every side). out is fp32 [(H+2*pad)][(W+2*pad)].
+ * scratch: 4 doubles. */
+int mccnn_standardize_pad(const uint8_t* image, float* out_padded, double* scratch4,
+                          int H, int W, int pad, void* stream);
+/* Same padding for an already standardised fp32 [H][W] image (the compute_feature signature). */
+int mccnn_pad_f32(const float* image, float* out_padded, int H, int W, int pad, void* stream);
+
+/* ---- conv tower ----------------------------------------------------------------------------
+ * Replaces Net.construct (mc_cnn_brunch.py:31-48) as run by compute_feature
+ * (process_functional.py:21-45): num_layers 3x3 VALID convolutions, bias, ReLU on all but the
+ * last, then l2_normalize over the 64 channels.
+ *  padded   : fp32 [(H+2*num_layers)][(W+2*num_layers)] (one channel)
+ *  weights  : packed by mccnn_pack_weights_host from the reference's HWIO tensors
+ *  features : fp32 [H][W][64]
+ *  workspace: mccnn_conv_workspace_bytes(H, W, num_layers) bytes. */
+size_t mccnn_conv_packed_weight_bytes(int num_layers);
+/* hwio_host[i] -> conv{i+1}/weights [3][3][Cin][64], bias_host[i] -> conv{i+1}/biases [64]
+ * (mc_cnn_brunch.py:76-77); packed_host is host memory to be copied to the device verbatim. */
+int mccnn_pack_weights_host(const float* const* hwio_host, const float* const* bias_host,
+                            int num_layers, void* packed_host);
+size_t mccnn_conv_workspace_bytes(int H, int W, int num_layers);
+int mccnn_conv_tower(const float* padded, const void* packed_weights, float* features,
+                     void* workspace, size_t workspace_bytes, int H, int W, int num_layers, void* stream);
+
+/* ---- cost volume ---------------------------------------------------------------------------
+ * Replaces compute_cost_volume_kernel (process_functional.py:120-131) and the host np.ones
+ * fill (:1111-1114): CL[y][x][d] = CR[y][x-d][d] = fp32(-sum_i fp32(fl*fr)) with an fp64
+ * accumulator, entries never written = fill (1.0 in the reference). CR may be NULL. */
+int mccnn_cost_volume(const float* fl, const float* fr, float* CL, float* CR,
+                      int H, int W, int D, float fill, void* stream);
+/* [H][W][Dp] -> dense [D][H][W] (layout of the reference's CPU compute_cost_volume, :48-73). */
+int mccnn_volume_to_dhw(const float* vol, float* out_dhw, int H, int W, int D, void* stream);
+
+/* ---- semi-global matching ------------------------------------------------------------------
+ * Replaces sgm_penelty_kernel (:134-262, penalties are recomputed from the images on the fly and
+ * never stored), SGM_Interation (:265-343), the 8 path kernels (:346-797) launched at :1166-1202
+ * and, fused into the last pass, WTA_and_SupixelRefinement_kernel (:800-837).
+ *  CL, CR   : cost volumes (read only)
+ *  SL, SR   : aggregated volumes (written; need no initialisation). With keep_volumes == 0 the
+ *             final contents are unspecified (the last pass does not store S).
+ *  dispL/R  : fp32 [H][W] raw winner-takes-all maps
+ *  workspace: mccnn_sgm_workspace_bytes(H, W, D) bytes. */
+size_t mccnn_sgm_workspace_bytes(int H, int W, int D);
+int mccnn_sgm(const float* CL, const float* CR, const uint8_t* imageL, const uint8_t* imageR,
+              float* SL, float* SR, float* dispL, float* dispR,
+              void* workspace, size_t workspace_bytes,
+              int H, int W, int D, const mccnn_sgm_params* params, int mode, int keep_volumes, void* stream);
+/* One path kernel on one volume, S += path (launch-for-launch twin of :1166-1202; for tests).
+ * path: 0..7 in the reference's launch order. */
+int mccnn_sgm_single_path(const float* C, const uint8_t* image, float* S, void* workspace, size_t workspace_bytes,
+                          int H, int W, int D, const mccnn_sgm_params* params, int path, void* stream);
+/* Stand-alone WTA (:800-837): first strict minimum over d, stored as fp32. */
+int mccnn_wta(const float* S, float* disp, int H, int W, int D, void* stream);
+/* WTA over a dense [D][H][W] volume (CPU WTA1, :96-113). */
+int mccnn_wta_dhw(const float* vol_dhw, float* disp, int H, int W, int D, void* stream);
+
+/* ---- left-right check, fill, filters -------------------------------------------------------
+ * is_error_match_kernel (:977-1000). flagR may be NULL. */
+int mccnn_lr_flags(const float* dispL, const float* dispR, uint8_t* flagL, uint8_t* flagR,
+                   int H, int W, void* stream);
+/* LRC_kernel (:1003-1088), left map only (the reference never writes the right output). */
+int mccnn_lrc_fill(const float* dispL, const uint8_t* flagL, float* filled, int H, int W, void* stream);
+/* Median_Filter_kernel (:840-879) launched as at :1250: interior <- 5x5 median of `filled`,
+ * 2-pixel border <- `wta` (the raw map). out may alias wta. */
+int mccnn_median5(const float* filled, const float* wta, float* out, int H, int W, void* stream);
+/* Bilateral_Filter_kernel (:882-974); its launch is commented out in the reference (:1260). */
+int mccnn_bilateral9(const uint8_t* image, const float* disp, float* out, int H, int W, void* stream);
+/* astype('uint8') [* scale] of match_single.py:55 / match.py:90 (truncation toward zero, wrap mod 256). */
+int mccnn_encode_u8(const float* disp, uint8_t* out, int H, int W, int scale, void* stream);
+/* error_calculate.py:68-83 on the device: counts[0] = bad pixels, counts[1] = valid GT pixels.
+ * gt_half is the ground truth already resized and halved (fp32 [H][W]). */
+int mccnn_bad_pixels(const uint8_t* disp_u8, const float* gt_half, unsigned long long* counts2,
+                     int H, int W, void* stream);
+
+/* ---- whole path ----------------------------------------------------------------------------
+ * disparity_compute_by_gpu (:1093-1267) from device-resident inputs: cost volume -> SGM -> WTA ->
+ * L-R flags -> fill -> median. Returns the filtered left map and the raw right WTA map (the
+ * reference's right output is the median of an uninitialised buffer, so only its border, which
+ * equals the raw map, is defined). stage_ms_host (may be NULL) receives 7 floats in the layout of
+ * the reference's detail_time (match.py:95-103); filling it synchronises the stream.
+ *  workspace: mccnn_pipeline_workspace_bytes(H, W, D) bytes. */
+size_t mccnn_pipeline_workspace_bytes(int H, int W, int D);
+int mccnn_disparity_pipeline(const uint8_t* imageL, const uint8_t* imageR, const float* fl, const float* fr,
+                             float* dispL_out, float* dispR_out, void* workspace, size_t workspace_bytes,
+                             int H, int W, int D, const mccnn_sgm_params* params, int mode,
+                             float* stage_ms_host, void* stream);
+
+/* match_single.py:34-55 between imread and imwrite, from device u8 images: standardise, pad, conv
+ * tower (both images), then mccnn_disparity_pipeline.
+ *  workspace: mccnn_match_workspace_bytes(H, W, D, num_layers) bytes. */
+size_t mccnn_match_workspace_bytes(int H, int W, int D, int num_layers);
+int mccnn_match_pair(const uint8_t* imageL, const uint8_t* imageR, const void* packed_weights,
+                     float* dispL_out, float* dispR_out, void* workspace, size_t workspace_bytes,
+                     int H, int W, int D, int num_layers, const mccnn_sgm_params* params, int mode,
+                     float* stage_ms_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCCNN_B200_H */

@@ -1,0 +1,273 @@
+// Winner-takes-all, left-right consistency check, occlusion fill, 5x5 median, 9x9 bilateral filter,
+// u8 encode and the bad-pixel metric (sm_100a). All are byte/row-bound per-pixel kernels.
+//
+// Replaces, with the reference's exact arithmetic:
+//   WTA_and_SupixelRefinement_kernel  process_functional.py:800-837   (and CPU WTA1, :96-113)
+//   is_error_match_kernel             process_functional.py:977-1000
+//   LRC_kernel                        process_functional.py:1003-1088
+//   Median_Filter_kernel              process_functional.py:840-879, launched at :1250
+//   Bilateral_Filter_kernel           process_functional.py:882-974  (launch commented out at :1260)
+//   astype('uint8')[*2]               match_single.py:55, match.py:90
+//   error_calculate.py:68-83
+#include "common.cuh"
+
+namespace mccnn {
+namespace {
+
+// ---- WTA over [H][W][Dp]: one warp per pixel, lanes along d (coalesced)
+__global__ void __launch_bounds__(256) wta_kernel(const float* __restrict__ S, float* __restrict__ disp, int npix, int D,
+                                                 int Dp) {
+    const int lane = threadIdx.x & 31;
+    const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pix >= npix) return;
+    const float* row = S + (size_t)pix * Dp;
+    float best = __int_as_float(0x7f800000);
+    int bd = 0x7fffffff;
+    for (int d = lane; d < D; d += 32) {
+        const float v = row[d] + 0.0f;
+        if (v < best) { best = v; bd = d; }
+    }
+    int k = __float_as_int(best);
+    k ^= (k >> 31) & 0x7fffffff;
+    const int mk = __reduce_min_sync(0xffffffffu, k);
+    const int md = __reduce_min_sync(0xffffffffu, k == mk ? bd : 0x7fffffff);
+    if (lane == 0) disp[pix] = (float)md;
+}
+
+// ---- WTA over dense [D][H][W] (CPU WTA1): thread per pixel, coalesced along x
+__global__ void wta_dhw_kernel(const float* __restrict__ vol, float* __restrict__ disp, int npix, int D) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    float best = __int_as_float(0x7f800000);
+    int bd = -1;
+    for (int d = 0; d < D; d++) {
+        const float v = vol[(size_t)d * npix + p];
+        if (v < best) { best = v; bd = d; }
+    }
+    disp[p] = (float)bd;
+}
+
+// ---- left-right consistency flags (:977-1000). The reference indexes with uint8(x - ld); run on a
+// B200 the index is NOT truncated (tests/golden/ref_wide_9x300.npz), so neither is it here.
+__global__ void lr_flags_kernel(const float* __restrict__ dl, const float* __restrict__ dr, unsigned char* __restrict__ fL,
+                                unsigned char* __restrict__ fR, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const size_t o = (size_t)y * W;
+    const float ld = dl[o + x];
+    const double rd = (double)x - (double)ld;
+    unsigned char f = 0;
+    if (rd >= 0) {
+        const int idx = (int)rd;
+        const float minus = ld - dr[o + idx];
+        f = (minus > 1.0f || minus < -1.0f) ? 1 : 0;
+    }
+    fL[o + x] = f;
+    if (fR) {
+        const float rdv = dr[o + x];
+        const double ldx = (double)x + (double)rdv;
+        unsigned char g = 0;
+        if (ldx < W) {
+            const int idx = (int)ldx;
+            const float minus = rdv - dl[o + idx];
+            g = (minus > 1.0f || minus < -1.0f) ? 1 : 0;
+        }
+        fR[o + x] = g;
+    }
+}
+
+// ---- occlusion fill (:1003-1088): mean of the nearest unflagged raw disparity up, down, right, left
+__global__ void lrc_fill_kernel(const float* __restrict__ dl, const unsigned char* __restrict__ fl, float* __restrict__ out,
+                                int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const size_t o = (size_t)y * W + x;
+    if (fl[o] != 1) {
+        out[o] = dl[o];
+        return;
+    }
+    int number = 0;
+    double sum_d = 0.0;
+    int idy = y;
+    while (idy >= 0 && fl[(size_t)idy * W + x] == 1) idy--;
+    if (idy >= 0) { number++; sum_d += (double)dl[(size_t)idy * W + x]; }
+    idy = y;
+    while (idy < H && fl[(size_t)idy * W + x] == 1) idy++;
+    if (idy < H) { number++; sum_d += (double)dl[(size_t)idy * W + x]; }
+    int idx = x;
+    while (idx < W && fl[(size_t)y * W + idx] == 1) idx++;
+    if (idx < W) { number++; sum_d += (double)dl[(size_t)y * W + idx]; }
+    idx = x;
+    while (idx >= 0 && fl[(size_t)y * W + idx] == 1) idx--;
+    if (idx >= 0) { number++; sum_d += (double)dl[(size_t)y * W + idx]; }
+    out[o] = number > 0 ? (float)(sum_d / (double)number) : dl[o];
+}
+
+// ---- 5x5 median (:840-879): the 13th smallest of 25; the 2-pixel border keeps the raw WTA map
+__global__ void median5_kernel(const float* __restrict__ filled, const float* __restrict__ wta, float* __restrict__ out,
+                               int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t o = (size_t)y * W + x;
+    if (x < 2 || y < 2 || x + 2 >= W || y + 2 >= H) {
+        if (out != wta) out[o] = wta[o];
+        return;
+    }
+    float w[25];
+#pragma unroll
+    for (int i = -2; i <= 2; i++)
+#pragma unroll
+        for (int j = -2; j <= 2; j++) w[(i + 2) * 5 + j + 2] = filled[(size_t)(y + i) * W + x + j];
+    // partial selection: after pass i, w[i] holds the (i+1)-th smallest (fully unrolled, registers only)
+    float cur = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 13; i++) {
+        cur = w[i];
+#pragma unroll
+        for (int j = i + 1; j < 25; j++) {
+            const float lo = fminf(cur, w[j]);
+            w[j] = fmaxf(cur, w[j]);
+            cur = lo;
+        }
+    }
+    out[o] = cur;
+}
+
+// ---- 9x9 range-weighted mean (:882-974); uint8 differences wrap to uint64 (App. A7)
+__constant__ float kBilateralW[10] = {0.167747f, 0.165145f, 0.157581f, 0.145735f, 0.130632f,
+                                      0.113490f, 0.095563f, 0.077991f, 0.061692f, 0.047297f};
+
+__global__ void bilateral9_kernel(const unsigned char* __restrict__ img, const float* __restrict__ disp,
+                                  float* __restrict__ out, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int ic = img[(size_t)y * W + x];
+    double wsum = 0.0, dsum = 0.0;
+    for (int i = -4; i <= 4; i++)
+        for (int j = -4; j <= 4; j++) {
+            const int yy = y + i, xx = x + j;
+            const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const int in_i = in ? (int)img[(size_t)yy * W + xx] : 0;
+            const float in_d = in ? disp[(size_t)yy * W + xx] : 0.0f;
+            const int minus = ic - in_i;  // unsigned wrap: negative differences are huge, never < 5
+            if (minus >= 0 && minus < 5) {
+                const float wgt = kBilateralW[minus];
+                wsum += (double)wgt;
+                dsum += (double)__fmul_rn(wgt, in_d);
+            }
+        }
+    out[(size_t)y * W + x] = (float)(dsum / wsum);
+}
+
+__global__ void encode_u8_kernel(const float* __restrict__ disp, unsigned char* __restrict__ out, size_t n, int scale) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned v = (unsigned)(long long)disp[i];  // astype('uint8'): truncate toward zero, modulo 256
+    out[i] = (unsigned char)((v & 255u) * (unsigned)scale);
+}
+
+__global__ void bad_pixels_kernel(const unsigned char* __restrict__ disp, const float* __restrict__ gt,
+                                  unsigned long long* __restrict__ counts, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = 0, valid = 0;
+    if (i < n) {
+        const float t = gt[i];
+        if (!(t == __int_as_float(0x7f800000) || t == 0.0f)) {
+            valid = 1;
+            bad = fabsf((float)disp[i] - t) > 1.0f ? 1 : 0;
+        }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, bad), v = __ballot_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0) {
+        if (b) atomicAdd(&counts[0], (unsigned long long)__popc(b));
+        if (v) atomicAdd(&counts[1], (unsigned long long)__popc(v));
+    }
+}
+
+inline int check_hw(const char* who, int H, int W) {
+    MCCNN_REQUIRE(H >= 1 && W >= 1 && H <= 65535, MCCNN_EINVAL, "%s: bad shape H=%d W=%d", who, H, W);
+    return 0;
+}
+
+}  // namespace
+}  // namespace mccnn
+
+using namespace mccnn;
+
+extern "C" int mccnn_wta(const float* S, float* disp, int H, int W, int D, void* stream) {
+    MCCNN_REQUIRE(S && disp, MCCNN_EINVAL, "mccnn_wta: null argument");
+    if (int e = check_hw("mccnn_wta", H, W)) return e;
+    MCCNN_REQUIRE(D >= 1, MCCNN_EINVAL, "mccnn_wta: D=%d", D);
+    const int npix = H * W;
+    wta_kernel<<<ceil_div(npix, 8), 256, 0, (cudaStream_t)stream>>>(S, disp, npix, D, disp_pitch(D));
+    MCCNN_LAUNCH_CHECK("wta_kernel");
+    return 0;
+}
+
+extern "C" int mccnn_wta_dhw(const float* vol, float* disp, int H, int W, int D, void* stream) {
+    MCCNN_REQUIRE(vol && disp, MCCNN_EINVAL, "mccnn_wta_dhw: null argument");
+    if (int e = check_hw("mccnn_wta_dhw", H, W)) return e;
+    MCCNN_REQUIRE(D >= 1, MCCNN_EINVAL, "mccnn_wta_dhw: D=%d", D);
+    const int npix = H * W;
+    wta_dhw_kernel<<<ceil_div(npix, 256), 256, 0, (cudaStream_t)stream>>>(vol, disp, npix, D);
+    MCCNN_LAUNCH_CHECK("wta_dhw_kernel");
+    return 0;
+}
+
+extern "C" int mccnn_lr_flags(const float* dispL, const float* dispR, uint8_t* flagL, uint8_t* flagR, int H, int W,
+                              void* stream) {
+    MCCNN_REQUIRE(dispL && dispR && flagL, MCCNN_EINVAL, "mccnn_lr_flags: null argument");
+    if (int e = check_hw("mccnn_lr_flags", H, W)) return e;
+    lr_flags_kernel<<<dim3(ceil_div(W, 128), H), 128, 0, (cudaStream_t)stream>>>(dispL, dispR, flagL, flagR, H, W);
+    MCCNN_LAUNCH_CHECK("lr_flags_kernel");
+    return 0;
+}
+
+extern "C" int mccnn_lrc_fill(const float* dispL, const uint8_t* flagL, float* filled, int H, int W, void* stream) {
+    MCCNN_REQUIRE(dispL && flagL && filled, MCCNN_EINVAL, "mccnn_lrc_fill: null argument");
+    if (int e = check_hw("mccnn_lrc_fill", H, W)) return e;
+    lrc_fill_kernel<<<dim3(ceil_div(W, 128), H), 128, 0, (cudaStream_t)stream>>>(dispL, flagL, filled, H, W);
+    MCCNN_LAUNCH_CHECK("lrc_fill_kernel");
+    return 0;
+}
+
+extern "C" int mccnn_median5(const float* filled, const float* wta, float* out, int H, int W, void* stream) {
+    MCCNN_REQUIRE(filled && wta && out, MCCNN_EINVAL, "mccnn_median5: null argument");
+    MCCNN_REQUIRE(filled != out, MCCNN_EINVAL, "mccnn_median5: out must not alias the filtered input");
+    if (int e = check_hw("mccnn_median5", H, W)) return e;
+    median5_kernel<<<dim3(ceil_div(W, 32), ceil_div(H, 8)), dim3(32, 8), 0, (cudaStream_t)stream>>>(filled, wta, out, H, W);
+    MCCNN_LAUNCH_CHECK("median5_kernel");
+    return 0;
+}
+
+extern "C" int mccnn_bilateral9(const uint8_t* image, const float* disp, float* out, int H, int W, void* stream) {
+    MCCNN_REQUIRE(image && disp && out && disp != out, MCCNN_EINVAL, "mccnn_bilateral9: null or aliased argument");
+    if (int e = check_hw("mccnn_bilateral9", H, W)) return e;
+    bilateral9_kernel<<<dim3(ceil_div(W, 32), ceil_div(H, 8)), dim3(32, 8), 0, (cudaStream_t)stream>>>(image, disp, out, H, W);
+    MCCNN_LAUNCH_CHECK("bilateral9_kernel");
+    return 0;
+}
+
+extern "C" int mccnn_encode_u8(const float* disp, uint8_t* out, int H, int W, int scale, void* stream) {
+    MCCNN_REQUIRE(disp && out, MCCNN_EINVAL, "mccnn_encode_u8: null argument");
+    if (int e = check_hw("mccnn_encode_u8", H, W)) return e;
+    const size_t n = (size_t)H * W;
+    encode_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(disp, out, n, scale);
+    MCCNN_LAUNCH_CHECK("encode_u8_kernel");
+    return 0;
+}
+
+extern "C" int mccnn_bad_pixels(const uint8_t* disp_u8, const float* gt_half, unsigned long long* counts2, int H, int W,
+                                void* stream) {
+    MCCNN_REQUIRE(disp_u8 && gt_half && counts2, MCCNN_EINVAL, "mccnn_bad_pixels: null argument");
+    if (int e = check_hw("mccnn_bad_pixels", H, W)) return e;
+    MCCNN_CUDA(cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
+    const size_t n = (size_t)H * W;
+    bad_pixels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(disp_u8, gt_half, counts2, n);
+    MCCNN_LAUNCH_CHECK("bad_pixels_kernel");
+    return 0;
+}

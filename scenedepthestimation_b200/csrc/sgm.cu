@@ -1,0 +1,448 @@
+// Semi-global matching, exact-arithmetic mode (sm_100a).
+//
+// Replaces, for any disparity count D <= 1024:
+//   sgm_penelty_kernel        process_functional.py:134-262  (penalties recomputed on the fly)
+//   SGM_Interation            process_functional.py:265-343
+//   the 8 SGM_*_kernel paths  process_functional.py:346-797, launched at :1166-1202
+//   WTA_and_SupixelRefinement process_functional.py:800-837  (fused into the last pass)
+//
+// Arithmetic contract (pinned by tests/golden/ref_*.npz):
+//   * path state L, min and min+P2 are fp64; P1/P2 are fp32 constants widened on use;
+//   * c[d] = fp64(C[d]) + (min(L[d-1]+P1, L[d], L[d+1]+P1, minL+P2) - minL), with the raw cost on the
+//     first pixel of a scanline and after a diagonal column wrap;
+//   * S = fp32(fp64(S) + c) once per path, paths in the launch order
+//     down, up, right, left, down-right, up-right, down-left, up-left;
+//   * a scanline visits N-1 of its N pixels; the "up" path has P1 = P2 = 0 (the reference never
+//     writes penalty channels 0/1) and therefore adds the raw cost: it is fused into the first pass.
+//   * penalty pair for a step prev -> cur: (P1, P2) iff 0 <= I[cur] - I[prev] <= threshold, else the
+//     reduced pair (uint8 differences wrap to uint64 in the reference, App. A3).
+//
+// Kernel shape: one warp owns one scanline. Lane l holds NPL consecutive disparities of the fp64
+// state in registers, so the d-1 / d+1 neighbours need two shuffles per step, and the minimum over
+// all disparities is two integer REDUX operations on an order-preserving key. Cost / S rows
+// (D * 4 bytes, contiguous) stream through shared memory with 1-D bulk async copies
+// (cp.async.bulk + mbarrier, a ring of STAGES rows per warp) and the updated S row goes back with a
+// bulk store. Warps pull scanlines from a global counter (persistent grid, multiple of the SM count).
+#include "common.cuh"
+
+namespace mccnn {
+namespace {
+
+enum SgmMode { SGM_MID = 0, SGM_FIRST_FUSED = 1, SGM_LAST_WTA = 2 };
+
+struct SgmArgs {
+    const float* C[2];
+    float* S[2];
+    const unsigned char* img[2];
+    float* disp[2];
+    int H, W, D, Dp;
+    int dy, dx, horizontal;
+    int nlines;        // scanlines per side
+    int nsteps_dp;     // pixels visited by the dynamic program
+    int nsteps_total;  // >= nsteps_dp: FIRST_FUSED / LAST_WTA also touch the pixel the path skips
+    int nsides;
+    double P1, P2, P1r, P2r;
+    int threshold;
+    int store_s;
+    unsigned* counter;
+};
+
+constexpr int WARPS_PER_CTA = 4;
+
+__device__ __forceinline__ void scan_pixel(const SgmArgs& a, int line, int t, int& row, int& col) {
+    if (a.horizontal) {
+        row = line;
+        col = a.dx > 0 ? t : a.W - 1 - t;
+    } else {
+        row = a.dy > 0 ? t : a.H - 1 - t;
+        if (a.dx == 0) {
+            col = line;
+        } else {
+            int c = (line + a.dx * t) % a.W;
+            col = c < 0 ? c + a.W : c;
+        }
+    }
+}
+
+// order-preserving map double -> signed 64-bit integer
+__device__ __forceinline__ long long dkey(double v) {
+    long long b = __double_as_longlong(v);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+
+__device__ __forceinline__ double warp_min_f64(double v) {
+    long long k = dkey(v);
+    int hi = (int)(k >> 32);
+    unsigned lo = (unsigned)k;
+    int mh = __reduce_min_sync(0xffffffffu, hi);
+    unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    long long mk = ((long long)mh << 32) | (long long)ml;
+    return __longlong_as_double(mk ^ ((mk >> 63) & 0x7fffffffffffffffLL));
+}
+
+template <int NPL>
+__device__ __forceinline__ void load_chunk(const float* buf, int lane, float (&v)[NPL]) {
+    const float* p = buf + lane * NPL;
+    if constexpr (NPL % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < NPL / 4; j++) {
+            float4 q = reinterpret_cast<const float4*>(p)[j];
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+        }
+    } else if constexpr (NPL % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < NPL / 2; j++) {
+            float2 q = reinterpret_cast<const float2*>(p)[j];
+            v[2 * j] = q.x; v[2 * j + 1] = q.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPL; j++) v[j] = p[j];
+    }
+}
+
+template <int NPL>
+__device__ __forceinline__ void store_chunk(float* buf, int lane, const float (&v)[NPL]) {
+    float* p = buf + lane * NPL;
+    if constexpr (NPL % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < NPL / 4; j++)
+            reinterpret_cast<float4*>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else if constexpr (NPL % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < NPL / 2; j++) reinterpret_cast<float2*>(p)[j] = make_float2(v[2 * j], v[2 * j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPL; j++) p[j] = v[j];
+    }
+}
+
+template <int NPL, int STAGES, int MODE>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmArgs a) {
+    constexpr bool kReadS = (MODE != SGM_FIRST_FUSED);
+    constexpr int ROW = 32 * NPL;  // floats per row buffer
+    constexpr int IN_BUFS = kReadS ? 2 : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PER_WARP_FLOATS = ROW * (STAGES * IN_BUFS + 2);
+    float* wbase = reinterpret_cast<float*>(smem_raw) + (size_t)warp * PER_WARP_FLOATS;
+    float* inbuf = wbase;                           // [STAGES][IN_BUFS][ROW]
+    float* outbuf = wbase + ROW * STAGES * IN_BUFS;  // [2][ROW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS_PER_CTA * PER_WARP_FLOATS * sizeof(float)) +
+                     warp * STAGES;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    const uint32_t copy_bytes = (uint32_t)a.Dp * 4u;
+    const size_t pix_stride = (size_t)a.Dp;
+    const int npix_line = a.horizontal ? a.W : a.H;
+    const int d0 = lane * NPL;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+
+    uint32_t gstep = 0;  // rows consumed by this warp so far (ring position / mbarrier phase)
+    uint32_t ostep = 0;  // rows stored so far (output staging parity)
+
+    for (;;) {
+        unsigned q = 0;
+        if (lane == 0) q = atomicAdd(a.counter, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= (unsigned)(a.nsides * a.nlines)) break;
+        const int side = (int)q / a.nlines;
+        const int line = (int)q - side * a.nlines;
+        const float* __restrict__ Cv = a.C[side];
+        float* __restrict__ Sv = a.S[side];
+        const unsigned char* __restrict__ img = a.img[side];
+
+        auto issue_load = [&](int t, uint32_t g) {
+            int row, col;
+            scan_pixel(a, line, t, row, col);
+            const size_t off = ((size_t)row * a.W + col) * pix_stride;
+            const int st = g % STAGES;
+            float* dst = inbuf + (size_t)st * IN_BUFS * ROW;
+            mbar_expect_tx(&bars[st], copy_bytes * IN_BUFS);
+            bulk_g2s(dst, Cv + off, copy_bytes, &bars[st]);
+            if constexpr (kReadS) bulk_g2s(dst + ROW, Sv + off, copy_bytes, &bars[st]);
+        };
+        auto image_at = [&](int t) -> int {
+            int row, col;
+            scan_pixel(a, line, min(t, npix_line - 1), row, col);
+            return (int)img[(size_t)row * a.W + col];
+        };
+
+        if (lane == 0) {
+            const int pre = min(STAGES, a.nsteps_total);
+            for (int t = 0; t < pre; t++) issue_load(t, gstep + t);
+        }
+        // image values: lane l of blk_cur holds I[pixel tb + 1 + l]
+        int i_cur = image_at(0);
+        int blk_cur = image_at(1 + lane);
+        int blk_next = image_at(33 + lane);
+
+        double L[NPL];
+#pragma unroll
+        for (int j = 0; j < NPL; j++) L[j] = 1.0;
+        double minL = 1.0, minLP2 = 1.0;
+        bool edge_full = true;  // penalty class of the edge (t-1 -> t)
+
+        for (int t = 0; t < a.nsteps_total; t++) {
+            int row, col;
+            scan_pixel(a, line, t, row, col);
+            const int st = gstep % STAGES;
+            mbar_wait(&bars[st], (gstep / STAGES) & 1u);
+            float cf[NPL], sf[NPL];
+            const float* ib = inbuf + (size_t)st * IN_BUFS * ROW;
+            load_chunk<NPL>(ib, lane, cf);
+            if constexpr (kReadS) load_chunk<NPL>(ib + ROW, lane, sf);
+            __syncwarp();
+            if (lane == 0 && t + STAGES < a.nsteps_total) issue_load(t + STAGES, gstep + STAGES);
+            gstep++;
+
+            if ((t & 31) == 0 && t > 0) {
+                blk_cur = blk_next;
+                blk_next = image_at(t + 33 + lane);
+            }
+            const int i_next = __shfl_sync(0xffffffffu, blk_cur, t & 31);
+            const int dn = i_next - i_cur;
+            const bool next_full = (dn >= 0) && (dn <= a.threshold);
+
+            const bool dp_active = t < a.nsteps_dp;
+            if (dp_active) {
+                const bool wrapped = (!a.horizontal) && (a.dx != 0) && (t > 0) && (a.dx > 0 ? col == 0 : col == a.W - 1);
+                if (t == 0 || wrapped) {
+#pragma unroll
+                    for (int j = 0; j < NPL; j++) L[j] = (d0 + j < a.D) ? (double)cf[j] : INF;
+                } else {
+                    const double P1 = edge_full ? a.P1 : a.P1r;
+                    double up = __shfl_up_sync(0xffffffffu, L[NPL - 1], 1);
+                    double dn_ = __shfl_down_sync(0xffffffffu, L[0], 1);
+                    if (lane == 0) up = INF;    // d-1 < 0: the reference clamps to L[0]+P1 >= L[0] (:300-301)
+                    if (lane == 31) dn_ = INF;  // d+1 >= 32*NPL
+                    double a_prev = up + P1;
+                    double a_cur = L[0] + P1;
+#pragma unroll
+                    for (int j = 0; j < NPL; j++) {
+                        const double a_next = ((j + 1 < NPL) ? L[j + 1 < NPL ? j + 1 : j] : dn_) + P1;
+                        const double m = fmin(fmin(a_prev, a_next), fmin(L[j], minLP2));
+                        double c = (double)cf[j];
+                        c += (m - minL);
+                        a_prev = a_cur;
+                        a_cur = a_next;
+                        L[j] = (d0 + j < a.D) ? c : INF;
+                    }
+                }
+                // minimum over d, consumed at the next pixel together with this pixel's P2 (:332-341)
+                double m = L[0];
+#pragma unroll
+                for (int j = 1; j < NPL; j++) m = fmin(m, L[j]);
+                minL = warp_min_f64(m);
+                minLP2 = minL + (next_full ? a.P2 : a.P2r);
+            }
+            edge_full = next_full;
+            i_cur = i_next;
+
+            // ---- S update: fp32 += fp64, one rounding per path (:321-330)
+            float so[NPL];
+#pragma unroll
+            for (int j = 0; j < NPL; j++) {
+                if constexpr (MODE == SGM_FIRST_FUSED) {
+                    // S starts at 0 (:1116-1117): down path, then the up path's raw-cost add on rows >= 1
+                    float s = dp_active ? (float)(0.0 + L[j]) : 0.0f;
+                    if (row >= 1) s = (float)((double)s + (double)cf[j]);
+                    so[j] = s;
+                } else {
+                    so[j] = dp_active ? (float)((double)sf[j] + L[j]) : sf[j];
+                }
+            }
+
+            if (MODE != SGM_LAST_WTA || a.store_s) {
+                float* ob = outbuf + (ostep & 1u) * ROW;
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+                store_chunk<NPL>(ob, lane, so);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_s2g(Sv + ((size_t)row * a.W + col) * pix_stride, ob, copy_bytes);
+                    bulk_commit();
+                }
+                ostep++;
+            }
+
+            if constexpr (MODE == SGM_LAST_WTA) {
+                // first strict minimum over d (:805-811)
+                float best = __int_as_float(0x7f800000);
+                int bj = 0;
+#pragma unroll
+                for (int j = 0; j < NPL; j++) {
+                    const float v = (d0 + j < a.D) ? so[j] + 0.0f : __int_as_float(0x7f800000);
+                    if (v < best) { best = v; bj = j; }
+                }
+                int k = __float_as_int(best);
+                k ^= (k >> 31) & 0x7fffffff;
+                const int mk = __reduce_min_sync(0xffffffffu, k);
+                const unsigned who = __ballot_sync(0xffffffffu, k == mk);
+                const int src = __ffs(who) - 1;
+                const int idx = __shfl_sync(0xffffffffu, d0 + bj, src);
+                if (lane == 0) a.disp[side][(size_t)row * a.W + col] = (float)idx;
+            }
+        }
+    }
+    if (lane == 0) bulk_wait_all<0>();
+}
+
+template <int NPL, int STAGES, int MODE>
+int launch_scan(const SgmArgs& a, cudaStream_t stream) {
+    constexpr int IN_BUFS = (MODE != SGM_FIRST_FUSED) ? 2 : 1;
+    const size_t smem = (size_t)WARPS_PER_CTA * (32 * NPL * (STAGES * IN_BUFS + 2)) * sizeof(float) +
+                        (size_t)WARPS_PER_CTA * STAGES * sizeof(uint64_t);
+    auto kern = sgm_scan_kernel<NPL, STAGES, MODE>;
+    MCCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    MCCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS_PER_CTA * 32, smem));
+    MCCNN_REQUIRE(per_sm >= 1, MCCNN_EINVAL, "sgm_scan_kernel<%d>: does not fit on an SM (smem %zu)", NPL, smem);
+    const int total_lines = a.nsides * a.nlines;
+    int grid = sm_count() * per_sm;
+    const int need = ceil_div(total_lines, WARPS_PER_CTA);
+    if (grid > need) grid = need;
+    kern<<<grid, WARPS_PER_CTA * 32, smem, stream>>>(a);
+    MCCNN_LAUNCH_CHECK("sgm_scan_kernel");
+    return 0;
+}
+
+template <int MODE>
+int dispatch_scan(const SgmArgs& a, cudaStream_t stream) {
+    const int need = ceil_div(a.D, 32);
+#define MCCNN_SGM_CASE(N, ST) \
+    if (need <= N) return launch_scan<N, ST, MODE>(a, stream);
+    MCCNN_SGM_CASE(1, 6)
+    MCCNN_SGM_CASE(2, 6)
+    MCCNN_SGM_CASE(3, 6)
+    MCCNN_SGM_CASE(4, 6)
+    MCCNN_SGM_CASE(5, 4)
+    MCCNN_SGM_CASE(6, 4)
+    MCCNN_SGM_CASE(7, 4)
+    MCCNN_SGM_CASE(8, 4)
+    MCCNN_SGM_CASE(10, 4)
+    MCCNN_SGM_CASE(13, 3)
+    MCCNN_SGM_CASE(16, 3)
+    MCCNN_SGM_CASE(20, 3)
+    MCCNN_SGM_CASE(25, 3)
+    MCCNN_SGM_CASE(32, 3)
+#undef MCCNN_SGM_CASE
+    set_error("sgm: D=%d exceeds the supported maximum of 1024", a.D);
+    return MCCNN_EINVAL;
+}
+
+// geometry of the reference's 8 path kernels in launch order (:1166-1202)
+const int kPathDy[8] = {1, -1, 0, 0, 1, -1, 1, -1};
+const int kPathDx[8] = {0, 0, 1, -1, 1, 1, -1, -1};
+
+void set_path(SgmArgs& a, int path) {
+    a.dy = kPathDy[path];
+    a.dx = kPathDx[path];
+    a.horizontal = (a.dy == 0);
+    a.nlines = a.horizontal ? a.H : a.W;
+    a.nsteps_dp = (a.horizontal ? a.W : a.H) - 1;
+    a.nsteps_total = a.nsteps_dp;
+}
+
+void set_params(SgmArgs& a, const mccnn_sgm_params* p) {
+    a.P1 = (double)p->P1;
+    a.P2 = (double)p->P2;
+    a.P1r = (double)p->P1_red;
+    a.P2r = (double)p->P2_red;
+    a.threshold = p->threshold;
+}
+
+int check_common(const void* C, int H, int W, int D) {
+    MCCNN_REQUIRE(C != nullptr, MCCNN_EINVAL, "sgm: null volume");
+    MCCNN_REQUIRE(H >= 3 && W >= 3, MCCNN_EINVAL, "sgm: image %dx%d too small (need >= 3x3)", W, H);
+    MCCNN_REQUIRE(D >= 1 && D <= 1024, MCCNN_EINVAL, "sgm: D=%d outside 1..1024", D);
+    return 0;
+}
+
+}  // namespace
+}  // namespace mccnn
+
+using namespace mccnn;
+
+extern "C" size_t mccnn_sgm_workspace_bytes(int H, int W, int D) {
+    (void)H; (void)W; (void)D;
+    return 256;  // 8 scanline counters
+}
+
+extern "C" int mccnn_sgm(const float* CL, const float* CR, const uint8_t* imageL, const uint8_t* imageR, float* SL,
+                         float* SR, float* dispL, float* dispR, void* workspace, size_t workspace_bytes, int H, int W,
+                         int D, const mccnn_sgm_params* params, int mode, int keep_volumes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (int e = check_common(CL, H, W, D)) return e;
+    MCCNN_REQUIRE(CR && SL && SR && imageL && imageR && dispL && dispR && params && workspace, MCCNN_EINVAL,
+                  "mccnn_sgm: null argument");
+    MCCNN_REQUIRE(mode == MCCNN_SGM_EXACT, MCCNN_EINVAL, "mccnn_sgm: unknown mode %d", mode);
+    MCCNN_REQUIRE(workspace_bytes >= mccnn_sgm_workspace_bytes(H, W, D), MCCNN_EWORKSPACE, "mccnn_sgm: workspace too small");
+    MCCNN_REQUIRE(aligned16(CL) && aligned16(CR) && aligned16(SL) && aligned16(SR), MCCNN_EALIGN,
+                  "mccnn_sgm: volumes must be 16-byte aligned");
+    MCCNN_REQUIRE(params->P1 >= 0 && params->P1_red >= 0, MCCNN_EINVAL, "mccnn_sgm: negative P1");
+
+    unsigned* counters = reinterpret_cast<unsigned*>(workspace);
+    MCCNN_CUDA(cudaMemsetAsync(counters, 0, 256, stream));
+
+    SgmArgs a{};
+    a.C[0] = CL; a.C[1] = CR;
+    a.S[0] = SL; a.S[1] = SR;
+    a.img[0] = imageL; a.img[1] = imageR;
+    a.disp[0] = dispL; a.disp[1] = dispR;
+    a.H = H; a.W = W; a.D = D; a.Dp = disp_pitch(D);
+    a.nsides = 2;
+    a.store_s = 1;
+    set_params(a, params);
+
+    // pass 0: down path fused with the up path's raw-cost add (paths 0 and 1); writes S without reading it
+    set_path(a, 0);
+    a.nsteps_total = H;
+    a.counter = counters + 0;
+    if (int e = dispatch_scan<SGM_FIRST_FUSED>(a, stream)) return e;
+    // passes 1..5: right, left, down-right, up-right, down-left
+    for (int path = 2; path <= 6; path++) {
+        set_path(a, path);
+        a.counter = counters + (path - 1);
+        if (int e = dispatch_scan<SGM_MID>(a, stream)) return e;
+    }
+    // pass 6: up-left + winner-takes-all; also visits row 0, which the path skips
+    set_path(a, 7);
+    a.nsteps_total = H;
+    a.store_s = keep_volumes ? 1 : 0;
+    a.counter = counters + 6;
+    return dispatch_scan<SGM_LAST_WTA>(a, stream);
+}
+
+extern "C" int mccnn_sgm_single_path(const float* C, const uint8_t* image, float* S, void* workspace,
+                                     size_t workspace_bytes, int H, int W, int D, const mccnn_sgm_params* params,
+                                     int path, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (int e = check_common(C, H, W, D)) return e;
+    MCCNN_REQUIRE(S && image && params && workspace, MCCNN_EINVAL, "mccnn_sgm_single_path: null argument");
+    MCCNN_REQUIRE(path >= 0 && path < 8, MCCNN_EINVAL, "mccnn_sgm_single_path: path %d outside 0..7", path);
+    MCCNN_REQUIRE(workspace_bytes >= 4, MCCNN_EWORKSPACE, "mccnn_sgm_single_path: workspace too small");
+    MCCNN_REQUIRE(aligned16(C) && aligned16(S), MCCNN_EALIGN, "mccnn_sgm_single_path: volumes must be 16-byte aligned");
+    unsigned* counter = reinterpret_cast<unsigned*>(workspace);
+    MCCNN_CUDA(cudaMemsetAsync(counter, 0, 4, stream));
+    SgmArgs a{};
+    a.C[0] = C; a.S[0] = S; a.img[0] = image; a.disp[0] = nullptr;
+    a.C[1] = C; a.S[1] = S; a.img[1] = image; a.disp[1] = nullptr;
+    a.H = H; a.W = W; a.D = D; a.Dp = disp_pitch(D);
+    a.nsides = 1;
+    a.store_s = 1;
+    set_params(a, params);
+    if (path == 1) {  // penalty channels 0/1 are never written by the reference: P1 = P2 = 0
+        a.P1 = a.P2 = a.P1r = a.P2r = 0.0;
+    }
+    set_path(a, path);
+    a.counter = counter;
+    return dispatch_scan<SGM_MID>(a, stream);
+}

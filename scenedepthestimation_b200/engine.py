@@ -1,0 +1,242 @@
+"""Device-side plumbing above the C ABI: torch tensors for memory and streams, nothing else.
+
+Every function here takes/returns CUDA torch tensors and forwards raw pointers to
+libmccnn_b200.so. The reference-shaped NumPy API lives in process_functional.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+FEATURES = 64
+EXACT = 0  # MCCNN_SGM_EXACT
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("scenedepthestimation_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def disp_pitch(D: int) -> int:
+    return _lib.load().mccnn_disp_pitch(int(D))
+
+
+def _dev(x, dtype) -> torch.Tensor:
+    """numpy / torch -> contiguous CUDA tensor of dtype."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    return x.to(device="cuda", dtype=dtype, non_blocking=True).contiguous()
+
+
+class Workspace:
+    """Caller-owned scratch memory, cached by size (the C ABI never allocates)."""
+
+    def __init__(self):
+        self._buf = None
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        if self._buf is None or self._buf.numel() < nbytes:
+            self._buf = None
+            self._buf = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
+        return self._buf
+
+
+_ws = Workspace()
+
+
+# ------------------------------------------------------------------------------ weights
+def pack_weights(weights: dict, num_layers: int = 5) -> torch.Tensor:
+    """Reference dict {'conv{i}/weights:0': HWIO, 'conv{i}/biases:0'} (mc_cnn_brunch.py:61-66) -> device blob."""
+    _require_cuda()
+    lib = _lib.load()
+    ws, bs = [], []
+    for i in range(1, num_layers + 1):
+        w = np.ascontiguousarray(weights[f"conv{i}/weights:0"], dtype=np.float32)
+        b = np.ascontiguousarray(weights[f"conv{i}/biases:0"], dtype=np.float32)
+        cin = 1 if i == 1 else FEATURES
+        if w.shape != (3, 3, cin, FEATURES) or b.shape != (FEATURES,):
+            raise ValueError(f"conv{i}: expected weights (3,3,{cin},{FEATURES}) and biases ({FEATURES},), got {w.shape} {b.shape}")
+        ws.append(w)
+        bs.append(b)
+    nbytes = lib.mccnn_conv_packed_weight_bytes(num_layers)
+    host = np.zeros(nbytes, np.uint8)
+    wp = (C.c_void_p * num_layers)(*[w.ctypes.data for w in ws])
+    bp = (C.c_void_p * num_layers)(*[b.ctypes.data for b in bs])
+    _lib.check(lib.mccnn_pack_weights_host(wp, bp, num_layers, host.ctypes.data), "mccnn_pack_weights_host")
+    return torch.from_numpy(host).cuda()
+
+
+# ------------------------------------------------------------------------------ stages
+def standardize_pad(image_u8: torch.Tensor, pad: int) -> torch.Tensor:
+    H, W = image_u8.shape
+    out = torch.empty((H + 2 * pad, W + 2 * pad), dtype=torch.float32, device="cuda")
+    scratch = torch.empty(4, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().mccnn_standardize_pad(_p(image_u8), _p(out), _p(scratch), H, W, pad, _stream()), "mccnn_standardize_pad")
+    return out
+
+
+def pad_f32(image: torch.Tensor, pad: int) -> torch.Tensor:
+    H, W = image.shape
+    out = torch.empty((H + 2 * pad, W + 2 * pad), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().mccnn_pad_f32(_p(image), _p(out), H, W, pad, _stream()), "mccnn_pad_f32")
+    return out
+
+
+def conv_tower(padded: torch.Tensor, packed: torch.Tensor, num_layers: int = 5) -> torch.Tensor:
+    lib = _lib.load()
+    Hp, Wp = padded.shape
+    H, W = Hp - 2 * num_layers, Wp - 2 * num_layers
+    feat = torch.empty((H, W, FEATURES), dtype=torch.float32, device="cuda")
+    nws = lib.mccnn_conv_workspace_bytes(H, W, num_layers)
+    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mccnn_conv_tower(_p(padded), _p(packed), _p(feat), _p(ws), nws, H, W, num_layers, _stream()), "mccnn_conv_tower")
+    return feat
+
+
+def cost_volume(fl: torch.Tensor, fr: torch.Tensor, D: int, fill: float = 1.0, right: bool = True):
+    H, W, F = fl.shape
+    assert F == FEATURES and fr.shape == fl.shape
+    Dp = disp_pitch(D)
+    CL = torch.empty((H, W, Dp), dtype=torch.float32, device="cuda")
+    CR = torch.empty((H, W, Dp), dtype=torch.float32, device="cuda") if right else None
+    _lib.check(_lib.load().mccnn_cost_volume(_p(fl), _p(fr), _p(CL), _p(CR), H, W, D, float(fill), _stream()), "mccnn_cost_volume")
+    return CL, CR
+
+
+def volume_to_dhw(vol: torch.Tensor, D: int) -> torch.Tensor:
+    H, W, _ = vol.shape
+    out = torch.empty((D, H, W), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().mccnn_volume_to_dhw(_p(vol), _p(out), H, W, D, _stream()), "mccnn_volume_to_dhw")
+    return out
+
+
+def sgm(CL, CR, imageL, imageR, D: int, params=None, keep_volumes: bool = True):
+    """8-path SGM + fused WTA. Returns (SL, SR, dispL, dispR)."""
+    lib = _lib.load()
+    H, W, Dp = CL.shape
+    params = params or _lib.default_sgm_params()
+    SL, SR = torch.empty_like(CL), torch.empty_like(CR)
+    dl = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    dr = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    nws = lib.mccnn_sgm_workspace_bytes(H, W, D)
+    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mccnn_sgm(_p(CL), _p(CR), _p(imageL), _p(imageR), _p(SL), _p(SR), _p(dl), _p(dr), _p(ws), nws,
+                             H, W, D, C.byref(params), EXACT, 1 if keep_volumes else 0, _stream()), "mccnn_sgm")
+    return SL, SR, dl, dr
+
+
+def sgm_single_path(Cv, image, S, D: int, path: int, params=None):
+    lib = _lib.load()
+    H, W, _ = Cv.shape
+    params = params or _lib.default_sgm_params()
+    ws = torch.empty(256, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mccnn_sgm_single_path(_p(Cv), _p(image), _p(S), _p(ws), 256, H, W, D, C.byref(params), path, _stream()),
+               "mccnn_sgm_single_path")
+    return S
+
+
+def wta(S: torch.Tensor, D: int) -> torch.Tensor:
+    H, W, _ = S.shape
+    out = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().mccnn_wta(_p(S), _p(out), H, W, D, _stream()), "mccnn_wta")
+    return out
+
+
+def wta_dhw(vol: torch.Tensor) -> torch.Tensor:
+    D, H, W = vol.shape
+    out = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().mccnn_wta_dhw(_p(vol), _p(out), H, W, D, _stream()), "mccnn_wta_dhw")
+    return out
+
+
+def lr_flags(dl, dr, right: bool = True):
+    H, W = dl.shape
+    fl = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+    fr = torch.empty((H, W), dtype=torch.uint8, device="cuda") if right else None
+    _lib.check(_lib.load().mccnn_lr_flags(_p(dl), _p(dr), _p(fl), _p(fr), H, W, _stream()), "mccnn_lr_flags")
+    return fl, fr
+
+
+def lrc_fill(dl, flag_l):
+    H, W = dl.shape
+    out = torch.empty_like(dl)
+    _lib.check(_lib.load().mccnn_lrc_fill(_p(dl), _p(flag_l), _p(out), H, W, _stream()), "mccnn_lrc_fill")
+    return out
+
+
+def median5(filled, wta_map):
+    H, W = filled.shape
+    out = torch.empty_like(filled)
+    _lib.check(_lib.load().mccnn_median5(_p(filled), _p(wta_map), _p(out), H, W, _stream()), "mccnn_median5")
+    return out
+
+
+def bilateral9(image_u8, disp):
+    H, W = disp.shape
+    out = torch.empty_like(disp)
+    _lib.check(_lib.load().mccnn_bilateral9(_p(image_u8), _p(disp), _p(out), H, W, _stream()), "mccnn_bilateral9")
+    return out
+
+
+def encode_u8(disp, scale: int = 1):
+    H, W = disp.shape
+    out = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.load().mccnn_encode_u8(_p(disp), _p(out), H, W, int(scale), _stream()), "mccnn_encode_u8")
+    return out
+
+
+def bad_pixels(disp_u8, gt_half):
+    H, W = disp_u8.shape
+    counts = torch.empty(2, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.load().mccnn_bad_pixels(_p(disp_u8), _p(gt_half), _p(counts), H, W, _stream()), "mccnn_bad_pixels")
+    bad, valid = counts.tolist()
+    return bad, valid
+
+
+# ------------------------------------------------------------------------------ whole path
+def disparity_pipeline(imageL, imageR, fl, fr, D: int, params=None, stage_ms: np.ndarray | None = None,
+                       out=None, workspace: torch.Tensor | None = None):
+    """mccnn_disparity_pipeline on device tensors -> (dispL filtered, dispR raw WTA)."""
+    lib = _lib.load()
+    H, W = imageL.shape
+    params = params or _lib.default_sgm_params()
+    nws = lib.mccnn_pipeline_workspace_bytes(H, W, D)
+    ws = workspace if workspace is not None else _ws.get(nws)
+    dl, dr = out if out is not None else (torch.empty((H, W), dtype=torch.float32, device="cuda"),
+                                          torch.empty((H, W), dtype=torch.float32, device="cuda"))
+    sm = stage_ms.ctypes.data if stage_ms is not None else None
+    _lib.check(lib.mccnn_disparity_pipeline(_p(imageL), _p(imageR), _p(fl), _p(fr), _p(dl), _p(dr), _p(ws), ws.numel(),
+                                            H, W, D, C.byref(params), EXACT, sm, _stream()), "mccnn_disparity_pipeline")
+    return dl, dr
+
+
+def match_workspace_bytes(H: int, W: int, D: int, num_layers: int = 5) -> int:
+    return _lib.load().mccnn_match_workspace_bytes(H, W, D, num_layers)
+
+
+def match_pair(imageL, imageR, packed, D: int, num_layers: int = 5, params=None, stage_ms: np.ndarray | None = None,
+               out=None, workspace: torch.Tensor | None = None):
+    """mccnn_match_pair on device u8 images -> (dispL filtered, dispR raw WTA)."""
+    lib = _lib.load()
+    H, W = imageL.shape
+    params = params or _lib.default_sgm_params()
+    nws = lib.mccnn_match_workspace_bytes(H, W, D, num_layers)
+    ws = workspace if workspace is not None else _ws.get(nws)
+    dl, dr = out if out is not None else (torch.empty((H, W), dtype=torch.float32, device="cuda"),
+                                          torch.empty((H, W), dtype=torch.float32, device="cuda"))
+    sm = stage_ms.ctypes.data if stage_ms is not None else None
+    _lib.check(lib.mccnn_match_pair(_p(imageL), _p(imageR), _p(packed), _p(dl), _p(dr), _p(ws), ws.numel(), H, W, D,
+                                    num_layers, C.byref(params), EXACT, sm, _stream()), "mccnn_match_pair")
+    return dl, dr

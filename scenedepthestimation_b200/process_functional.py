@@ -1,0 +1,116 @@
+"""Drop-in for the reference's process_functional.py (same names, arguments and returns).
+
+NumPy in / NumPy out, like the reference; everything between runs on the B200 through the
+C ABI (engine.py -> libmccnn_b200.so). Differences a caller can see:
+  * `checkpoint` is the reference's .npy weight dict (Net.save_weights_dict, mc_cnn_brunch.py:61-66)
+    or such a dict; a TF1 .ckpt cannot be read without TensorFlow and raises;
+  * the disparity count is a parameter (`ndisp`, default 128 = the reference's hard-coded range,
+    process_functional.py:125) instead of a constant;
+  * the device is the current torch CUDA device, not the reference's cuda.select_device(1) (:1095);
+  * the returned right map is the raw right WTA map (the reference returns the median of an
+    uninitialised buffer there, App. A6);
+  * no per-disparity prints.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import engine as _e
+
+NDISP = 128  # process_functional.py:125
+
+_weights_cache: dict = {}
+
+
+def _load_weights(checkpoint, num_layers):
+    if isinstance(checkpoint, dict):
+        weights = checkpoint
+        key = ("dict", id(checkpoint), num_layers)
+    else:
+        path = os.fspath(checkpoint)
+        if not path.endswith(".npy"):
+            raise RuntimeError(
+                f"checkpoint {path!r}: TensorFlow checkpoints cannot be read without TensorFlow; export the weights with "
+                "Net.save_weights_dict (mc_cnn_brunch.py:61-66) and pass the .npy file (or the dict itself)")
+        key = ("file", path, os.path.getmtime(path), num_layers)
+        weights = None
+    if key not in _weights_cache:
+        if weights is None:
+            weights = np.load(checkpoint, encoding="bytes", allow_pickle=True).item()
+            weights = {(k.decode() if isinstance(k, bytes) else k): v for k, v in weights.items()}
+        _weights_cache.clear()
+        _weights_cache[key] = _e.pack_weights(weights, num_layers)
+    return _weights_cache[key]
+
+
+def compute_feature(left_image, right_image, patch_height, patch_width, num_of_feature_maps, checkpoint):
+    """process_functional.py:11-45: [H,W,1] standardised f32 images -> two [H,W,64] f32 feature maps."""
+    _e._require_cuda()
+    if patch_height != patch_width or patch_height % 2 == 0:
+        raise ValueError("square odd patches only (the tower has patch//2 3x3 layers)")
+    if num_of_feature_maps != _e.FEATURES:
+        raise ValueError(f"num_of_feature_maps must be {_e.FEATURES}")
+    nl = patch_height // 2
+    packed = _load_weights(checkpoint, nl)
+    height, width = left_image.shape[0:2]
+    out = []
+    for img in (left_image, right_image):
+        d = _e._dev(np.asarray(img, dtype=np.float32).reshape(height, width), torch.float32)
+        out.append(_e.conv_tower(_e.pad_f32(d, (patch_height - 1) // 2), packed, nl).cpu().numpy())
+    return out[0], out[1]
+
+
+def compute_cost_volume(featuresl, featuresr, ndisp):
+    """process_functional.py:48-73 (the reference's CPU path): -> f32 [ndisp,H,W], invalid entries 0 (negated)."""
+    _e._require_cuda()
+    fl, fr = _e._dev(featuresl, torch.float32), _e._dev(featuresr, torch.float32)
+    cl, _ = _e.cost_volume(fl, fr, int(ndisp), fill=-0.0, right=False)
+    return _e.volume_to_dhw(cl, int(ndisp)).cpu().numpy()
+
+
+def WTA(left_cost_volume):
+    """process_functional.py:76-93: argmin over the last axis of [H,W,D]."""
+    _e._require_cuda()
+    vol = np.asarray(left_cost_volume, dtype=np.float32)
+    H, W, D = vol.shape
+    Dp = _e.disp_pitch(D)
+    dev = torch.zeros((H, W, Dp), dtype=torch.float32, device="cuda")
+    dev[:, :, :D] = _e._dev(vol, torch.float32)
+    return _e.wta(dev, D).cpu().numpy()
+
+
+def WTA1(left_cost_volume):
+    """process_functional.py:96-113: argmin over the first axis of [D,H,W]."""
+    _e._require_cuda()
+    return _e.wta_dhw(_e._dev(left_cost_volume, torch.float32)).cpu().numpy()
+
+
+def disparity_compute_by_gpu(imagel, imager, featuresl, featuresr, detail_time, ndisp=None):
+    """process_functional.py:1093-1267: u8 images + features -> (left disparity, right disparity, detail_time)."""
+    _e._require_cuda()
+    assert imagel.shape == imager.shape
+    D = int(NDISP if ndisp is None else ndisp)
+    il, ir = _e._dev(imagel, torch.uint8), _e._dev(imager, torch.uint8)
+    fl, fr = _e._dev(featuresl, torch.float32), _e._dev(featuresr, torch.float32)
+    stage = np.zeros(7, np.float32)
+    dl, dr = _e.disparity_pipeline(il, ir, fl, fr, D, stage_ms=stage)
+    if detail_time is not None:
+        detail_time += (stage / 1000.0).astype(detail_time.dtype)  # the reference accumulates seconds
+    return dl.cpu().numpy(), dr.cpu().numpy(), detail_time
+
+
+def match_pair(left_u8, right_u8, checkpoint, ndisp=None, patch=11, detail_time=None):
+    """Fused match_single.py:34-55: u8 pair -> (left disparity f32, right raw WTA f32), one C call."""
+    _e._require_cuda()
+    D = int(NDISP if ndisp is None else ndisp)
+    nl = patch // 2
+    packed = _load_weights(checkpoint, nl)
+    il, ir = _e._dev(left_u8, torch.uint8), _e._dev(right_u8, torch.uint8)
+    stage = np.zeros(7, np.float32) if detail_time is not None else None
+    dl, dr = _e.match_pair(il, ir, packed, D, nl, stage_ms=stage)
+    if detail_time is not None:
+        detail_time += (stage / 1000.0).astype(detail_time.dtype)
+    return dl.cpu().numpy(), dr.cpu().numpy()

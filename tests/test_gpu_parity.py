@@ -1,0 +1,204 @@
+"""GPU parity tests: every CUDA stage, called through the C ABI, against (a) the golden vectors
+produced by the reference's own Numba kernels on a B200 and (b) the CPU oracle on seeded inputs.
+
+Bars (north_star): integer / index outputs bit-exact; the exact-arithmetic stages (cost volume with
+fp64 accumulation, fp64-state SGM with per-path fp32 rounding) are compared bit for bit as well; the
+conv tower (whose arithmetic the reference delegates to TensorFlow/cuDNN) within 2e-6 absolute on
+unit-norm features.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*x*.npz")))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from scenedepthestimation_b200 import _lib, engine
+
+    assert _lib.load().mccnn_device_supported(torch.cuda.current_device()) == 1, _lib.load().mccnn_last_error()
+    return engine
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def unpitch(t, D):
+    return t[..., :D].contiguous().cpu().numpy()
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_stages_match_reference_kernels(eng, path):
+    """Stage by stage against the reference kernels' own outputs (D = 128)."""
+    g = np.load(path)
+    D = 128
+    il, ir = dev(g["imagel"]), dev(g["imager"])
+    CL, CR = eng.cost_volume(dev(g["fl"]), dev(g["fr"]), D)
+    assert np.array_equal(unpitch(CL, D), g["CL"])
+    assert np.array_equal(unpitch(CR, D), g["CR"])
+    SL, SR, dl, dr = eng.sgm(CL, CR, il, ir, D, keep_volumes=True)
+    assert np.array_equal(unpitch(SL, D), g["SL"])
+    assert np.array_equal(unpitch(SR, D), g["SR"])
+    assert np.array_equal(dl.cpu().numpy(), g["dl_wta"])
+    assert np.array_equal(dr.cpu().numpy(), g["dr_wta"])
+    assert np.array_equal(eng.wta(SL, D).cpu().numpy(), g["dl_wta"])
+    fl_, fr_ = eng.lr_flags(dl, dr)
+    assert np.array_equal(fl_.cpu().numpy(), g["flag_l"])
+    assert np.array_equal(fr_.cpu().numpy(), g["flag_r"])
+    filled = eng.lrc_fill(dl, fl_)
+    assert np.array_equal(filled.cpu().numpy(), g["dl_fill"])
+    assert np.array_equal(eng.median5(filled, dl).cpu().numpy(), g["dl_final"])
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_pipeline_matches_reference_e2e(eng, path):
+    """disparity_compute_by_gpu drop-in (host arrays in and out) == the reference's returned left map."""
+    from scenedepthestimation_b200 import process_functional as pf
+
+    g = np.load(path)
+    dt = np.zeros(7, np.float32)
+    dl, dr, dt = pf.disparity_compute_by_gpu(g["imagel"], g["imager"], g["fl"], g["fr"], dt)
+    assert np.array_equal(dl, g["dl_e2e"])
+    assert np.array_equal(dr, g["dr_wta"])
+    assert dt[1] > 0 and dt[3] > 0
+
+
+def test_single_paths_match_reference_order(eng):
+    """Each of the 8 path kernels, launch for launch (S after path i, both volumes)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_tiny_6x10.npz"))
+    D = 128
+    CL, CR = eng.cost_volume(dev(g["fl"]), dev(g["fr"]), D)
+    for C, img, tag in ((CL, dev(g["imagel"]), "SL"), (CR, dev(g["imager"]), "SR")):
+        S = torch.zeros_like(C)
+        for p in range(8):
+            eng.sgm_single_path(C, img, S, D, p)
+            assert np.array_equal(unpitch(S, D), g[f"{tag}_after{p + 1}"]), (tag, p)
+
+
+@pytest.mark.parametrize("H,W,D,kind", [
+    (11, 37, 80, "tex"),      # c1's D, 3 disparities per lane with idle lanes
+    (9, 45, 128, "noise"),
+    (8, 70, 228, "tex"),      # c5's D (not a multiple of 32)
+    (7, 130, 400, "tex"),     # c3's D, D > W on part of the image
+    (6, 90, 800, "noise"),    # c4's D, D > W everywhere
+    (23, 9, 20, "noise"),     # tall: diagonal paths wrap several times
+    (5, 33, 1, "tex"), (4, 40, 3, "noise"), (6, 21, 33, "tex"), (5, 50, 1000, "noise"),
+])
+def test_pipeline_vs_oracle_generic_D(eng, H, W, D, kind):
+    """Any disparity count: all stages bit-exact against the CPU oracle."""
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import synthetic as syn
+
+    seed = H * 1000 + W + D
+    if kind == "tex":
+        il, ir, _ = syn.textured_pair(H, W, D, seed)
+        fl, fr, _ = syn.correlated_features(H, W, D, 64, seed)
+    else:
+        il, ir = syn.noise_pair(H, W, seed)
+        fl, fr = syn.unit_features(H, W, 64, seed)
+    final, dr_o, k = st.disparity_pipeline(il, ir, fl, fr, D, keep=True)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    assert np.array_equal(unpitch(CL, D), k["CL"]) and np.array_equal(unpitch(CR, D), k["CR"])
+    SL, SR, dl, dr = eng.sgm(CL, CR, dev(il), dev(ir), D, keep_volumes=True)
+    assert np.array_equal(unpitch(SL, D), k["SL"]) and np.array_equal(unpitch(SR, D), k["SR"])
+    assert np.array_equal(dl.cpu().numpy(), k["dl_wta"]) and np.array_equal(dr.cpu().numpy(), k["dr_wta"])
+    out_l, out_r = eng.disparity_pipeline(dev(il), dev(ir), dev(fl), dev(fr), D)
+    assert np.array_equal(out_l.cpu().numpy(), final)
+    assert np.array_equal(out_r.cpu().numpy(), dr_o)
+
+
+def test_conv_tower_vs_oracle(eng):
+    from oracle import conv_tower as ct
+    from scenedepthestimation_b200 import synthetic as syn
+
+    H, W = 37, 53
+    il, _, _ = syn.textured_pair(H, W, 16, 5)
+    w = syn.glorot_weights()
+    std = syn.standardise(il)
+    padded = ct.pad_image(std)
+    ref64 = ct.conv_tower(padded, w, 5, torch.float64)
+    ref32 = ct.conv_tower(padded, w, 5, torch.float32)
+    packed = eng.pack_weights(w, 5)
+    got = eng.conv_tower(eng.pad_f32(dev(std[:, :, 0]), 5), packed, 5).cpu().numpy()
+    err = np.abs(got - ref64).max()
+    err32 = np.abs(ref32 - ref64).max()
+    assert err <= 2e-6, (err, err32)
+    np.testing.assert_allclose(np.sum(got.astype(np.float64) ** 2, -1), 1.0, atol=1e-5)
+    # fused standardise + pad from u8 (integer-exact statistics) stays within the same tolerance
+    got2 = eng.conv_tower(eng.standardize_pad(dev(il), 5), packed, 5).cpu().numpy()
+    assert np.abs(got2 - ref64).max() <= 5e-6
+
+
+def test_match_pair_end_to_end(eng):
+    """u8 images -> disparity through ONE C call; compared with the oracle run on the GPU's own features
+    (bit-exact) and with the all-CPU oracle (identical except at near-ties caused by 1e-6 feature noise)."""
+    from oracle import conv_tower as ct
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import process_functional as pf
+    from scenedepthestimation_b200 import synthetic as syn
+
+    H, W, D = 40, 96, 48
+    il, ir, gt = syn.textured_pair(H, W, D, 11)
+    w = syn.glorot_weights()
+    dl, dr = pf.match_pair(il, ir, w, ndisp=D)
+    packed = eng.pack_weights(w, 5)
+    fl = eng.conv_tower(eng.standardize_pad(dev(il), 5), packed, 5).cpu().numpy()
+    fr = eng.conv_tower(eng.standardize_pad(dev(ir), 5), packed, 5).cpu().numpy()
+    exp, exp_r = st.disparity_pipeline(il, ir, fl, fr, D)
+    assert np.array_equal(dl, exp) and np.array_equal(dr, exp_r)
+    flc, frc = ct.compute_feature(syn.standardise(il), syn.standardise(ir), 11, 11, 64, w)
+    cpu, _ = st.disparity_pipeline(il, ir, flc, frc, D)
+    assert np.mean(cpu != dl) < 0.01
+
+
+def test_cpu_path_dropins(eng):
+    """compute_cost_volume / WTA / WTA1 drop-ins vs the reference's NumPy CPU path (:48-113)."""
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import process_functional as pf
+    from scenedepthestimation_b200 import synthetic as syn
+
+    fl, fr, _ = syn.correlated_features(12, 60, 24, 64, 3)
+    vol = pf.compute_cost_volume(fl, fr, 24)
+    ref = st.cost_volume_cpu_reference(fl, fr, 24)
+    np.testing.assert_allclose(vol, ref, rtol=0, atol=2e-6)
+    assert np.array_equal(pf.WTA1(ref), st.wta_dhw(ref))
+    hwd = np.ascontiguousarray(np.transpose(ref, (1, 2, 0)))
+    assert np.array_equal(pf.WTA(hwd), st.wta(hwd))
+
+
+def test_bilateral_encode_and_metric(eng):
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import synthetic as syn
+
+    il, _, gt = syn.textured_pair(30, 44, 64, 9)
+    rng = np.random.default_rng(0)
+    disp = rng.integers(0, 300, (30, 44)).astype(np.float32)
+    got = eng.bilateral9(dev(il), dev(disp)).cpu().numpy()
+    assert np.array_equal(got, st.bilateral9(il, disp))
+    enc = eng.encode_u8(dev(disp), 2).cpu().numpy()
+    assert np.array_equal(enc, (disp.astype("uint8") * 2).astype("uint8"))
+    u8 = disp.astype("uint8")
+    full = (gt * 2).astype(np.float32)
+    full[3, 4] = np.inf
+    full[5, 6] = 0.0
+    bad, valid = eng.bad_pixels(dev(u8), dev((full / 2).astype(np.float32)))
+    assert bad / (30 * 44) == st.bad_pixel_rate(u8, full, resize=False)
+
+
+def test_errors_are_loud(eng):
+    from scenedepthestimation_b200 import _lib
+
+    t = torch.zeros((2, 2, 4), device="cuda")
+    with pytest.raises(RuntimeError):
+        eng.sgm(t, t, torch.zeros((2, 2), dtype=torch.uint8, device="cuda"), torch.zeros((2, 2), dtype=torch.uint8, device="cuda"), 4)
+    assert b"too small" in _lib.load().mccnn_last_error()
