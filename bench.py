@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""Benchmark of the MC-CNN stereo hot path (BASELINE.json metric: full-resolution Middlebury-2014-shaped
+pairs/sec and Gdisp-evals/s on B200, next to the reference's CPU path on the box's own host cores).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference, host cores
+
+A step = one pass of the whole hot path (standardise, conv tower x2, cost volume, 8-path SGM, WTA, L-R
+check + fill, median) over one synthetic stereo pair of config c4 (2880x1988, 800 disparities,
+random-init weights). With N > 1 every rank processes its own pair (pairs are independent units: weak
+scaling, no data-path collective). Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KERNELS_PER_STEP = 2 * 2 + 2 * 5 + 1 + 7 + 3  # standardise(2x2) + conv(2x5) + cost volume + SGM passes + lr/fill/median
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c4", help="c1..c5 (SURVEY.md App. B); the metric is quoted on c4")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------- helpers
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_pair(cfg: str, seed: int):
+    from scenedepthestimation_b200 import synthetic as syn
+
+    W, H, D = syn.CONFIGS[cfg]
+    il, ir, gt = syn.textured_pair(H, W, D, seed)
+    return il, ir, gt, (W, H, D)
+
+
+# ----------------------------------------------------------------------------------------- CPU legs
+def cpu_hot_path_band(il, ir, weights, D, rows, threads):
+    """The oracle (CPU restatement of the reference) on a horizontal band of `rows` rows of the pair:
+    conv tower (torch CPU fp32, standing in for TensorFlow) + cost volume + SGM + WTA + L-R + median."""
+    import torch
+
+    from oracle import conv_tower as ct
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import synthetic as syn
+
+    torch.set_num_threads(threads)
+    H = il.shape[0]
+    r0 = max(0, (H - rows) // 2)
+    bl, br = np.ascontiguousarray(il[r0:r0 + rows]), np.ascontiguousarray(ir[r0:r0 + rows])
+    t0 = time.perf_counter()
+    fl, fr = ct.compute_feature(syn.standardise(bl), syn.standardise(br), 11, 11, 64, weights)
+    st.disparity_pipeline(bl, br, fl, fr, D)
+    return time.perf_counter() - t0
+
+
+def cpu_sample(il, ir, weights, D, target_s, threads):
+    """Pick a band height that costs about target_s seconds, run it, return (pairs/s equivalent, description)."""
+    import numba
+
+    numba.set_num_threads(threads)
+    H, W = il.shape
+    cpu_hot_path_band(il[:, :64], ir[:, :64], weights, min(D, 16), 4, threads)  # JIT warm-up, not timed
+    probe_rows = 4
+    t = cpu_hot_path_band(il, ir, weights, D, probe_rows, threads)
+    rows = int(max(probe_rows, min(H, probe_rows * target_s / max(t, 1e-3))))
+    t = cpu_hot_path_band(il, ir, weights, D, rows, threads)
+    pairs_per_s = (rows / H) / t
+    return pairs_per_s, t, f"{rows} of {H} rows x {W} px x {D} disparities of the same pair (whole hot path), {t:.1f} s"
+
+
+# ----------------------------------------------------------------------------------------- main
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    threads = len(os.sched_getaffinity(0))
+    from scenedepthestimation_b200 import synthetic as syn
+
+    W, H, D = syn.CONFIGS[a.config]
+    evals = H * W * D
+    config = {"workload": f"{a.config}: synthetic Middlebury-2014-shaped full-res pair {W}x{H}, {D} disparities, MC-CNN-fast "
+                          "(5x 3x3 conv, 64 maps, random-init) + 8-path SGM + WTA + L-R check/fill + 5x5 median",
+              "pairs_per_step_per_gpu": 1, "parallelism": f"pair-per-rank x{world}",
+              "l2": "per-step working set (4 fp32 volumes, 73 GB) exceeds the 126 MB L2 by >500x; no flush needed",
+              "arithmetic": "reference-exact (fp64 SGM state and cost accumulator, fp32 S rounded per path in reference order)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        il, ir, _, _ = make_pair(a.config, 1000 + 4)
+        weights = syn.glorot_weights()
+        import numba
+
+        numba.set_num_threads(threads)
+        cpu_hot_path_band(il[:, :64], ir[:, :64], weights, min(D, 16), 4, threads)
+        t = cpu_hot_path_band(il, ir, weights, D, 4, threads)
+        per_step_s = max(2.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
+        rows = int(max(4, min(H, 4 * per_step_s / max(t, 1e-3))))
+        for _ in range(a.warmup):
+            cpu_hot_path_band(il, ir, weights, D, rows, threads)
+        ts = [cpu_hot_path_band(il, ir, weights, D, rows, threads) for _ in range(a.steps)]
+        tot = float(np.sum(ts))
+        v = (rows / H) * a.steps / tot
+        sample = f"each step = {rows} of {H} rows x {W} px x {D} disparities (whole hot path), scaled to pairs"
+        print(json.dumps({
+            "impl": "reference", "metric": "pairs_per_sec", "value": v, "unit": "pairs/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "gdisp_evals_per_sec": v * evals / 1e9,
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU restatement of the reference (njit-parallel oracle; torch CPU conv stands in for TensorFlow); "
+                    "the reference has no CPU implementation of SGM/L-R/median and cannot be imported without TensorFlow"}))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local % torch.cuda.device_count())
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    from scenedepthestimation_b200 import engine as eng
+
+    il, ir, _, _ = make_pair(a.config, 1000 + 4 + rank)
+    weights = syn.glorot_weights()
+    packed = eng.pack_weights(weights, 5)
+    d_il, d_ir = torch.from_numpy(il).cuda(), torch.from_numpy(ir).cuda()
+    ws = torch.empty(eng.match_workspace_bytes(H, W, D, 5), dtype=torch.uint8, device="cuda")
+    out = (torch.empty((H, W), device="cuda"), torch.empty((H, W), device="cuda"))
+
+    def step():
+        eng.match_pair(d_il, d_ir, packed, D, 5, out=out, workspace=ws)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, a.warmup)):
+        step()
+    sampler = ClockSampler(torch.cuda.current_device())
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    value = world * a.steps / (total_ms / 1e3)
+
+    # ---- end to end through the public host-buffer API: pinned host images in, host disparity out, every step
+    h_il, h_ir = torch.from_numpy(il).pin_memory(), torch.from_numpy(ir).pin_memory()
+    h_dl, h_dr = torch.empty((H, W), dtype=torch.float32).pin_memory(), torch.empty((H, W), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        dl_, dr_ = eng.match_pair(h_il.cuda(non_blocking=True), h_ir.cuda(non_blocking=True), packed, D, 5, out=out, workspace=ws)
+        h_dl.copy_(dl_, non_blocking=True)
+        h_dr.copy_(dr_, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller holds the result on the host
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * a.steps / float(e2e_s.item())
+
+    # ---- roofline of the dominant kernel (the SGM scanline kernel, 7 launches per pair), timed alone with
+    # CUDA events on the launching stream; algorithmic bytes per pair = 16 * H*W*D (both sides,
+    # read C once + write S once)
+    from scenedepthestimation_b200 import _lib
+    import ctypes as C
+
+    lib = _lib.load()
+    stage = np.zeros(7, np.float32)
+    reps = max(3, a.steps)
+    for _ in range(reps):
+        eng.match_pair(d_il, d_ir, packed, D, 5, stage_ms=stage, out=out, workspace=ws)
+    stage /= reps
+    sgm_launch_ms = float(stage[3]) / 7.0
+    peak, peak_src = load_peaks()
+    alg_bytes_launch = 16.0 * evals / 7.0
+    achieved = alg_bytes_launch / (sgm_launch_ms * 1e-3) / 1e9
+    roofline = {"kernel": "sgm_scan_kernel (7 launches per pair: down+up fused, right, left, 4 diagonals, last + WTA)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes_launch, "avg_launch_ms": sgm_launch_ms,
+                "stage_ms": {"features": float(stage[0]), "cost_volume": float(stage[1]), "sgm": float(stage[3]),
+                             "lr_check_fill": float(stage[5]), "median": float(stage[6])}}
+    tr = os.path.join(ROOT, "profiles", "sgm_traffic.json")
+    if os.path.exists(tr):
+        with open(tr) as f:
+            t = json.load(f)
+        roofline["traffic"] = t.get("dram_bytes_per_launch")
+        roofline["traffic_source"] = t.get("source")
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, t, desc = cpu_sample(il, ir, weights, D, a.cpu_seconds, threads)
+        cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(3, a.warmup), "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "gdisp_evals_per_sec": value * evals / 1e9,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * H * W, "d2h_bytes_per_step": 2 * H * W * 4,
+                    "api": "engine.match_pair (mccnn_match_pair) with pinned host u8 images in, host fp32 maps out"},
+            "gpu_launches": KERNELS_PER_STEP * a.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

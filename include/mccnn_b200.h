@@ -17,7 +17,8 @@
  *  - Return value: 0 on success, a positive cudaError_t, or a negative MCCNN_E* argument
  *    error. mccnn_last_error() returns a thread-local message. There is no CPU fallback.
  *  - Volumes are fp32 [H][W][Dp] with the disparity innermost and pitch
- *    Dp = mccnn_disp_pitch(D) (D rounded up to a multiple of 4; pad entries undefined).
+ *    Dp = mccnn_disp_pitch(D) (D rounded up to a multiple of 4). Pad entries [D, Dp) of a COST volume must
+ *    be +INF (mccnn_cost_volume writes them so; the SGM kernels rely on it); those of S volumes are undefined.
  *    Feature maps are fp32 [H][W][64]. Images are u8 [H][W]. Disparity maps are fp32 [H][W]
  *    holding integer values, as in the reference.
  */
@@ -87,6 +88,11 @@ int mccnn_pack_weights_host(const float* const* hwio_host, const float* const* b
 size_t mccnn_conv_workspace_bytes(int H, int W, int num_layers);
 int mccnn_conv_tower(const float* padded, const void* packed_weights, float* features,
                      void* workspace, size_t workspace_bytes, int H, int W, int num_layers, void* stream);
+/* Same contract on the CUDA cores in plain fp32 (exact fp32 products, fp32 accumulation): the numerically
+ * trusted twin of the tensor-core path above (which splits every operand into two fp16 numbers and
+ * accumulates in fp32 in TMEM); used to cross-check it on the device. */
+int mccnn_conv_tower_fp32(const float* padded, const void* packed_weights, float* features,
+                          void* workspace, size_t workspace_bytes, int H, int W, int num_layers, void* stream);
 
 /* ---- cost volume ---------------------------------------------------------------------------
  * Replaces compute_cost_volume_kernel (process_functional.py:120-131) and the host np.ones

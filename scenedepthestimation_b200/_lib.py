@@ -33,6 +33,7 @@ SIGNATURES = {
     "mccnn_pack_weights_host": (_i, [C.POINTER(_vp), C.POINTER(_vp), _i, _vp]),
     "mccnn_conv_workspace_bytes": (_sz, [_i, _i, _i]),
     "mccnn_conv_tower": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
+    "mccnn_conv_tower_fp32": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
     "mccnn_cost_volume": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "mccnn_volume_to_dhw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mccnn_sgm_workspace_bytes": (_sz, [_i, _i, _i]),

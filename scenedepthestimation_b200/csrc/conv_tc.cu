@@ -1,0 +1,385 @@
+// Conv tower layers 2..n as an implicit GEMM on the 5th-generation tensor cores (sm_100a):
+// tcgen05.mma with accumulators in TMEM, operands staged in shared memory by TMA.
+//
+// Replaces the tf.nn.conv2d + bias + relu / l2_normalize calls of conv() and Net.construct
+// (mc_cnn_brunch.py:38-48, 70-92) that compute_feature evaluates with sess.run
+// (process_functional.py:38-39).
+//
+// GEMM view of one 3x3 VALID layer, 64 -> 64 channels, activations NHWC:
+//   M = 128 consecutive output pixels of one image row, N = 64 output channels,
+//   K = 9 taps x 64 input channels. For tap (ky,kx) the A operand is the [128 pixels][64 channels]
+//   block starting at input pixel (y+ky, x0+kx): contiguous in memory, fetched by one TMA 2-D tile
+//   load into the 128-byte-swizzled K-major layout tcgen05 wants. B = the tap's [64 cout][64 cin]
+//   weights, resident in shared memory for the whole (persistent) CTA.
+//
+// Precision: the reference runs fp32 convolutions. Every operand is split into two fp16 numbers,
+// x = hi + lo / 2048 (22-bit significand, lo scaled so that it cannot underflow), and each k-step
+// issues three MMAs: hi*hi into one fp32 TMEM accumulator, hi*lo and lo*hi into a second one; the
+// epilogue forms main + corr / 2048. The dropped lo*lo term is 2^-22 relative. Activations travel
+// between layers as two fp16 NHWC tensors (same bytes as fp32).
+//
+// Warp roles (192 threads, one CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM
+// allocator, warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/split or l2-normalise -> global).
+// Two smem stages for A, two TMEM accumulator sets so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cstring>
+
+namespace mccnn {
+namespace {
+
+constexpr int NF = MCCNN_FEATURES;
+constexpr int TILE_M = 128;
+constexpr int A_TILE_BYTES = TILE_M * 128;  // 128 pixels x 64 fp16
+constexpr int B_TILE_BYTES = NF * 128;      // 64 cout x 64 fp16
+constexpr int W_TC_BYTES = 2 * 9 * B_TILE_BYTES;  // hi + lo, 9 taps
+constexpr int TC_STAGES = 2;
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES;  // hi + lo
+constexpr int SMEM_A_OFF = W_TC_BYTES;         // 147456, a multiple of 1024
+constexpr int SMEM_BAR_OFF = SMEM_A_OFF + TC_STAGES * STAGE_BYTES;
+constexpr int TC_SMEM_BYTES = SMEM_BAR_OFF + 128 + 1024;  // + barriers + alignment slack
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t IDESC_F16_M128_N64 = (1u << 4) | ((uint32_t)(NF >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_dst),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_addr(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC_F16_M128_N64), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void split_store(float v, __half& h, __half& l) {
+    h = __float2half_rn(v);
+    l = __float2half_rn((v - __half2float(h)) * 2048.0f);
+}
+
+// ---------------------------------------------------------------- layer 1 (1 -> 64) on CUDA cores, fp16 hi/lo output
+__global__ void __launch_bounds__(256) conv1_split_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                         const float* __restrict__ b, __half* __restrict__ out_hi,
+                                                         __half* __restrict__ out_lo, int Hin, int Win) {
+    __shared__ float ws[9 * NF];
+    __shared__ float bs[NF];
+    for (int i = threadIdx.x; i < 9 * NF; i += 256) ws[i] = w[i];
+    if (threadIdx.x < NF) bs[threadIdx.x] = b[threadIdx.x];
+    __syncthreads();
+    const int Hout = Hin - 2, Wout = Win - 2;
+    const size_t npix = (size_t)Hout * Wout;
+    const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t pix = gid >> 3;
+    const int q = (int)(gid & 7);  // 8 output channels per thread
+    if (pix >= npix) return;
+    const int y = (int)(pix / Wout), x = (int)(pix % Wout);
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) acc[c] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+            const float v = in[(size_t)(y + ky) * Win + x + kx];
+#pragma unroll
+            for (int c = 0; c < 8; c++) acc[c] = fmaf(v, ws[(ky * 3 + kx) * NF + 8 * q + c], acc[c]);
+        }
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) split_store(fmaxf(acc[c] + bs[8 * q + c], 0.f), hi[c], lo[c]);
+    *reinterpret_cast<uint4*>(&out_hi[pix * NF + 8 * q]) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(&out_lo[pix * NF + 8 * q]) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// ---------------------------------------------------------------- layers 2..n on tcgen05
+struct TcArgs {
+    const unsigned char* w_tc;  // [hi: 9 x 8 KB][lo: 9 x 8 KB], rows pre-swizzled (128B pattern)
+    const float* bias;
+    __half* out_hi;
+    __half* out_lo;
+    float* out_f32;
+    int Hin, Win;  // input activation size; output is (Hin-2) x (Win-2)
+    int tiles_per_row, ntiles;
+};
+
+template <bool LAST>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SMEM_BAR_OFF);
+    uint64_t* full = bars;                    // [TC_STAGES]
+    uint64_t* empty = bars + TC_STAGES;       // [TC_STAGES]
+    uint64_t* tfull = bars + 2 * TC_STAGES;   // [2]
+    uint64_t* tempty = bars + 2 * TC_STAGES + 2;  // [2]
+    uint64_t* wbar = bars + 2 * TC_STAGES + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        mbar_init(wbar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int Wout = a.Win - 2;
+
+    if (warp == 0) {
+        // ===== TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(wbar, W_TC_BYTES);
+            for (int i = 0; i < W_TC_BYTES / 16384; i++) bulk_g2s_addr(base + i * 16384, a.w_tc + (size_t)i * 16384, 16384, wbar);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                const int y = tile / a.tiles_per_row, x0 = (tile % a.tiles_per_row) * TILE_M;
+                for (int tap = 0; tap < 9; tap++, it++) {
+                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    const int pix = (y + tap / 3) * a.Win + x0 + tap % 3;
+                    const uint32_t dst = base + SMEM_A_OFF + s * STAGE_BYTES;
+                    tma_load_2d(dst, &tm_hi, 0, pix, &full[s]);
+                    tma_load_2d(dst + A_TILE_BYTES, &tm_lo, 0, pix, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread)
+        if (lane == 0) {
+            mbar_wait(wbar, 0);
+            uint32_t it = 0, tc = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tc++) {
+                const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
+                mbar_wait(&tempty[acc], aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_main = tmem_base + acc * 128u, d_corr = d_main + 64u;
+                for (int tap = 0; tap < 9; tap++, it++) {
+                    const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = base + SMEM_A_OFF + s * STAGE_BYTES;
+                    const uint64_t a_hi = sw128_desc(a_addr), a_lo = sw128_desc(a_addr + A_TILE_BYTES);
+                    const uint64_t b_hi = sw128_desc(base + tap * B_TILE_BYTES);
+                    const uint64_t b_lo = sw128_desc(base + 9 * B_TILE_BYTES + tap * B_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {  // UMMA_K = 16 fp16 = 32 bytes = 2 descriptor units
+                        const uint32_t first = (tap | k) != 0 ? 1u : 0u;
+                        umma_f16(d_main, a_hi + 2 * k, b_hi + 2 * k, first);
+                        umma_f16(d_corr, a_hi + 2 * k, b_lo + 2 * k, first);
+                        umma_f16(d_corr, a_lo + 2 * k, b_hi + 2 * k, 1u);
+                    }
+                    umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+                }
+                umma_commit(&tfull[acc]);  // accumulators of this tile are complete
+            }
+        }
+    } else {
+        // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        uint32_t tc = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tc++) {
+            const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
+            const int y = tile / a.tiles_per_row, x0 = (tile % a.tiles_per_row) * TILE_M;
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128u;
+            float v[NF];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float mn[16], cr[16];
+                tmem_ld16(taddr + c * 16, mn);
+                tmem_ld16(taddr + 64 + c * 16, cr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++) v[c * 16 + j] = fmaf(cr[j], 1.0f / 2048.0f, mn[j]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+
+            const int x = x0 + m;
+            if (x < Wout) {
+                const size_t o = ((size_t)y * Wout + x) * NF;
+                if (!LAST) {
+#pragma unroll
+                    for (int c8 = 0; c8 < NF / 8; c8++) {
+                        __align__(16) __half hi[8], lo[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) split_store(fmaxf(v[c8 * 8 + j] + __ldg(&a.bias[c8 * 8 + j]), 0.f), hi[j], lo[j]);
+                        *reinterpret_cast<uint4*>(&a.out_hi[o + c8 * 8]) = *reinterpret_cast<const uint4*>(hi);
+                        *reinterpret_cast<uint4*>(&a.out_lo[o + c8 * 8]) = *reinterpret_cast<const uint4*>(lo);
+                    }
+                } else {
+                    float ss = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NF; j++) {
+                        v[j] += __ldg(&a.bias[j]);
+                        ss = fmaf(v[j], v[j], ss);
+                    }
+                    const float s = 1.0f / sqrtf(fmaxf(ss, 1e-12f));
+#pragma unroll
+                    for (int c4 = 0; c4 < NF / 4; c4++)
+                        *reinterpret_cast<float4*>(&a.out_f32[o + c4 * 4]) =
+                            make_float4(v[c4 * 4] * s, v[c4 * 4 + 1] * s, v[c4 * 4 + 2] * s, v[c4 * 4 + 3] * s);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_act_map(CUtensorMap* tm, const __half* ptr, size_t npix) {
+    EncodeTiledFn enc = get_encode();
+    MCCNN_REQUIRE(enc != nullptr, MCCNN_EINVAL, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)NF, (cuuint64_t)npix};
+    cuuint64_t strides[1] = {(cuuint64_t)NF * sizeof(__half)};
+    cuuint32_t box[2] = {(cuuint32_t)NF, (cuuint32_t)TILE_M};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MCCNN_REQUIRE(r == CUDA_SUCCESS, MCCNN_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+}  // namespace
+
+// fp16 hi/lo images of one layer's weights in the smem layout the kernel copies verbatim: per tap a
+// [64 cout][64 cin] K-major tile, 128-byte rows, 16-byte chunks XOR-swizzled by (row % 8).
+void pack_tc_weights(const float* hwio, unsigned char* dst) {
+    for (int part = 0; part < 2; part++)
+        for (int tap = 0; tap < 9; tap++)
+            for (int n = 0; n < NF; n++)
+                for (int k = 0; k < NF; k++) {
+                    const float w = hwio[((size_t)tap * NF + k) * NF + n];
+                    const __half h = __float2half_rn(w);
+                    const __half l = __float2half_rn((w - __half2float(h)) * 2048.0f);
+                    const size_t off = (size_t)part * 9 * B_TILE_BYTES + (size_t)tap * B_TILE_BYTES + (size_t)(n / 8) * 1024 +
+                                       (size_t)(n % 8) * 128 + (size_t)(((k / 8) ^ (n % 8)) * 16) + (size_t)(k % 8) * 2;
+                    const __half val = part == 0 ? h : l;
+                    memcpy(dst + off, &val, 2);
+                }
+}
+
+size_t tc_weight_bytes_per_layer() { return W_TC_BYTES; }
+
+int conv_tower_tc(const float* padded, const float* w_fp32, const size_t* layer_off_floats, const unsigned char* w_tc,
+                  float* features, void* workspace, size_t half_bytes, int H, int W, int num_layers, cudaStream_t stream) {
+    // workspace: two ping-pong activation sets, each = [hi fp16 | lo fp16] of the largest layer output
+    __half* buf[2][2];
+    for (int i = 0; i < 2; i++) {
+        buf[i][0] = reinterpret_cast<__half*>(reinterpret_cast<char*>(workspace) + i * half_bytes);
+        buf[i][1] = reinterpret_cast<__half*>(reinterpret_cast<char*>(workspace) + i * half_bytes + half_bytes / 2);
+    }
+    int Hin = H + 2 * num_layers, Win = W + 2 * num_layers;
+    {
+        const size_t npix = (size_t)(Hin - 2) * (Win - 2);
+        const float* w = w_fp32 + layer_off_floats[0];
+        conv1_split_kernel<<<(unsigned)((npix * 8 + 255) / 256), 256, 0, stream>>>(padded, w, w + 9 * NF, buf[0][0], buf[0][1], Hin, Win);
+        MCCNN_LAUNCH_CHECK("conv1_split_kernel");
+        Hin -= 2; Win -= 2;
+    }
+    MCCNN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    MCCNN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    int cur = 0;
+    for (int l = 1; l < num_layers; l++) {
+        const bool last = (l == num_layers - 1);
+        CUtensorMap tm_hi, tm_lo;
+        const size_t npix_in = (size_t)Hin * Win;
+        if (int e = make_act_map(&tm_hi, buf[cur][0], npix_in)) return e;
+        if (int e = make_act_map(&tm_lo, buf[cur][1], npix_in)) return e;
+        TcArgs a{};
+        a.w_tc = w_tc + (size_t)(l - 1) * W_TC_BYTES;
+        a.bias = w_fp32 + layer_off_floats[l] + (size_t)9 * NF * NF;
+        a.out_hi = buf[cur ^ 1][0];
+        a.out_lo = buf[cur ^ 1][1];
+        a.out_f32 = features;
+        a.Hin = Hin; a.Win = Win;
+        a.tiles_per_row = ceil_div(Win - 2, TILE_M);
+        a.ntiles = a.tiles_per_row * (Hin - 2);
+        int grid = sm_count();
+        if (grid > a.ntiles) grid = a.ntiles;
+        if (last)
+            conv_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tm_hi, tm_lo, a);
+        else
+            conv_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tm_hi, tm_lo, a);
+        MCCNN_LAUNCH_CHECK("conv_tc_kernel");
+        cur ^= 1;
+        Hin -= 2; Win -= 2;
+    }
+    return 0;
+}
+
+}  // namespace mccnn

@@ -153,15 +153,25 @@ inline size_t layer_offset_floats(int layer) {
     for (int i = 0; i < layer; i++) o += layer_w_floats(i) + NF;
     return o;
 }
+// packed blob = [fp32 section: per layer HWIO weights + bias][pad to 1 KB][tensor-core section: per layer >= 2
+// the fp16 hi/lo tiles in their shared-memory image, conv_tc.cu]
+inline size_t tc_section_offset(int num_layers) { return (layer_offset_floats(num_layers) * sizeof(float) + 1023) & ~(size_t)1023; }
 
 }  // namespace
+
+// conv_tc.cu
+void pack_tc_weights(const float* hwio, unsigned char* dst);
+size_t tc_weight_bytes_per_layer();
+int conv_tower_tc(const float* padded, const float* w_fp32, const size_t* layer_off_floats, const unsigned char* w_tc,
+                  float* features, void* workspace, size_t half_bytes, int H, int W, int num_layers, cudaStream_t stream);
+
 }  // namespace mccnn
 
 using namespace mccnn;
 
 extern "C" size_t mccnn_conv_packed_weight_bytes(int num_layers) {
     if (num_layers < 2 || num_layers > 16) return 0;
-    return layer_offset_floats(num_layers) * sizeof(float);
+    return tc_section_offset(num_layers) + (size_t)(num_layers - 1) * tc_weight_bytes_per_layer();
 }
 
 extern "C" int mccnn_pack_weights_host(const float* const* hwio_host, const float* const* bias_host, int num_layers,
@@ -175,6 +185,9 @@ extern "C" int mccnn_pack_weights_host(const float* const* hwio_host, const floa
         // HWIO [3][3][Cin][64] is already [tap][cin][cout]
         memcpy(dst + layer_offset_floats(l), hwio_host[l], layer_w_floats(l) * sizeof(float));
         memcpy(dst + layer_offset_floats(l) + layer_w_floats(l), bias_host[l], NF * sizeof(float));
+        if (l >= 1)
+            pack_tc_weights(hwio_host[l], reinterpret_cast<unsigned char*>(packed_host) + tc_section_offset(num_layers) +
+                                              (size_t)(l - 1) * tc_weight_bytes_per_layer());
     }
     return 0;
 }
@@ -190,6 +203,24 @@ extern "C" int mccnn_conv_tower(const float* padded, const void* packed_weights,
                                 size_t workspace_bytes, int H, int W, int num_layers, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MCCNN_REQUIRE(padded && packed_weights && features && workspace, MCCNN_EINVAL, "mccnn_conv_tower: null argument");
+    MCCNN_REQUIRE(H >= 1 && W >= 1 && num_layers >= 2 && num_layers <= 16, MCCNN_EINVAL,
+                  "mccnn_conv_tower: bad shape H=%d W=%d layers=%d", H, W, num_layers);
+    MCCNN_REQUIRE(workspace_bytes >= mccnn_conv_workspace_bytes(H, W, num_layers), MCCNN_EWORKSPACE,
+                  "mccnn_conv_tower: workspace too small");
+    MCCNN_REQUIRE(aligned16(features) && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0 && aligned16(packed_weights),
+                  MCCNN_EALIGN, "mccnn_conv_tower: features/weights must be 16-byte and workspace 256-byte aligned");
+    MCCNN_REQUIRE((size_t)(H + 2 * num_layers) * (W + 2 * num_layers) < 0x7fffffffu, MCCNN_EINVAL, "mccnn_conv_tower: image too large");
+    size_t offs[16];
+    for (int l = 0; l < num_layers; l++) offs[l] = layer_offset_floats(l);
+    const unsigned char* blob = reinterpret_cast<const unsigned char*>(packed_weights);
+    return conv_tower_tc(padded, reinterpret_cast<const float*>(packed_weights), offs, blob + tc_section_offset(num_layers),
+                         features, workspace, mccnn_conv_workspace_bytes(H, W, num_layers) / 2, H, W, num_layers, stream);
+}
+
+extern "C" int mccnn_conv_tower_fp32(const float* padded, const void* packed_weights, float* features, void* workspace,
+                                     size_t workspace_bytes, int H, int W, int num_layers, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MCCNN_REQUIRE(padded && packed_weights && features && workspace, MCCNN_EINVAL, "mccnn_conv_tower_fp32: null argument");
     MCCNN_REQUIRE(H >= 1 && W >= 1 && num_layers >= 2 && num_layers <= 16, MCCNN_EINVAL,
                   "mccnn_conv_tower: bad shape H=%d W=%d layers=%d", H, W, num_layers);
     MCCNN_REQUIRE(workspace_bytes >= mccnn_conv_workspace_bytes(H, W, num_layers), MCCNN_EWORKSPACE,

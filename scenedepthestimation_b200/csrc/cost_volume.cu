@@ -12,7 +12,8 @@
 // padded to 65 floats so that lanes walking x-d hit distinct banks); lanes run along d so the CL
 // stores are 128-byte coalesced; the CR values of the tile are transposed through shared memory and
 // written as runs along d as well. The x grid extends to W+D-1 so that the tiles past the right image
-// edge write the `fill` entries of CR: every element of both volumes is written exactly once.
+// edge write the `fill` entries of CR: every element of both volumes is written exactly once. The pad
+// entries [D, Dp) of both volumes are written as +INF (the SGM kernels use them as "never the minimum").
 #include "common.cuh"
 
 namespace mccnn {
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(CV_THREADS) cost_volume_exact_kernel(const flo
             const bool valid = (x < W) && (x - d >= 0);
             const float v = valid ? (float)(-acc[a][k]) : fill;
             sm.res[xl][dl] = v;
-            if (x < W && d < D) CL[((size_t)y * W + x) * Dp + d] = v;
+            if (x < W && d < Dp) CL[((size_t)y * W + x) * Dp + d] = (d < D) ? v : __int_as_float(0x7f800000);
         }
     }
     if (CR == nullptr) return;
@@ -104,6 +105,13 @@ __global__ void __launch_bounds__(CV_THREADS) cost_volume_exact_kernel(const flo
         const int x = x0 + lane;  // lane runs along the left pixels of the tile == along d
         const int d = x - xr;
         if (d >= dblk && d < dblk + DB && d < D) CR[((size_t)y * W + xr) * Dp + d] = sm.res[lane][d - dblk];
+    }
+    // pad entries [D, Dp) of CR: +INF (the SGM kernels rely on it)
+    if (Dp > D && dblk + DB >= D && dblk < D) {
+        for (int i = tid; i < TX * (Dp - D); i += CV_THREADS) {
+            const int x = x0 + i / (Dp - D), d = D + i % (Dp - D);
+            if (x < W) CR[((size_t)y * W + x) * Dp + d] = __int_as_float(0x7f800000);
+        }
     }
 }
 

@@ -70,6 +70,9 @@ __device__ __forceinline__ long long dkey(double v) {
     return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
 }
 
+// inputs are never NaN: a plain compare-select (DSETP + 2 SEL) instead of fmin()'s NaN-propagating sequence
+__device__ __forceinline__ double dmin(double x, double y) { return x < y ? x : y; }
+
 __device__ __forceinline__ double warp_min_f64(double v) {
     long long k = dkey(v);
     int hi = (int)(k >> 32);
@@ -136,6 +139,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
         for (int s = 0; s < STAGES; s++) mbar_init(&bars[s], 1);
         mbar_fence_init();
     }
+    // Disparities d >= D never need a validity test: the cost they read is +INF (the volume's pad entries
+    // [D, Dp) are written as +INF by mccnn_cost_volume; the row-buffer tail [Dp, 32*NPL) is set here and never
+    // overwritten by the bulk copies), so their state stays +INF and they never win a minimum.
+    for (int i = lane; i < ROW * STAGES * IN_BUFS; i += 32) inbuf[i] = __int_as_float(0x7f800000);
+    fence_proxy_async_smem();
     __syncwarp();
 
     const uint32_t copy_bytes = (uint32_t)a.Dp * 4u;
@@ -143,6 +151,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
     const int npix_line = a.horizontal ? a.W : a.H;
     const int d0 = lane * NPL;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    (void)d0;
 
     uint32_t gstep = 0;  // rows consumed by this warp so far (ring position / mbarrier phase)
     uint32_t ostep = 0;  // rows stored so far (output staging parity)
@@ -198,9 +207,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             const float* ib = inbuf + (size_t)st * IN_BUFS * ROW;
             load_chunk<NPL>(ib, lane, cf);
             if constexpr (kReadS) load_chunk<NPL>(ib + ROW, lane, sf);
-            __syncwarp();
-            if (lane == 0 && t + STAGES < a.nsteps_total) issue_load(t + STAGES, gstep + STAGES);
-            gstep++;
+            // The stage is refilled at the END of the step, after every lane has consumed cf/sf in arithmetic:
+            // a warp barrier alone does not wait for outstanding shared loads, and an early refill (async
+            // proxy) could overwrite the row under a still-queued LDS.
 
             if ((t & 31) == 0 && t > 0) {
                 blk_cur = blk_next;
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
                 const bool wrapped = (!a.horizontal) && (a.dx != 0) && (t > 0) && (a.dx > 0 ? col == 0 : col == a.W - 1);
                 if (t == 0 || wrapped) {
 #pragma unroll
-                    for (int j = 0; j < NPL; j++) L[j] = (d0 + j < a.D) ? (double)cf[j] : INF;
+                    for (int j = 0; j < NPL; j++) L[j] = (double)cf[j];
                 } else {
                     const double P1 = edge_full ? a.P1 : a.P1r;
                     double up = __shfl_up_sync(0xffffffffu, L[NPL - 1], 1);
@@ -227,18 +236,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
 #pragma unroll
                     for (int j = 0; j < NPL; j++) {
                         const double a_next = ((j + 1 < NPL) ? L[j + 1 < NPL ? j + 1 : j] : dn_) + P1;
-                        const double m = fmin(fmin(a_prev, a_next), fmin(L[j], minLP2));
+                        const double m = dmin(dmin(a_prev, a_next), dmin(L[j], minLP2));
                         double c = (double)cf[j];
                         c += (m - minL);
                         a_prev = a_cur;
                         a_cur = a_next;
-                        L[j] = (d0 + j < a.D) ? c : INF;
+                        L[j] = c;
                     }
                 }
                 // minimum over d, consumed at the next pixel together with this pixel's P2 (:332-341)
                 double m = L[0];
 #pragma unroll
-                for (int j = 1; j < NPL; j++) m = fmin(m, L[j]);
+                for (int j = 1; j < NPL; j++) m = dmin(m, L[j]);
                 minL = warp_min_f64(m);
                 minLP2 = minL + (next_full ? a.P2 : a.P2r);
             }
@@ -251,7 +260,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             for (int j = 0; j < NPL; j++) {
                 if constexpr (MODE == SGM_FIRST_FUSED) {
                     // S starts at 0 (:1116-1117): down path, then the up path's raw-cost add on rows >= 1
-                    float s = dp_active ? (float)(0.0 + L[j]) : 0.0f;
+                    float s = dp_active ? (float)L[j] : 0.0f;
                     if (row >= 1) s = (float)((double)s + (double)cf[j]);
                     so[j] = s;
                 } else {
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
                 int bj = 0;
 #pragma unroll
                 for (int j = 0; j < NPL; j++) {
-                    const float v = (d0 + j < a.D) ? so[j] + 0.0f : __int_as_float(0x7f800000);
+                    const float v = so[j] + 0.0f;  // entries d >= D are +INF or NaN here: never selected
                     if (v < best) { best = v; bj = j; }
                 }
                 int k = __float_as_int(best);
@@ -290,6 +299,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
                 const int idx = __shfl_sync(0xffffffffu, d0 + bj, src);
                 if (lane == 0) a.disp[side][(size_t)row * a.W + col] = (float)idx;
             }
+            // every lane's results (which depend on all of its cf/sf loads) are stored or reduced: refill the stage
+            __syncwarp();
+            if (lane == 0 && t + STAGES < a.nsteps_total) issue_load(t + STAGES, gstep + STAGES);
+            gstep++;
         }
     }
     if (lane == 0) bulk_wait_all<0>();

@@ -94,14 +94,16 @@ def pad_f32(image: torch.Tensor, pad: int) -> torch.Tensor:
     return out
 
 
-def conv_tower(padded: torch.Tensor, packed: torch.Tensor, num_layers: int = 5) -> torch.Tensor:
+def conv_tower(padded: torch.Tensor, packed: torch.Tensor, num_layers: int = 5, fp32: bool = False) -> torch.Tensor:
+    """Tensor-core tower (tcgen05, fp16 hi/lo split); fp32=True runs the CUDA-core fp32 twin."""
     lib = _lib.load()
     Hp, Wp = padded.shape
     H, W = Hp - 2 * num_layers, Wp - 2 * num_layers
     feat = torch.empty((H, W, FEATURES), dtype=torch.float32, device="cuda")
     nws = lib.mccnn_conv_workspace_bytes(H, W, num_layers)
     ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
-    _lib.check(lib.mccnn_conv_tower(_p(padded), _p(packed), _p(feat), _p(ws), nws, H, W, num_layers, _stream()), "mccnn_conv_tower")
+    fn = lib.mccnn_conv_tower_fp32 if fp32 else lib.mccnn_conv_tower
+    _lib.check(fn(_p(padded), _p(packed), _p(feat), _p(ws), nws, H, W, num_layers, _stream()), "mccnn_conv_tower")
     return feat
 
 

@@ -129,14 +129,32 @@ def test_conv_tower_vs_oracle(eng):
     ref64 = ct.conv_tower(padded, w, 5, torch.float64)
     ref32 = ct.conv_tower(padded, w, 5, torch.float32)
     packed = eng.pack_weights(w, 5)
-    got = eng.conv_tower(eng.pad_f32(dev(std[:, :, 0]), 5), packed, 5).cpu().numpy()
-    err = np.abs(got - ref64).max()
     err32 = np.abs(ref32 - ref64).max()
-    assert err <= 2e-6, (err, err32)
-    np.testing.assert_allclose(np.sum(got.astype(np.float64) ** 2, -1), 1.0, atol=1e-5)
+    pad = eng.pad_f32(dev(std[:, :, 0]), 5)
+    # CUDA-core fp32 twin and the tcgen05 path (fp16 hi/lo split, fp32 TMEM accumulators): same bar
+    for fp32 in (True, False):
+        got = eng.conv_tower(pad, packed, 5, fp32=fp32).cpu().numpy()
+        err = np.abs(got - ref64).max()
+        assert err <= 2e-6, (fp32, err, err32)
+        np.testing.assert_allclose(np.sum(got.astype(np.float64) ** 2, -1), 1.0, atol=1e-5)
     # fused standardise + pad from u8 (integer-exact statistics) stays within the same tolerance
     got2 = eng.conv_tower(eng.standardize_pad(dev(il), 5), packed, 5).cpu().numpy()
     assert np.abs(got2 - ref64).max() <= 5e-6
+
+
+@pytest.mark.parametrize("H,W", [(3, 5), (9, 128), (17, 129), (40, 300), (2, 1000)])
+def test_conv_tower_tensor_core_vs_fp32_twin(eng, H, W):
+    """tcgen05 implicit GEMM vs the CUDA-core fp32 tower on the same device, incl. partial 128-pixel tiles."""
+    from scenedepthestimation_b200 import synthetic as syn
+
+    rng = np.random.default_rng(H * 7 + W)
+    img = rng.standard_normal((H, W)).astype(np.float32)
+    packed = eng.pack_weights(syn.glorot_weights(seed=H + W), 5)
+    pad = eng.pad_f32(dev(img), 5)
+    a = eng.conv_tower(pad, packed, 5, fp32=True).cpu().numpy()
+    b = eng.conv_tower(pad, packed, 5, fp32=False).cpu().numpy()
+    assert np.isfinite(b).all()
+    assert np.abs(a - b).max() <= 3e-6
 
 
 def test_match_pair_end_to_end(eng):
