@@ -8,9 +8,13 @@
 // GEMM view of one 3x3 VALID layer, 64 -> 64 channels, activations NHWC:
 //   M = 128 consecutive output pixels of one image row, N = 64 output channels,
 //   K = 9 taps x 64 input channels. For tap (ky,kx) the A operand is the [128 pixels][64 channels]
-//   block starting at input pixel (y+ky, x0+kx): contiguous in memory, fetched by one TMA 2-D tile
-//   load into the 128-byte-swizzled K-major layout tcgen05 wants. B = the tap's [64 cout][64 cin]
-//   weights, resident in shared memory for the whole (persistent) CTA.
+//   block starting at input pixel (y+ky, x0+kx): contiguous in memory. One TMA 2-D tile load per ky
+//   brings the 136-pixel window of that image row into the 128-byte-swizzled K-major layout tcgen05
+//   wants; the three kx taps read it through descriptors whose start is shifted by kx rows (128 B).
+//   The 128B swizzle is a function of the shared-memory ADDRESS bits (measured: the shifted start
+//   needs base_offset 0; base_offset = kx gives wrong results), so the rows TMA wrote are found
+//   where the MMA looks for them. Every activation byte crosses L2->smem 3x, not 9x.
+//   B = the tap's [64 cout][64 cin] weights, resident in shared memory for the whole (persistent) CTA.
 //
 // Precision: the reference runs fp32 convolutions. Every operand is split into two fp16 numbers,
 // x = hi + lo / 2048 (22-bit significand, lo scaled so that it cannot underflow), and each k-step
@@ -31,7 +35,8 @@ namespace {
 
 constexpr int NF = MCCNN_FEATURES;
 constexpr int TILE_M = 128;
-constexpr int A_TILE_BYTES = TILE_M * 128;  // 128 pixels x 64 fp16
+constexpr int WIN_ROWS = 136;               // 128 + 2 pixels of kx shift, rounded up to the 8-row swizzle atom
+constexpr int A_TILE_BYTES = WIN_ROWS * 128;  // one image-row window: 136 pixels x 64 fp16
 constexpr int B_TILE_BYTES = NF * 128;      // 64 cout x 64 fp16
 constexpr int W_TC_BYTES = 2 * 9 * B_TILE_BYTES;  // hi + lo, 9 taps
 constexpr int TC_STAGES = 2;
@@ -61,9 +66,10 @@ __device__ __forceinline__ void bulk_g2s_addr(uint32_t smem_dst, const void* gme
                  : "memory");
 }
 // K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+// base_offset stays 0 also for starts shifted by whole 128-byte rows (see the header comment).
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr, uint32_t base_offset = 0) {
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
+           ((uint64_t)(base_offset & 7u) << 49) | ((uint64_t)2 << 61);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
@@ -99,34 +105,36 @@ __device__ __forceinline__ void split_store(float v, __half& h, __half& l) {
 __global__ void __launch_bounds__(256) conv1_split_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                          const float* __restrict__ b, __half* __restrict__ out_hi,
                                                          __half* __restrict__ out_lo, int Hin, int Win) {
-    __shared__ float ws[9 * NF];
-    __shared__ float bs[NF];
-    for (int i = threadIdx.x; i < 9 * NF; i += 256) ws[i] = w[i];
-    if (threadIdx.x < NF) bs[threadIdx.x] = b[threadIdx.x];
-    __syncthreads();
+    // thread = 8 output channels (weights in registers) x a strided set of pixels; 8 threads share a pixel
+    const int q = threadIdx.x & 7;
+    float wr[9][8], br[8];
+#pragma unroll
+    for (int t = 0; t < 9; t++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) wr[t][c] = __ldg(&w[t * NF + 8 * q + c]);
+#pragma unroll
+    for (int c = 0; c < 8; c++) br[c] = __ldg(&b[8 * q + c]);
     const int Hout = Hin - 2, Wout = Win - 2;
     const size_t npix = (size_t)Hout * Wout;
-    const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
-    const size_t pix = gid >> 3;
-    const int q = (int)(gid & 7);  // 8 output channels per thread
-    if (pix >= npix) return;
-    const int y = (int)(pix / Wout), x = (int)(pix % Wout);
-    float acc[8];
+    for (size_t pix = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); pix < npix; pix += (size_t)gridDim.x * 32) {
+        const int y = (int)(pix / Wout), x = (int)(pix % Wout);
+        float acc[8];
 #pragma unroll
-    for (int c = 0; c < 8; c++) acc[c] = 0.f;
+        for (int c = 0; c < 8; c++) acc[c] = 0.f;
 #pragma unroll
-    for (int ky = 0; ky < 3; ky++)
+        for (int ky = 0; ky < 3; ky++)
 #pragma unroll
-        for (int kx = 0; kx < 3; kx++) {
-            const float v = in[(size_t)(y + ky) * Win + x + kx];
+            for (int kx = 0; kx < 3; kx++) {
+                const float v = __ldg(&in[(size_t)(y + ky) * Win + x + kx]);
 #pragma unroll
-            for (int c = 0; c < 8; c++) acc[c] = fmaf(v, ws[(ky * 3 + kx) * NF + 8 * q + c], acc[c]);
-        }
-    __align__(16) __half hi[8], lo[8];
+                for (int c = 0; c < 8; c++) acc[c] = fmaf(v, wr[ky * 3 + kx][c], acc[c]);
+            }
+        __align__(16) __half hi[8], lo[8];
 #pragma unroll
-    for (int c = 0; c < 8; c++) split_store(fmaxf(acc[c] + bs[8 * q + c], 0.f), hi[c], lo[c]);
-    *reinterpret_cast<uint4*>(&out_hi[pix * NF + 8 * q]) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(&out_lo[pix * NF + 8 * q]) = *reinterpret_cast<const uint4*>(lo);
+        for (int c = 0; c < 8; c++) split_store(fmaxf(acc[c] + br[c], 0.f), hi[c], lo[c]);
+        *reinterpret_cast<uint4*>(&out_hi[pix * NF + 8 * q]) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(&out_lo[pix * NF + 8 * q]) = *reinterpret_cast<const uint4*>(lo);
+    }
 }
 
 // ---------------------------------------------------------------- layers 2..n on tcgen05
@@ -181,11 +189,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 const int y = tile / a.tiles_per_row, x0 = (tile % a.tiles_per_row) * TILE_M;
-                for (int tap = 0; tap < 9; tap++, it++) {
+                for (int ky = 0; ky < 3; ky++, it++) {
                     const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
                     mbar_expect_tx(&full[s], STAGE_BYTES);
-                    const int pix = (y + tap / 3) * a.Win + x0 + tap % 3;
+                    const int pix = (y + ky) * a.Win + x0;
                     const uint32_t dst = base + SMEM_A_OFF + s * STAGE_BYTES;
                     tma_load_2d(dst, &tm_hi, 0, pix, &full[s]);
                     tma_load_2d(dst + A_TILE_BYTES, &tm_lo, 0, pix, &full[s]);
@@ -202,20 +210,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 mbar_wait(&tempty[acc], aph ^ 1u);
                 tc_fence_after();
                 const uint32_t d_main = tmem_base + acc * 128u, d_corr = d_main + 64u;
-                for (int tap = 0; tap < 9; tap++, it++) {
+                for (int ky = 0; ky < 3; ky++, it++) {
                     const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t a_addr = base + SMEM_A_OFF + s * STAGE_BYTES;
-                    const uint64_t a_hi = sw128_desc(a_addr), a_lo = sw128_desc(a_addr + A_TILE_BYTES);
-                    const uint64_t b_hi = sw128_desc(base + tap * B_TILE_BYTES);
-                    const uint64_t b_lo = sw128_desc(base + 9 * B_TILE_BYTES + tap * B_TILE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {  // UMMA_K = 16 fp16 = 32 bytes = 2 descriptor units
-                        const uint32_t first = (tap | k) != 0 ? 1u : 0u;
-                        umma_f16(d_main, a_hi + 2 * k, b_hi + 2 * k, first);
-                        umma_f16(d_corr, a_hi + 2 * k, b_lo + 2 * k, first);
-                        umma_f16(d_corr, a_lo + 2 * k, b_hi + 2 * k, 1u);
+                    for (int kx = 0; kx < 3; kx++) {
+                        const int tap = ky * 3 + kx;
+                        // same window, start shifted by kx pixels (= kx 128-byte rows)
+                        const uint64_t a_hi = sw128_desc(a_addr + kx * 128);
+                        const uint64_t a_lo = sw128_desc(a_addr + A_TILE_BYTES + kx * 128);
+                        const uint64_t b_hi = sw128_desc(base + tap * B_TILE_BYTES);
+                        const uint64_t b_lo = sw128_desc(base + 9 * B_TILE_BYTES + tap * B_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {  // UMMA_K = 16 fp16 = 32 bytes = 2 descriptor units
+                            const uint32_t first = (tap | k) != 0 ? 1u : 0u;
+                            umma_f16(d_main, a_hi + 2 * k, b_hi + 2 * k, first);
+                            umma_f16(d_corr, a_hi + 2 * k, b_lo + 2 * k, first);
+                            umma_f16(d_corr, a_lo + 2 * k, b_hi + 2 * k, 1u);
+                        }
                     }
                     umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
                 }
@@ -305,7 +319,7 @@ int make_act_map(CUtensorMap* tm, const __half* ptr, size_t npix) {
     MCCNN_REQUIRE(enc != nullptr, MCCNN_EINVAL, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {(cuuint64_t)NF, (cuuint64_t)npix};
     cuuint64_t strides[1] = {(cuuint64_t)NF * sizeof(__half)};
-    cuuint32_t box[2] = {(cuuint32_t)NF, (cuuint32_t)TILE_M};
+    cuuint32_t box[2] = {(cuuint32_t)NF, (cuuint32_t)WIN_ROWS};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -347,7 +361,9 @@ int conv_tower_tc(const float* padded, const float* w_fp32, const size_t* layer_
     {
         const size_t npix = (size_t)(Hin - 2) * (Win - 2);
         const float* w = w_fp32 + layer_off_floats[0];
-        conv1_split_kernel<<<(unsigned)((npix * 8 + 255) / 256), 256, 0, stream>>>(padded, w, w + 9 * NF, buf[0][0], buf[0][1], Hin, Win);
+        size_t blocks = (npix + 31) / 32;
+        if (blocks > (size_t)sm_count() * 16) blocks = (size_t)sm_count() * 16;
+        conv1_split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(padded, w, w + 9 * NF, buf[0][0], buf[0][1], Hin, Win);
         MCCNN_LAUNCH_CHECK("conv1_split_kernel");
         Hin -= 2; Win -= 2;
     }

@@ -3,114 +3,180 @@
 // Replaces compute_cost_volume_kernel (process_functional.py:120-131) and the host-side
 // np.ones fill of both volumes (:1111-1114).
 //
-// Arithmetic contract: temp is fp64; every product fl*fr is an fp32 multiply
-// that is widened and added in fp64, i = 0..63 in order; the store rounds -temp to fp32.
-// CL[y][x][d] and CR[y][x-d][d] receive the same value; entries never written keep `fill`.
+// Arithmetic contract (pinned bit for bit by tests/golden): temp is fp64; every
+// product fl*fr is an fp32 multiply that is widened and added in fp64, i = 0..63 in order; the store
+// rounds -temp to fp32. CL[y][x][d] and CR[y][x-d][d] receive the same value; entries never written
+// keep `fill`.
 //
-// Shape: a CTA owns (row y, TX left pixels, DB disparities). The 64-float feature rows of the TX
-// left pixels and of the TX+DB-1 right pixels they can meet are staged in shared memory (right rows
-// padded to 65 floats so that lanes walking x-d hit distinct banks); lanes run along d so the CL
-// stores are 128-byte coalesced; the CR values of the tile are transposed through shared memory and
-// written as runs along d as well. The x grid extends to W+D-1 so that the tiles past the right image
-// edge write the `fill` entries of CR: every element of both volumes is written exactly once. The pad
-// entries [D, Dp) of both volumes are written as +INF (the SGM kernels use them as "never the minimum").
+// Shape: with u = x - d (the right pixel) the volume of one image row is a BAND of the plain product
+// matrix C'[x][u] = -<fl[x], fr[u]>, 0 <= x-u < D. A CTA computes one 64x64 (x,u) tile of the band as a
+// small GEMM: both 64-pixel feature tiles are transposed into shared memory (k-major, 16-byte-chunk
+// XOR swizzle), each thread owns a 4x4 register tile (two 128-bit shared loads per k for 16 products),
+// and the finished tile goes through shared memory so that BOTH outputs are written as contiguous
+// runs along d: for a fixed x the tile's u-range is a run of CL[y][x][.], for a fixed u its x-range
+// is a run of CR[y][u][.]. Tiles past the band edges (u < 0, x >= W) only write `fill`; every element
+// of both volumes is written exactly once, pad entries [D, Dp) as +INF (the SGM kernels rely on it).
+//
+// The exact contract costs one fp32->fp64 widening per product. F2F.F64.F32 issues at 16/clk/SM on
+// B200 (profiles/r01_ubench_pipes.txt), which bounds a straightforward kernel far below HBM speed, so
+// half of the products are widened on the integer pipe instead (4 ALU ops, bit-exact for normal
+// numbers). A CTA whose staged features are not all comfortably normal falls back to F2F for all.
 #include "common.cuh"
 
 namespace mccnn {
 namespace {
 
-constexpr int TX = 32;
-constexpr int DB = 128;
 constexpr int NF = MCCNN_FEATURES;
-constexpr int FR_PITCH = NF + 1;
-constexpr int WIN = TX + DB - 1;
+constexpr int T = 64;  // tile edge in x and in u
 constexpr int CV_THREADS = 256;
+constexpr int RES_PITCH = T + 1;
+constexpr float kInfF = __builtin_huge_valf();
 
 struct CvSmem {
-    float fl[TX][NF];
-    float fr[WIN][FR_PITCH];
-    float res[TX][DB + 1];
+    union {
+        struct {
+            float a[NF][T];  // [k][x], chunk-swizzled
+            float b[NF][T];  // [k][u]
+        } op;
+        float res[T][RES_PITCH];  // [x][u]
+    };
 };
 
-__global__ void __launch_bounds__(CV_THREADS) cost_volume_exact_kernel(const float* __restrict__ fl,
-                                                                      const float* __restrict__ fr,
-                                                                      float* __restrict__ CL, float* __restrict__ CR,
-                                                                      int H, int W, int D, int Dp, float fill) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CvSmem& sm = *reinterpret_cast<CvSmem*>(smem_raw);
-    const int x0 = blockIdx.x * TX;
-    const int y = blockIdx.y;
-    const int dblk = blockIdx.z * DB;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int xr0 = x0 - dblk - (DB - 1);  // first right pixel of the window
-    const bool any_left = x0 < W;
+// bit-exact fp32 -> fp64 widening of a NORMAL, finite fp32 number on the integer pipe
+__device__ __forceinline__ double widen_normal(float p) {
+    const uint32_t x = __float_as_uint(p);
+    const int32_t t = (int32_t)x >> 3;  // sign copies | exponent | mantissa >> 3
+    const uint32_t hi = ((uint32_t)t & 0x8fffffffu) + 0x38000000u;  // rebias 127 -> 1023
+    return __hiloint2double((int)hi, (int)(x << 29));
+}
 
-    if (any_left) {
-        // stage features (coalesced: 64 consecutive floats per pixel)
-        for (int i = tid; i < TX * NF; i += CV_THREADS) {
-            const int p = i / NF, f = i % NF;
-            const int x = x0 + p;
-            sm.fl[p][f] = (x < W) ? fl[((size_t)y * W + x) * NF + f] : 0.0f;
-        }
-        for (int i = tid; i < WIN * NF; i += CV_THREADS) {
-            const int p = i / NF, f = i % NF;
-            const int x = xr0 + p;
-            sm.fr[p][f] = (x >= 0 && x < W) ? fr[((size_t)y * W + x) * NF + f] : 0.0f;
-        }
+// features whose pairwise products are guaranteed normal and finite: 2^-60 <= |v| < 2^64
+__device__ __forceinline__ bool comfortably_normal(float v) {
+    const uint32_t e = (__float_as_uint(v) >> 23) & 0xffu;
+    return e >= 67u && e <= 190u;
+}
+
+// Stage 64 pixels x 64 features: global [pixel][k] -> shared [k][pixel], 4-pixel chunks XOR-swizzled by k/4.
+// Out-of-image pixels get 1.0 (their results are never stored). Returns false if a value is not comfortably normal.
+__device__ __forceinline__ bool stage_tile(float (*dst)[T], const float* __restrict__ feat, int y, int W, int p0, int tid) {
+    bool ok = true;
+#pragma unroll
+    for (int rep = 0; rep < 4; rep++) {
+        const int pl = (tid >> 4) + 16 * rep;  // pixel within tile
+        const int k4 = tid & 15;               // features 4*k4 .. 4*k4+3
+        const int p = p0 + pl;
+        float4 v = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p >= 0 && p < W) v = *reinterpret_cast<const float4*>(&feat[((size_t)y * W + p) * NF + 4 * k4]);
+        ok = ok && comfortably_normal(v.x) && comfortably_normal(v.y) && comfortably_normal(v.z) && comfortably_normal(v.w);
+        const int col = ((((pl >> 2) ^ k4) & 15) << 2) | (pl & 3);  // swizzle key = (k / 4) & 15 = k4
+        dst[4 * k4 + 0][col] = v.x;
+        dst[4 * k4 + 1][col] = v.y;
+        dst[4 * k4 + 2][col] = v.z;
+        dst[4 * k4 + 3][col] = v.w;
     }
-    __syncthreads();
+    return ok;
+}
 
-    // warp w owns left pixels x0 + 4w + a (a = 0..3); lane owns d = dblk + lane + 32k (k = 0..3)
+template <bool SPLIT>
+__device__ __forceinline__ void tile_products(const CvSmem& sm, int tx, int ty, double (&acc)[4][4]) {
+#pragma unroll 2
+    for (int k = 0; k < NF; k++) {
+        const int key = (k >> 2) & 15;
+        const float4 av = *reinterpret_cast<const float4*>(&sm.op.a[k][((tx ^ key) & 15) << 2]);
+        const float4 bv = *reinterpret_cast<const float4*>(&sm.op.b[k][((ty ^ key) & 15) << 2]);
+        const float a[4] = {av.x, av.y, av.z, av.w};
+        const float b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float p = __fmul_rn(a[i], b[j]);
+                if (SPLIT && ((i + j) & 1))
+                    acc[i][j] += widen_normal(p);  // integer pipe
+                else
+                    acc[i][j] += (double)p;  // F2F.F64.F32
+            }
+    }
+}
+
+__global__ void __launch_bounds__(CV_THREADS) cost_volume_band_kernel(const float* __restrict__ fl,
+                                                                     const float* __restrict__ fr,
+                                                                     float* __restrict__ CL, float* __restrict__ CR, int H,
+                                                                     int W, int D, int Dp, float fill, int ut_min) {
+    __shared__ __align__(16) CvSmem sm;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int y = blockIdx.z;
+    const int x0 = blockIdx.y * T;
+    // u tiles of this x tile: aligned to multiples of T (negative allowed), from the one holding x0-(D-1)
+    const int first_ut = (x0 - (D - 1) >= 0) ? (x0 - (D - 1)) / T : -((-(x0 - (D - 1)) + T - 1) / T);
+    const int ut = first_ut + (int)blockIdx.x;
+    (void)ut_min;
+    const int u0 = ut * T;
+    if (u0 > x0 + T - 1) return;                  // entirely above the diagonal: d < 0
+    if (CR == nullptr && x0 >= W) return;         // nothing to write
+    const bool has_left = x0 < W, has_right = (u0 + T - 1 >= 0) && (u0 < W);
+    const bool compute = has_left && has_right;
+
+    const int tx = tid & 15, ty = tid >> 4;  // thread tile: x = x0 + 4tx + i, u = u0 + 4ty + j
     double acc[4][4];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int k = 0; k < 4; k++) acc[a][k] = 0.0;
-    if (any_left) {
-        const int base = 4 * warp - lane + (DB - 1);  // window index of (a = 0, k = 0)
-#pragma unroll 4
-        for (int i = 0; i < NF; i++) {
-            float fa[4];
-#pragma unroll
-            for (int a = 0; a < 4; a++) fa[a] = sm.fl[4 * warp + a][i];
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float fb = sm.fr[base + a - 32 * k][i];
-                    acc[a][k] += (double)__fmul_rn(fa[a], fb);
-                }
-        }
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+
+    if (compute) {
+        bool ok = stage_tile(sm.op.a, fl, y, W, x0, tid);
+        ok = stage_tile(sm.op.b, fr, y, W, u0, tid) && ok;
+        const int all_ok = __syncthreads_and(ok ? 1 : 0);
+        if (all_ok)
+            tile_products<true>(sm, tx, ty, acc);
+        else
+            tile_products<false>(sm, tx, ty, acc);
     }
+    __syncthreads();  // operands are dead: the result tile aliases them
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
-        const int xl = 4 * warp + a;
-        const int x = x0 + xl;
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int dl = lane + 32 * k;
-            const int d = dblk + dl;
-            const bool valid = (x < W) && (x - d >= 0);
-            const float v = valid ? (float)(-acc[a][k]) : fill;
-            sm.res[xl][dl] = v;
-            if (x < W && d < Dp) CL[((size_t)y * W + x) * Dp + d] = (d < D) ? v : __int_as_float(0x7f800000);
+        for (int j = 0; j < 4; j++) {
+            const int xl = 4 * tx + i, ul = 4 * ty + j;
+            const int x = x0 + xl, u = u0 + ul;
+            const bool valid = compute && x < W && u >= 0 && u < W;
+            sm.res[xl][ul] = valid ? (float)(-acc[i][j]) : fill;
         }
-    }
-    if (CR == nullptr) return;
     __syncthreads();
-    // CR[y][xr][d] = value of left pixel x = xr + d: for a fixed xr the tile holds a run of <= TX disparities
-    for (int p = warp; p < WIN; p += CV_THREADS / 32) {
-        const int xr = xr0 + p;
-        if (xr < 0 || xr >= W) continue;
-        const int x = x0 + lane;  // lane runs along the left pixels of the tile == along d
-        const int d = x - xr;
-        if (d >= dblk && d < dblk + DB && d < D) CR[((size_t)y * W + xr) * Dp + d] = sm.res[lane][d - dblk];
+
+    // CL[y][x][d], d = x - u: for a fixed x the tile's u range is a contiguous run of d
+    if (has_left) {
+        for (int xl = warp; xl < T; xl += CV_THREADS / 32) {
+            const int x = x0 + xl;
+            if (x >= W) break;
+            float* row = CL + ((size_t)y * W + x) * Dp;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int ul = (T - 1) - (lane + 32 * h);  // descending u = ascending d
+                const int d = x - (u0 + ul);
+                if (d >= 0 && d < D) row[d] = sm.res[xl][ul];
+            }
+            // the tile that holds d = D-1 for this x also writes the +INF pad
+            const int dl = x - (u0 + T - 1), dh = x - u0;
+            if (Dp > D && dl <= D - 1 && D - 1 <= dh && lane < Dp - D) row[D + lane] = kInfF;
+        }
     }
-    // pad entries [D, Dp) of CR: +INF (the SGM kernels rely on it)
-    if (Dp > D && dblk + DB >= D && dblk < D) {
-        for (int i = tid; i < TX * (Dp - D); i += CV_THREADS) {
-            const int x = x0 + i / (Dp - D), d = D + i % (Dp - D);
-            if (x < W) CR[((size_t)y * W + x) * Dp + d] = __int_as_float(0x7f800000);
+    // CR[y][u][d], d = x - u: for a fixed u the tile's x range is a contiguous run of d
+    if (CR != nullptr && has_right) {
+        for (int ul = warp; ul < T; ul += CV_THREADS / 32) {
+            const int u = u0 + ul;
+            if (u < 0) continue;
+            if (u >= W) break;
+            float* row = CR + ((size_t)y * W + u) * Dp;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int xl = lane + 32 * h;
+                const int d = (x0 + xl) - u;
+                if (d >= 0 && d < D) row[d] = sm.res[xl][ul];
+            }
+            const int dl = x0 - u, dh = x0 + T - 1 - u;
+            if (Dp > D && dl <= D - 1 && D - 1 <= dh && lane < Dp - D) row[D + lane] = kInfF;
         }
     }
 }
@@ -142,13 +208,16 @@ extern "C" int mccnn_cost_volume(const float* fl, const float* fr, float* CL, fl
     MCCNN_REQUIRE(H >= 1 && W >= 1 && D >= 1 && D <= 4096, MCCNN_EINVAL, "mccnn_cost_volume: bad shape H=%d W=%d D=%d", H,
                   W, D);
     MCCNN_REQUIRE(H <= 65535, MCCNN_EINVAL, "mccnn_cost_volume: H=%d exceeds 65535", H);
+    MCCNN_REQUIRE(aligned16(fl) && aligned16(fr), MCCNN_EALIGN, "mccnn_cost_volume: features must be 16-byte aligned");
     const int Dp = disp_pitch(D);
-    const size_t smem = sizeof(CvSmem);
-    MCCNN_CUDA(cudaFuncSetAttribute(cost_volume_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int xt = ceil_div(CR ? (W + D - 1) : W, TX);
-    dim3 grid(xt, H, ceil_div(D, DB));
-    cost_volume_exact_kernel<<<grid, CV_THREADS, smem, stream>>>(fl, fr, CL, CR, H, W, D, Dp, fill);
-    MCCNN_LAUNCH_CHECK("cost_volume_exact_kernel");
+    // x tiles cover [0, W + D - 1) when CR is written (the tiles past the image edge write CR's fill entries);
+    // each x tile meets at most ceil((D - 1 + 2T - 1) / T) u tiles of the band
+    const int nxt = ceil_div(CR ? (W + D - 1) : W, T);
+    const int nut = (D - 1 + T - 1) / T + 2;
+    MCCNN_REQUIRE(nxt <= 65535, MCCNN_EINVAL, "mccnn_cost_volume: image too wide");
+    dim3 grid(nut, nxt, H);
+    cost_volume_band_kernel<<<grid, CV_THREADS, 0, stream>>>(fl, fr, CL, CR, H, W, D, Dp, fill, 0);
+    MCCNN_LAUNCH_CHECK("cost_volume_band_kernel");
     return 0;
 }
 

@@ -117,6 +117,32 @@ def test_pipeline_vs_oracle_generic_D(eng, H, W, D, kind):
     assert np.array_equal(out_r.cpu().numpy(), dr_o)
 
 
+@pytest.mark.parametrize("H,W,D", [(3, 200, 150), (2, 65, 64), (4, 129, 7), (2, 64, 300)])
+def test_cost_volume_special_values_and_tiles(eng, H, W, D):
+    """Band-GEMM cost volume: tile-edge shapes, and features with zeros / denormals / tiny values, which force
+    the all-F2F widening path of a CTA (the integer-pipe widening is only exact for normal products)."""
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import synthetic as syn
+
+    fl, fr = syn.unit_features(H, W, 64, H + W + D)
+    fl[0, :: 7, 3] = 0.0
+    fr[-1, 5, :] = 0.0
+    fl[0, 1, 0] = np.float32(1e-41)   # denormal
+    fr[0, 2, 1] = np.float32(-3e-30)  # products may underflow
+    cl, cr = st.cost_volume(fl, fr, D)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    assert np.array_equal(unpitch(CL, D), cl) and np.array_equal(unpitch(CR, D), cr)
+    Dp = CL.shape[-1]
+    if Dp > D:
+        assert torch.isinf(CL[..., D:]).all() and torch.isinf(CR[..., D:]).all()
+    only_left, _ = eng.cost_volume(dev(fl), dev(fr), D, fill=-0.0, right=False)
+    exp = cl.copy()
+    exp[cl == 1.0] = 0.0  # same entries, other fill
+    x = np.arange(W)[None, :, None]
+    d = np.arange(D)[None, None, :]
+    assert np.array_equal(unpitch(only_left, D)[np.broadcast_to(x - d >= 0, cl.shape)], cl[np.broadcast_to(x - d >= 0, cl.shape)])
+
+
 def test_conv_tower_vs_oracle(eng):
     from oracle import conv_tower as ct
     from scenedepthestimation_b200 import synthetic as syn
