@@ -25,7 +25,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-KERNELS_PER_STEP = 2 * 2 + 2 * 5 + 1 + 7 + 3  # standardise(2x2) + conv(2x5) + cost volume + SGM passes + lr/fill/median
+KERNELS_PER_STEP = 2 * 2 + 2 * 5 + 1 + 7 + 4  # standardise(2x2) + conv(2x5) + cost volume + SGM passes + lr flags, fill (2), median
 
 
 def parse():

@@ -130,8 +130,11 @@ int mccnn_wta_dhw(const float* vol_dhw, float* disp, int H, int W, int D, void* 
  * is_error_match_kernel (:977-1000). flagR may be NULL. */
 int mccnn_lr_flags(const float* dispL, const float* dispR, uint8_t* flagL, uint8_t* flagR,
                    int H, int W, void* stream);
-/* LRC_kernel (:1003-1088), left map only (the reference never writes the right output). */
-int mccnn_lrc_fill(const float* dispL, const uint8_t* flagL, float* filled, int H, int W, void* stream);
+/* LRC_kernel (:1003-1088), left map only (the reference never writes the right output).
+ * workspace: mccnn_lrc_fill_workspace_bytes(H, W) bytes (two fp32 maps). filled must not alias dispL. */
+size_t mccnn_lrc_fill_workspace_bytes(int H, int W);
+int mccnn_lrc_fill(const float* dispL, const uint8_t* flagL, float* filled, void* workspace, size_t workspace_bytes,
+                   int H, int W, void* stream);
 /* Median_Filter_kernel (:840-879) launched as at :1250: interior <- 5x5 median of `filled`,
  * 2-pixel border <- `wta` (the raw map). out may alias wta. */
 int mccnn_median5(const float* filled, const float* wta, float* out, int H, int W, void* stream);

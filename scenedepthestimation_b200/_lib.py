@@ -42,7 +42,8 @@ SIGNATURES = {
     "mccnn_wta": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mccnn_wta_dhw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mccnn_lr_flags": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
-    "mccnn_lrc_fill": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "mccnn_lrc_fill_workspace_bytes": (_sz, [_i, _i]),
+    "mccnn_lrc_fill": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "mccnn_median5": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mccnn_bilateral9": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mccnn_encode_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),

@@ -15,7 +15,7 @@ namespace {
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct PipeLayout {
-    size_t CL, CR, SL, SR, dl_wta, filled, flagL, sgm_ws, end;
+    size_t CL, CR, SL, SR, dl_wta, filled, flagL, sgm_ws, lrc_ws, end;
 };
 
 PipeLayout pipe_layout(int H, int W, int D) {
@@ -31,6 +31,7 @@ PipeLayout pipe_layout(int H, int W, int D) {
     l.filled = o; o += map;
     l.flagL = o; o += align_up((size_t)H * W);
     l.sgm_ws = o; o += align_up(mccnn_sgm_workspace_bytes(H, W, D));
+    l.lrc_ws = o; o += align_up(mccnn_lrc_fill_workspace_bytes(H, W));
     l.end = o;
     return l;
 }
@@ -113,7 +114,7 @@ static int run_pipeline(const uint8_t* imageL, const uint8_t* imageR, const floa
         return e;
     if (int e = tm.mark()) return e;  // [3] SGM (+ fused WTA)
     if (int e = mccnn_lr_flags(dl_wta, dispR_out, flagL, nullptr, H, W, stream)) return e;
-    if (int e = mccnn_lrc_fill(dl_wta, flagL, filled, H, W, stream)) return e;
+    if (int e = mccnn_lrc_fill(dl_wta, flagL, filled, ws + l.lrc_ws, mccnn_lrc_fill_workspace_bytes(H, W), H, W, stream)) return e;
     if (int e = tm.mark()) return e;  // [5] L-R check + fill
     if (int e = mccnn_median5(filled, dl_wta, dispL_out, H, W, stream)) return e;
     if (int e = tm.mark()) return e;  // [6] filter

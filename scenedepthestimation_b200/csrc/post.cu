@@ -77,32 +77,79 @@ __global__ void lr_flags_kernel(const float* __restrict__ dl, const float* __res
     }
 }
 
-// ---- occlusion fill (:1003-1088): mean of the nearest unflagged raw disparity up, down, right, left
-__global__ void lrc_fill_kernel(const float* __restrict__ dl, const unsigned char* __restrict__ fl, float* __restrict__ out,
-                                int H, int W) {
+// ---- occlusion fill (:1003-1088): mean of the nearest unflagged raw disparity up, down, right, left.
+// The reference walks four data-dependent while-loops per flagged pixel; here the four "nearest unflagged
+// value" maps are running carries: two column sweeps (thread per column, coalesced along x) and two row
+// sweeps (warp per row, 32-pixel chunks, ballot + shuffle), O(H*W) work whatever the flag pattern.
+// Disparities are >= 0, so -1 marks "none found".
+__global__ void __launch_bounds__(128) lrc_vertical_kernel(const float* __restrict__ dl, const unsigned char* __restrict__ fl,
+                                                          float* __restrict__ up, float* __restrict__ down, int H, int W) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
     if (x >= W) return;
-    const size_t o = (size_t)y * W + x;
-    if (fl[o] != 1) {
-        out[o] = dl[o];
-        return;
+    float carry = -1.0f;
+#pragma unroll 8
+    for (int y = 0; y < H; y++) {
+        const size_t o = (size_t)y * W + x;
+        const unsigned char f = fl[o];
+        const float v = dl[o];
+        if (f == 1) up[o] = carry; else carry = v;
     }
-    int number = 0;
-    double sum_d = 0.0;
-    int idy = y;
-    while (idy >= 0 && fl[(size_t)idy * W + x] == 1) idy--;
-    if (idy >= 0) { number++; sum_d += (double)dl[(size_t)idy * W + x]; }
-    idy = y;
-    while (idy < H && fl[(size_t)idy * W + x] == 1) idy++;
-    if (idy < H) { number++; sum_d += (double)dl[(size_t)idy * W + x]; }
-    int idx = x;
-    while (idx < W && fl[(size_t)y * W + idx] == 1) idx++;
-    if (idx < W) { number++; sum_d += (double)dl[(size_t)y * W + idx]; }
-    idx = x;
-    while (idx >= 0 && fl[(size_t)y * W + idx] == 1) idx--;
-    if (idx >= 0) { number++; sum_d += (double)dl[(size_t)y * W + idx]; }
-    out[o] = number > 0 ? (float)(sum_d / (double)number) : dl[o];
+    carry = -1.0f;
+#pragma unroll 8
+    for (int y = H - 1; y >= 0; y--) {
+        const size_t o = (size_t)y * W + x;
+        const unsigned char f = fl[o];
+        const float v = dl[o];
+        if (f == 1) down[o] = carry; else carry = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) lrc_horizontal_kernel(const float* __restrict__ dl, const unsigned char* __restrict__ fl,
+                                                            const float* __restrict__ up, const float* __restrict__ down,
+                                                            float* __restrict__ out, int H, int W) {
+    const int lane = threadIdx.x & 31;
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (y >= H) return;
+    const size_t ro = (size_t)y * W;
+    const int nchunks = (W + 31) / 32;
+    // sweep 1, right to left: nearest unflagged value to the right, parked in `out` at flagged pixels
+    float carry = -1.0f;
+    for (int c = nchunks - 1; c >= 0; c--) {
+        const int x = c * 32 + lane;
+        const bool inb = x < W;
+        const unsigned char f = inb ? fl[ro + x] : 1;
+        const float v = inb ? dl[ro + x] : 0.0f;
+        const unsigned m = __ballot_sync(0xffffffffu, inb && f != 1);
+        const unsigned right = m & (0xfffffffeu << lane);
+        const float rv = __shfl_sync(0xffffffffu, v, right ? __ffs(right) - 1 : 0);
+        if (inb && f == 1) out[ro + x] = right ? rv : carry;
+        if (m) carry = __shfl_sync(0xffffffffu, v, __ffs(m) - 1);
+    }
+    // sweep 2, left to right: nearest unflagged value to the left, then combine in the reference's order
+    carry = -1.0f;
+    for (int c = 0; c < nchunks; c++) {
+        const int x = c * 32 + lane;
+        const bool inb = x < W;
+        const unsigned char f = inb ? fl[ro + x] : 1;
+        const float v = inb ? dl[ro + x] : 0.0f;
+        const unsigned m = __ballot_sync(0xffffffffu, inb && f != 1);
+        const unsigned left = m & ((1u << lane) - 1u);
+        const float lv = __shfl_sync(0xffffffffu, v, left ? 31 - __clz(left) : 0);
+        if (inb) {
+            float r = v;
+            if (f == 1) {
+                const float cand[4] = {up[ro + x], down[ro + x], out[ro + x], left ? lv : carry};
+                int number = 0;
+                double sum_d = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (cand[i] >= 0.0f) { number++; sum_d += (double)cand[i]; }
+                if (number > 0) r = (float)(sum_d / (double)number);
+            }
+            out[ro + x] = r;
+        }
+        if (m) carry = __shfl_sync(0xffffffffu, v, 31 - __clz(m));
+    }
 }
 
 // ---- 5x5 median (:840-879): the 13th smallest of 25; the 2-pixel border keeps the raw WTA map
@@ -227,11 +274,23 @@ extern "C" int mccnn_lr_flags(const float* dispL, const float* dispR, uint8_t* f
     return 0;
 }
 
-extern "C" int mccnn_lrc_fill(const float* dispL, const uint8_t* flagL, float* filled, int H, int W, void* stream) {
-    MCCNN_REQUIRE(dispL && flagL && filled, MCCNN_EINVAL, "mccnn_lrc_fill: null argument");
+extern "C" size_t mccnn_lrc_fill_workspace_bytes(int H, int W) {
+    if (H < 1 || W < 1) return 0;
+    return 2 * (((size_t)H * W * sizeof(float) + 255) & ~(size_t)255);
+}
+
+extern "C" int mccnn_lrc_fill(const float* dispL, const uint8_t* flagL, float* filled, void* workspace, size_t workspace_bytes,
+                              int H, int W, void* stream) {
+    MCCNN_REQUIRE(dispL && flagL && filled && workspace, MCCNN_EINVAL, "mccnn_lrc_fill: null argument");
+    MCCNN_REQUIRE(dispL != filled, MCCNN_EINVAL, "mccnn_lrc_fill: output must not alias the input map");
     if (int e = check_hw("mccnn_lrc_fill", H, W)) return e;
-    lrc_fill_kernel<<<dim3(ceil_div(W, 128), H), 128, 0, (cudaStream_t)stream>>>(dispL, flagL, filled, H, W);
-    MCCNN_LAUNCH_CHECK("lrc_fill_kernel");
+    MCCNN_REQUIRE(workspace_bytes >= mccnn_lrc_fill_workspace_bytes(H, W), MCCNN_EWORKSPACE, "mccnn_lrc_fill: workspace too small");
+    float* up = reinterpret_cast<float*>(workspace);
+    float* down = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + mccnn_lrc_fill_workspace_bytes(H, W) / 2);
+    lrc_vertical_kernel<<<ceil_div(W, 128), 128, 0, (cudaStream_t)stream>>>(dispL, flagL, up, down, H, W);
+    MCCNN_LAUNCH_CHECK("lrc_vertical_kernel");
+    lrc_horizontal_kernel<<<ceil_div(H, 8), 256, 0, (cudaStream_t)stream>>>(dispL, flagL, up, down, filled, H, W);
+    MCCNN_LAUNCH_CHECK("lrc_horizontal_kernel");
     return 0;
 }
 

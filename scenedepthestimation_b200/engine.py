@@ -174,7 +174,10 @@ def lr_flags(dl, dr, right: bool = True):
 def lrc_fill(dl, flag_l):
     H, W = dl.shape
     out = torch.empty_like(dl)
-    _lib.check(_lib.load().mccnn_lrc_fill(_p(dl), _p(flag_l), _p(out), H, W, _stream()), "mccnn_lrc_fill")
+    lib = _lib.load()
+    nws = lib.mccnn_lrc_fill_workspace_bytes(H, W)
+    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mccnn_lrc_fill(_p(dl), _p(flag_l), _p(out), _p(ws), nws, H, W, _stream()), "mccnn_lrc_fill")
     return out
 
 

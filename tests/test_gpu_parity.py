@@ -239,6 +239,18 @@ def test_bilateral_encode_and_metric(eng):
     assert bad / (30 * 44) == st.bad_pixel_rate(u8, full, resize=False)
 
 
+@pytest.mark.parametrize("H,W,p", [(5, 7, 0.5), (40, 100, 0.9), (33, 65, 0.1), (9, 31, 1.0), (12, 200, 0.0), (64, 33, 0.97)])
+def test_lrc_fill_scan_vs_oracle(eng, H, W, p):
+    """Scan-based fill == the reference's four while-loops, for any flag density (incl. all / none flagged)."""
+    from oracle import stereo as st
+
+    rng = np.random.default_rng(int(H * W + 100 * p))
+    dl = rng.integers(0, 800, (H, W)).astype(np.float32)
+    fl = (rng.random((H, W)) < p).astype(np.uint8)
+    got = eng.lrc_fill(dev(dl), dev(fl)).cpu().numpy()
+    assert np.array_equal(got, st.lrc_fill(dl, fl))
+
+
 def test_errors_are_loud(eng):
     from scenedepthestimation_b200 import _lib
 
