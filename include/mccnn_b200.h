@@ -117,6 +117,33 @@ int mccnn_sgm(const float* CL, const float* CR, const uint8_t* imageL, const uin
               float* SL, float* SR, float* dispL, float* dispR,
               void* workspace, size_t workspace_bytes,
               int H, int W, int D, const mccnn_sgm_params* params, int mode, int keep_volumes, void* stream);
+/* ---- one pair split over several GPUs of a node ------------------------------
+ * Row-band sharding: rank r owns image rows [row0, row0 + rows) and holds only those rows of the cost / S volumes
+ * and of the output maps ([rows][W][Dp] / [rows][W]); the u8 images are whole on every rank (penalties). Horizontal
+ * paths are band-local. A vertical or diagonal scanline that crosses a band boundary is resumed by the next rank from
+ * the fp64 path state the previous rank wrote into that rank's exchange buffer over NVLink peer memory (state + flag,
+ * inside the scan kernel: no collective, no host round trip); the result is bit-identical to the unsharded run.
+ *  xchg_local: this rank's exchange buffer, mccnn_sgm_shard_exchange_bytes(W) bytes, peer-mapped on its neighbours
+ *  xchg_prev / xchg_next: peer-mapped device pointers to the neighbours' buffers (NULL at the ends)
+ *  epoch: non-zero, the same on every rank, different for every pair (flags are compared with it, never reset);
+ *         ranks must not start pair k+1 before their neighbours have finished pair k (one barrier per pair)
+ *  pass_mask: bit p launches pass p of 7 (0x7f = all); partial masks let a test run several bands on one GPU in
+ *         dependency order. */
+typedef struct {
+    int rank, world;
+    int H_full;
+    int row0, rows;
+    void* xchg_local;
+    void* xchg_prev;
+    void* xchg_next;
+    unsigned epoch;
+} mccnn_shard;
+size_t mccnn_sgm_shard_exchange_bytes(int W);
+int mccnn_sgm_sharded(const float* CLb, const float* CRb, const uint8_t* imageL, const uint8_t* imageR,
+                      float* SLb, float* SRb, float* dispLb, float* dispRb, void* workspace, size_t workspace_bytes,
+                      int W, int D, const mccnn_sgm_params* params, int mode, int keep_volumes,
+                      const mccnn_shard* shard, int pass_mask, void* stream);
+
 /* One path kernel on one volume, S += path (launch-for-launch twin of :1166-1202; for tests).
  * path: 0..7 in the reference's launch order. */
 int mccnn_sgm_single_path(const float* C, const uint8_t* image, float* S, void* workspace, size_t workspace_bytes,

@@ -17,6 +17,11 @@ class SgmParams(C.Structure):
                 ("threshold", C.c_int)]
 
 
+class Shard(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("H_full", C.c_int), ("row0", C.c_int), ("rows", C.c_int),
+                ("xchg_local", C.c_void_p), ("xchg_prev", C.c_void_p), ("xchg_next", C.c_void_p), ("epoch", C.c_uint)]
+
+
 _vp, _sz, _i, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_float
 _PP = C.POINTER(SgmParams)
 
@@ -38,6 +43,8 @@ SIGNATURES = {
     "mccnn_volume_to_dhw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mccnn_sgm_workspace_bytes": (_sz, [_i, _i, _i]),
     "mccnn_sgm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _PP, _i, _i, _vp]),
+    "mccnn_sgm_shard_exchange_bytes": (_sz, [_i]),
+    "mccnn_sgm_sharded": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _PP, _i, _i, C.POINTER(Shard), _i, _vp]),
     "mccnn_sgm_single_path": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _PP, _i, _vp]),
     "mccnn_wta": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mccnn_wta_dhw": (_i, [_vp, _vp, _i, _i, _i, _vp]),

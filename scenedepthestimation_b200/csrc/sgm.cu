@@ -45,13 +45,26 @@ struct SgmArgs {
     int threshold;
     int store_s;
     unsigned* counter;
+    // row-band sharding (one pair split over several GPUs): this launch owns image rows [row0, row0 + Hb); the
+    // volumes / maps it is given hold only those rows, the u8 images are whole. A scanline that enters the band
+    // from another rank resumes from the fp64 path state that rank left in hand_in (local memory, written by
+    // the peer over NVLink) once its flag shows `epoch`; a scanline that leaves the band publishes its state
+    // to hand_out (PEER memory). Unsharded: row0 = 0, Hb = H, both null.
+    int row0, Hb;
+    const double* hand_in;
+    const unsigned* flag_in;
+    double* hand_out;
+    unsigned* flag_out;
+    unsigned epoch;
 };
+
+constexpr int HAND_STRIDE = 1024 + 8;  // doubles per (side, scanline) slot: state of up to 1024 disparities + min
 
 constexpr int WARPS_PER_CTA = 4;
 
 __device__ __forceinline__ void scan_pixel(const SgmArgs& a, int line, int t, int& row, int& col) {
     if (a.horizontal) {
-        row = line;
+        row = a.row0 + line;
         col = a.dx > 0 ? t : a.W - 1 - t;
     } else {
         row = a.dy > 0 ? t : a.H - 1 - t;
@@ -72,6 +85,15 @@ __device__ __forceinline__ long long dkey(double v) {
 
 // inputs are never NaN: a plain compare-select (DSETP + 2 SEL) instead of fmin()'s NaN-propagating sequence
 __device__ __forceinline__ double dmin(double x, double y) { return x < y ? x : y; }
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ double warp_min_f64(double v) {
     long long k = dkey(v);
@@ -167,10 +189,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
         float* __restrict__ Sv = a.S[side];
         const unsigned char* __restrict__ img = a.img[side];
 
+        // steps of this scanline that fall into the band [row0, row0 + Hb)
+        int t_begin = 0, t_end = a.nsteps_total;
+        if (!a.horizontal) {
+            if (a.dy > 0) {
+                t_begin = a.row0;
+                t_end = min(a.nsteps_total, a.row0 + a.Hb);
+            } else {
+                t_begin = max(0, a.H - (a.row0 + a.Hb));
+                t_end = min(a.nsteps_total, a.H - a.row0);
+            }
+        }
+        if (t_begin >= t_end) continue;
+
         auto issue_load = [&](int t, uint32_t g) {
             int row, col;
             scan_pixel(a, line, t, row, col);
-            const size_t off = ((size_t)row * a.W + col) * pix_stride;
+            const size_t off = ((size_t)(row - a.row0) * a.W + col) * pix_stride;
             const int st = g % STAGES;
             float* dst = inbuf + (size_t)st * IN_BUFS * ROW;
             mbar_expect_tx(&bars[st], copy_bytes * IN_BUFS);
@@ -179,18 +214,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
         };
         auto image_at = [&](int t) -> int {
             int row, col;
-            scan_pixel(a, line, min(t, npix_line - 1), row, col);
+            scan_pixel(a, line, max(0, min(t, npix_line - 1)), row, col);
             return (int)img[(size_t)row * a.W + col];
         };
 
         if (lane == 0) {
-            const int pre = min(STAGES, a.nsteps_total);
-            for (int t = 0; t < pre; t++) issue_load(t, gstep + t);
+            const int pre = min(STAGES, t_end - t_begin);
+            for (int k = 0; k < pre; k++) issue_load(t_begin + k, gstep + k);
         }
         // image values: lane l of blk_cur holds I[pixel tb + 1 + l]
-        int i_cur = image_at(0);
-        int blk_cur = image_at(1 + lane);
-        int blk_next = image_at(33 + lane);
+        int i_cur = image_at(t_begin);
+        int blk_cur = image_at(t_begin + 1 + lane);
+        int blk_next = image_at(t_begin + 33 + lane);
 
         double L[NPL];
 #pragma unroll
@@ -198,7 +233,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
         double minL = 1.0, minLP2 = 1.0;
         bool edge_full = true;  // penalty class of the edge (t-1 -> t)
 
-        for (int t = 0; t < a.nsteps_total; t++) {
+        if (t_begin > 0 && t_begin < a.nsteps_dp) {
+            // resume a scanline started on another rank: wait for its state (fp64 L[], min over d)
+            const size_t slot = (size_t)side * a.nlines + line;
+            if (lane == 0)
+                while (ld_acquire_sys(a.flag_in + slot) != a.epoch) __nanosleep(64);
+            __syncwarp();
+            const double* src = a.hand_in + slot * HAND_STRIDE;
+#pragma unroll
+            for (int j = 0; j < NPL; j++) L[j] = __ldcv(src + lane * NPL + j);
+            minL = __ldcv(src + 1024);
+            const int dprev = i_cur - image_at(t_begin - 1);
+            edge_full = (dprev >= 0) && (dprev <= a.threshold);
+            minLP2 = minL + (edge_full ? a.P2 : a.P2r);
+        }
+
+        for (int t = t_begin; t < t_end; t++) {
             int row, col;
             scan_pixel(a, line, t, row, col);
             const int st = gstep % STAGES;
@@ -211,11 +261,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             // a warp barrier alone does not wait for outstanding shared loads, and an early refill (async
             // proxy) could overwrite the row under a still-queued LDS.
 
-            if ((t & 31) == 0 && t > 0) {
+            if (((t - t_begin) & 31) == 0 && t > t_begin) {
                 blk_cur = blk_next;
                 blk_next = image_at(t + 33 + lane);
             }
-            const int i_next = __shfl_sync(0xffffffffu, blk_cur, t & 31);
+            const int i_next = __shfl_sync(0xffffffffu, blk_cur, (t - t_begin) & 31);
             const int dn = i_next - i_cur;
             const bool next_full = (dn >= 0) && (dn <= a.threshold);
 
@@ -276,7 +326,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    bulk_s2g(Sv + ((size_t)row * a.W + col) * pix_stride, ob, copy_bytes);
+                    bulk_s2g(Sv + ((size_t)(row - a.row0) * a.W + col) * pix_stride, ob, copy_bytes);
                     bulk_commit();
                 }
                 ostep++;
@@ -297,12 +347,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
                 const unsigned who = __ballot_sync(0xffffffffu, k == mk);
                 const int src = __ffs(who) - 1;
                 const int idx = __shfl_sync(0xffffffffu, d0 + bj, src);
-                if (lane == 0) a.disp[side][(size_t)row * a.W + col] = (float)idx;
+                if (lane == 0) a.disp[side][(size_t)(row - a.row0) * a.W + col] = (float)idx;
             }
             // every lane's results (which depend on all of its cf/sf loads) are stored or reduced: refill the stage
             __syncwarp();
-            if (lane == 0 && t + STAGES < a.nsteps_total) issue_load(t + STAGES, gstep + STAGES);
+            if (lane == 0 && t + STAGES < t_end) issue_load(t + STAGES, gstep + STAGES);
             gstep++;
+        }
+        if (a.hand_out != nullptr && t_end < a.nsteps_dp) {
+            // the path continues on the neighbouring rank: publish the state over NVLink, then raise its flag
+            const size_t slot = (size_t)side * a.nlines + line;
+            double* dst = a.hand_out + slot * HAND_STRIDE;
+#pragma unroll
+            for (int j = 0; j < NPL; j++) dst[lane * NPL + j] = L[j];
+            if (lane == 0) dst[1024] = minL;
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) st_release_sys(a.flag_out + slot, a.epoch);
         }
     }
     if (lane == 0) bulk_wait_all<0>();
@@ -356,10 +417,11 @@ const int kPathDy[8] = {1, -1, 0, 0, 1, -1, 1, -1};
 const int kPathDx[8] = {0, 0, 1, -1, 1, 1, -1, -1};
 
 void set_path(SgmArgs& a, int path) {
+    if (a.Hb == 0) { a.row0 = 0; a.Hb = a.H; }
     a.dy = kPathDy[path];
     a.dx = kPathDx[path];
     a.horizontal = (a.dy == 0);
-    a.nlines = a.horizontal ? a.H : a.W;
+    a.nlines = a.horizontal ? a.Hb : a.W;
     a.nsteps_dp = (a.horizontal ? a.W : a.H) - 1;
     a.nsteps_total = a.nsteps_dp;
 }
@@ -389,6 +451,61 @@ extern "C" size_t mccnn_sgm_workspace_bytes(int H, int W, int D) {
     return 256;  // 8 scanline counters
 }
 
+static int run_sgm(const float* CL, const float* CR, const uint8_t* imageL, const uint8_t* imageR, float* SL, float* SR,
+                   float* dispL, float* dispR, void* workspace, int H, int W, int D, const mccnn_sgm_params* params,
+                   int keep_volumes, const mccnn_shard* sh, int pass_mask, cudaStream_t stream) {
+    unsigned* counters = reinterpret_cast<unsigned*>(workspace);
+    MCCNN_CUDA(cudaMemsetAsync(counters, 0, 256, stream));
+
+    SgmArgs a{};
+    a.C[0] = CL; a.C[1] = CR;
+    a.S[0] = SL; a.S[1] = SR;
+    a.img[0] = imageL; a.img[1] = imageR;
+    a.disp[0] = dispL; a.disp[1] = dispR;
+    a.H = H; a.W = W; a.D = D; a.Dp = disp_pitch(D);
+    a.nsides = 2;
+    set_params(a, params);
+    a.row0 = sh ? sh->row0 : 0;
+    a.Hb = sh ? sh->rows : H;
+    a.epoch = sh ? sh->epoch : 0;
+
+    // pass -> reference path: pass 0 = down (+ the up path's raw-cost add), 1..5 = right, left, down-right, up-right,
+    // down-left, 6 = up-left + winner-takes-all (also visits row 0, which the path skips)
+    static const int kPassPath[7] = {0, 2, 3, 4, 5, 6, 7};
+    const size_t slot_doubles = (size_t)2 * W * HAND_STRIDE;
+    for (int pass = 0; pass < 7; pass++) {
+        if (!(pass_mask & (1 << pass))) continue;
+        set_path(a, kPassPath[pass]);
+        if (pass == 0 || pass == 6) a.nsteps_total = H;
+        a.store_s = (pass == 6 && !keep_volumes) ? 0 : 1;
+        a.counter = counters + pass;
+        a.hand_in = nullptr; a.flag_in = nullptr; a.hand_out = nullptr; a.flag_out = nullptr;
+        if (sh && sh->world > 1 && !a.horizontal) {
+            // a rank receives from the rank the path comes from and publishes to the rank it runs into
+            const bool down = a.dy > 0;
+            char* from_me = reinterpret_cast<char*>(sh->xchg_local);
+            char* to_peer = reinterpret_cast<char*>(down ? sh->xchg_next : sh->xchg_prev);
+            const bool has_in = down ? sh->rank > 0 : sh->rank < sh->world - 1;
+            const bool has_out = down ? sh->rank < sh->world - 1 : sh->rank > 0;
+            const size_t flags_off = (size_t)7 * slot_doubles * sizeof(double);
+            if (has_in) {
+                a.hand_in = reinterpret_cast<const double*>(from_me) + (size_t)pass * slot_doubles;
+                a.flag_in = reinterpret_cast<const unsigned*>(from_me + flags_off) + (size_t)pass * 2 * W;
+            }
+            if (has_out) {
+                MCCNN_REQUIRE(to_peer != nullptr, MCCNN_EINVAL, "mccnn_sgm_sharded: missing peer exchange pointer");
+                a.hand_out = reinterpret_cast<double*>(to_peer) + (size_t)pass * slot_doubles;
+                a.flag_out = reinterpret_cast<unsigned*>(to_peer + flags_off) + (size_t)pass * 2 * W;
+            }
+        }
+        int e = pass == 0 ? dispatch_scan<SGM_FIRST_FUSED>(a, stream)
+                : pass == 6 ? dispatch_scan<SGM_LAST_WTA>(a, stream)
+                            : dispatch_scan<SGM_MID>(a, stream);
+        if (e) return e;
+    }
+    return 0;
+}
+
 extern "C" int mccnn_sgm(const float* CL, const float* CR, const uint8_t* imageL, const uint8_t* imageR, float* SL,
                          float* SR, float* dispL, float* dispR, void* workspace, size_t workspace_bytes, int H, int W,
                          int D, const mccnn_sgm_params* params, int mode, int keep_volumes, void* stream_) {
@@ -401,37 +518,39 @@ extern "C" int mccnn_sgm(const float* CL, const float* CR, const uint8_t* imageL
     MCCNN_REQUIRE(aligned16(CL) && aligned16(CR) && aligned16(SL) && aligned16(SR), MCCNN_EALIGN,
                   "mccnn_sgm: volumes must be 16-byte aligned");
     MCCNN_REQUIRE(params->P1 >= 0 && params->P1_red >= 0, MCCNN_EINVAL, "mccnn_sgm: negative P1");
+    return run_sgm(CL, CR, imageL, imageR, SL, SR, dispL, dispR, workspace, H, W, D, params, keep_volumes, nullptr, 0x7f, stream);
+}
 
-    unsigned* counters = reinterpret_cast<unsigned*>(workspace);
-    MCCNN_CUDA(cudaMemsetAsync(counters, 0, 256, stream));
+extern "C" size_t mccnn_sgm_shard_exchange_bytes(int W) {
+    if (W < 1) return 0;
+    const size_t payload = (size_t)7 * 2 * W * HAND_STRIDE * sizeof(double);
+    const size_t flags = (size_t)7 * 2 * W * sizeof(unsigned);
+    return (payload + flags + 255) & ~(size_t)255;
+}
 
-    SgmArgs a{};
-    a.C[0] = CL; a.C[1] = CR;
-    a.S[0] = SL; a.S[1] = SR;
-    a.img[0] = imageL; a.img[1] = imageR;
-    a.disp[0] = dispL; a.disp[1] = dispR;
-    a.H = H; a.W = W; a.D = D; a.Dp = disp_pitch(D);
-    a.nsides = 2;
-    a.store_s = 1;
-    set_params(a, params);
-
-    // pass 0: down path fused with the up path's raw-cost add (paths 0 and 1); writes S without reading it
-    set_path(a, 0);
-    a.nsteps_total = H;
-    a.counter = counters + 0;
-    if (int e = dispatch_scan<SGM_FIRST_FUSED>(a, stream)) return e;
-    // passes 1..5: right, left, down-right, up-right, down-left
-    for (int path = 2; path <= 6; path++) {
-        set_path(a, path);
-        a.counter = counters + (path - 1);
-        if (int e = dispatch_scan<SGM_MID>(a, stream)) return e;
-    }
-    // pass 6: up-left + winner-takes-all; also visits row 0, which the path skips
-    set_path(a, 7);
-    a.nsteps_total = H;
-    a.store_s = keep_volumes ? 1 : 0;
-    a.counter = counters + 6;
-    return dispatch_scan<SGM_LAST_WTA>(a, stream);
+extern "C" int mccnn_sgm_sharded(const float* CLb, const float* CRb, const uint8_t* imageL, const uint8_t* imageR, float* SLb,
+                                 float* SRb, float* dispLb, float* dispRb, void* workspace, size_t workspace_bytes, int W,
+                                 int D, const mccnn_sgm_params* params, int mode, int keep_volumes, const mccnn_shard* shard,
+                                 int pass_mask, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MCCNN_REQUIRE(shard != nullptr, MCCNN_EINVAL, "mccnn_sgm_sharded: null shard");
+    const int H = shard->H_full;
+    if (int e = check_common(CLb, H, W, D)) return e;
+    MCCNN_REQUIRE(CRb && SLb && SRb && imageL && imageR && dispLb && dispRb && params && workspace, MCCNN_EINVAL,
+                  "mccnn_sgm_sharded: null argument");
+    MCCNN_REQUIRE(mode == MCCNN_SGM_EXACT, MCCNN_EINVAL, "mccnn_sgm_sharded: unknown mode %d", mode);
+    MCCNN_REQUIRE(workspace_bytes >= mccnn_sgm_workspace_bytes(H, W, D), MCCNN_EWORKSPACE, "mccnn_sgm_sharded: workspace too small");
+    MCCNN_REQUIRE(aligned16(CLb) && aligned16(CRb) && aligned16(SLb) && aligned16(SRb), MCCNN_EALIGN,
+                  "mccnn_sgm_sharded: volumes must be 16-byte aligned");
+    MCCNN_REQUIRE(shard->world >= 1 && shard->rank >= 0 && shard->rank < shard->world && shard->rows >= 1 && shard->row0 >= 0 &&
+                      shard->row0 + shard->rows <= H,
+                  MCCNN_EINVAL, "mccnn_sgm_sharded: bad band rank=%d/%d rows [%d,+%d) of %d", shard->rank, shard->world,
+                  shard->row0, shard->rows, H);
+    MCCNN_REQUIRE(shard->world == 1 || (shard->xchg_local != nullptr && shard->epoch != 0), MCCNN_EINVAL,
+                  "mccnn_sgm_sharded: exchange buffer and a non-zero epoch are required");
+    MCCNN_REQUIRE(params->P1 >= 0 && params->P1_red >= 0, MCCNN_EINVAL, "mccnn_sgm_sharded: negative P1");
+    return run_sgm(CLb, CRb, imageL, imageR, SLb, SRb, dispLb, dispRb, workspace, H, W, D, params, keep_volumes, shard,
+                   pass_mask & 0x7f, stream);
 }
 
 extern "C" int mccnn_sgm_single_path(const float* C, const uint8_t* image, float* S, void* workspace,

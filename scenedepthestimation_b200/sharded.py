@@ -1,0 +1,141 @@
+"""One stereo pair split over the GPUs of a node by image rows (BASELINE config 4 at N > 1).
+
+Rank r owns rows [row0, row0 + rows). What crosses NVLink:
+  * the u8 image bands are all-gathered once (11 MB for the full-res pair): every rank needs whole images for
+    the SGM penalties, and the gather also provides the 5-row conv halos and the global mean / std;
+  * conv tower, cost volume and the horizontal SGM paths are band-local;
+  * vertical / diagonal SGM scanlines resume on the next rank from the fp64 path state the previous rank stored
+    into its neighbour's exchange buffer from INSIDE the scan kernel (peer stores + a release flag; no collective,
+    no host round trip): 5 passes x 2 sides x W scanlines x (D + 1) doubles per boundary;
+  * the two raw WTA bands are all-gathered (23 MB each) and the cheap L-R check / fill / median run on the whole map.
+The result is bit-identical to the single-GPU path.
+
+torch.distributed provides the process group and torch's symmetric memory the peer-mapped exchange buffers.
+`emulate_bands` runs the same band kernels for several "ranks" on ONE GPU in dependency order (tests).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import engine as eng
+
+PASS_DOWNWARD = (True, None, None, True, False, True, False)  # pass -> sweeps down / band-local / sweeps up
+
+
+def band_rows(H: int, world: int):
+    """Even split of H rows: [(row0, rows)] per rank."""
+    base, extra = divmod(H, world)
+    out, r0 = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append((r0, n))
+        r0 += n
+    return out
+
+
+def _shard(rank, world, H, row0, rows, local, prev, nxt, epoch) -> _lib.Shard:
+    return _lib.Shard(rank, world, H, row0, rows, local, prev, nxt, epoch)
+
+
+def sgm_band(CLb, CRb, il_full, ir_full, D, shard: _lib.Shard, pass_mask=0x7F, keep_volumes=True, out=None, params=None):
+    """mccnn_sgm_sharded on this rank's band -> (SLb, SRb, dispLb, dispRb)."""
+    lib = _lib.load()
+    rows, W, _ = CLb.shape
+    params = params or _lib.default_sgm_params()
+    if out is None:
+        out = (torch.empty_like(CLb), torch.empty_like(CRb),
+               torch.empty((rows, W), dtype=torch.float32, device="cuda"), torch.empty((rows, W), dtype=torch.float32, device="cuda"))
+    SLb, SRb, dl, dr = out
+    nws = lib.mccnn_sgm_workspace_bytes(shard.H_full, W, D)
+    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mccnn_sgm_sharded(CLb.data_ptr(), CRb.data_ptr(), il_full.data_ptr(), ir_full.data_ptr(), SLb.data_ptr(),
+                                     SRb.data_ptr(), dl.data_ptr(), dr.data_ptr(), ws.data_ptr(), nws, W, D, C.byref(params),
+                                     eng.EXACT, 1 if keep_volumes else 0, C.byref(shard), pass_mask,
+                                     torch.cuda.current_stream().cuda_stream), "mccnn_sgm_sharded")
+    return out
+
+
+def emulate_bands(CL, CR, il, ir, D, world: int, epoch: int = 1):
+    """Run `world` row bands of one pair on ONE GPU, pass by pass in dependency order (a band never waits: the band
+    it depends on has already finished its launch). Returns (SL, SR, dispL, dispR) assembled from the bands."""
+    lib = _lib.load()
+    H, W, _ = CL.shape
+    bands = band_rows(H, world)
+    nx = lib.mccnn_sgm_shard_exchange_bytes(W)
+    xchg = [torch.zeros(nx, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    SL, SR = torch.empty_like(CL), torch.empty_like(CR)
+    dl = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    dr = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    shards = []
+    for r, (r0, n) in enumerate(bands):
+        shards.append(_shard(r, world, H, r0, n, xchg[r].data_ptr(), xchg[r - 1].data_ptr() if r > 0 else None,
+                             xchg[r + 1].data_ptr() if r < world - 1 else None, epoch))
+    for p in range(7):
+        order = range(world) if PASS_DOWNWARD[p] in (True, None) else range(world - 1, -1, -1)
+        for r in order:
+            r0, n = bands[r]
+            sgm_band(CL[r0:r0 + n], CR[r0:r0 + n], il, ir, D, shards[r], pass_mask=1 << p,
+                     out=(SL[r0:r0 + n], SR[r0:r0 + n], dl[r0:r0 + n], dr[r0:r0 + n]))
+    return SL, SR, dl, dr
+
+
+class ShardedMatcher:
+    """One pair per call, split by rows over the ranks of `group` (one process per GPU, NCCL)."""
+
+    def __init__(self, H: int, W: int, D: int, weights: dict, num_layers: int = 5, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.dist = dist
+        self.group = group or dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.H, self.W, self.D, self.nl = H, W, D, num_layers
+        self.bands = band_rows(H, self.world)
+        self.row0, self.rows = self.bands[self.rank]
+        if len({n for _, n in self.bands}) != 1:
+            raise ValueError("ShardedMatcher needs H divisible by the world size (equal bands for all_gather)")
+        self.packed = eng.pack_weights(weights, num_layers)
+        lib = _lib.load()
+        nx = lib.mccnn_sgm_shard_exchange_bytes(W)
+        self.xchg = symm_mem.empty(nx, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        self.xchg.zero_()
+        self.handle = symm_mem.rendezvous(self.xchg, self.group)
+        ptrs = list(self.handle.buffer_ptrs)
+        self.prev = ptrs[self.rank - 1] if self.rank > 0 else None
+        self.next = ptrs[self.rank + 1] if self.rank < self.world - 1 else None
+        self.epoch = 0
+        Dp = eng.disp_pitch(D)
+        self.S = (torch.empty((self.rows, W, Dp), dtype=torch.float32, device="cuda"),
+                  torch.empty((self.rows, W, Dp), dtype=torch.float32, device="cuda"))
+        self.il = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+        self.ir = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+        self.dl = torch.empty((H, W), dtype=torch.float32, device="cuda")
+        self.dr = torch.empty((H, W), dtype=torch.float32, device="cuda")
+        self.dlb = torch.empty((self.rows, W), dtype=torch.float32, device="cuda")
+        self.drb = torch.empty((self.rows, W), dtype=torch.float32, device="cuda")
+
+    def match(self, il_band: torch.Tensor, ir_band: torch.Tensor):
+        """u8 bands [rows, W] of this rank -> (filtered left disparity, raw right WTA), whole maps on every rank."""
+        dist, nl = self.dist, self.nl
+        dist.all_gather_into_tensor(self.il, il_band.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(self.ir, ir_band.contiguous(), group=self.group)
+        r0, n = self.row0, self.rows
+        feats = []
+        for img in (self.il, self.ir):
+            padded = eng.standardize_pad(img, nl)          # global statistics, zero padding at the image borders
+            feats.append(eng.conv_tower(padded[r0:r0 + n + 2 * nl], self.packed, nl))  # band + 5-row halos
+        CL, CR = eng.cost_volume(feats[0], feats[1], self.D)
+        # neighbours must have finished the previous pair before their exchange slots are written again
+        dist.barrier(group=self.group)
+        self.epoch += 1
+        shard = _shard(self.rank, self.world, self.H, r0, n, self.xchg.data_ptr(), self.prev, self.next, self.epoch)
+        sgm_band(CL, CR, self.il, self.ir, self.D, shard, keep_volumes=False, out=(self.S[0], self.S[1], self.dlb, self.drb))
+        dist.all_gather_into_tensor(self.dl, self.dlb, group=self.group)
+        dist.all_gather_into_tensor(self.dr, self.drb, group=self.group)
+        fl, _ = eng.lr_flags(self.dl, self.dr, right=False)
+        filled = eng.lrc_fill(self.dl, fl)
+        return eng.median5(filled, self.dl), self.dr

@@ -251,6 +251,21 @@ def test_lrc_fill_scan_vs_oracle(eng, H, W, p):
     assert np.array_equal(got, st.lrc_fill(dl, fl))
 
 
+@pytest.mark.parametrize("H,W,D,world", [(12, 40, 48, 2), (13, 21, 20, 3), (30, 9, 16, 4), (5, 33, 128, 3), (16, 50, 800, 2), (9, 64, 33, 8)])
+def test_row_band_sharded_sgm_equals_unsharded(eng, H, W, D, world):
+    """Row bands + fp64 path-state hand-off between bands (the multi-GPU single-pair path), emulated on one GPU
+    by launching the bands pass by pass in dependency order: bit-identical S volumes and WTA maps."""
+    from scenedepthestimation_b200 import sharded, synthetic as syn
+
+    il, ir = syn.noise_pair(H, W, H + W + D)
+    fl, fr = syn.unit_features(H, W, 64, H * W + D)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    ref = eng.sgm(CL, CR, dev(il), dev(ir), D, keep_volumes=True)
+    got = sharded.emulate_bands(CL, CR, dev(il), dev(ir), D, world, epoch=7)
+    for a, b, name in zip(ref, got, ("SL", "SR", "dispL", "dispR")):
+        assert torch.equal(a[..., :D] if a.dim() == 3 else a, b[..., :D] if b.dim() == 3 else b), name
+
+
 def test_errors_are_loud(eng):
     from scenedepthestimation_b200 import _lib
 
