@@ -96,8 +96,7 @@ class ShardedMatcher:
         self.H, self.W, self.D, self.nl = H, W, D, num_layers
         self.bands = band_rows(H, self.world)
         self.row0, self.rows = self.bands[self.rank]
-        if len({n for _, n in self.bands}) != 1:
-            raise ValueError("ShardedMatcher needs H divisible by the world size (equal bands for all_gather)")
+        self.max_rows = max(n for _, n in self.bands)  # bands may differ by one row: gathers are padded to this
         self.packed = eng.pack_weights(weights, num_layers)
         lib = _lib.load()
         nx = lib.mccnn_sgm_shard_exchange_bytes(W)
@@ -115,15 +114,26 @@ class ShardedMatcher:
         self.ir = torch.empty((H, W), dtype=torch.uint8, device="cuda")
         self.dl = torch.empty((H, W), dtype=torch.float32, device="cuda")
         self.dr = torch.empty((H, W), dtype=torch.float32, device="cuda")
-        self.dlb = torch.empty((self.rows, W), dtype=torch.float32, device="cuda")
-        self.drb = torch.empty((self.rows, W), dtype=torch.float32, device="cuda")
+        # [left | right] band of this rank, padded to max_rows, and the gathered stacks
+        self.u8_send = torch.zeros((2, self.max_rows, W), dtype=torch.uint8, device="cuda")
+        self.u8_recv = torch.empty((self.world, 2, self.max_rows, W), dtype=torch.uint8, device="cuda")
+        self.f_send = torch.zeros((2, self.max_rows, W), dtype=torch.float32, device="cuda")
+        self.f_recv = torch.empty((self.world, 2, self.max_rows, W), dtype=torch.float32, device="cuda")
+
+    def _gather(self, send, recv, left_full, right_full):
+        """One all_gather of the (padded) [left | right] bands, then the valid rows are laid out as whole maps."""
+        self.dist.all_gather_into_tensor(recv, send, group=self.group)
+        for r, (r0, n) in enumerate(self.bands):
+            left_full[r0:r0 + n].copy_(recv[r, 0, :n])
+            right_full[r0:r0 + n].copy_(recv[r, 1, :n])
 
     def match(self, il_band: torch.Tensor, ir_band: torch.Tensor):
         """u8 bands [rows, W] of this rank -> (filtered left disparity, raw right WTA), whole maps on every rank."""
         dist, nl = self.dist, self.nl
-        dist.all_gather_into_tensor(self.il, il_band.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(self.ir, ir_band.contiguous(), group=self.group)
         r0, n = self.row0, self.rows
+        self.u8_send[0, :n].copy_(il_band)
+        self.u8_send[1, :n].copy_(ir_band)
+        self._gather(self.u8_send, self.u8_recv, self.il, self.ir)
         feats = []
         for img in (self.il, self.ir):
             padded = eng.standardize_pad(img, nl)          # global statistics, zero padding at the image borders
@@ -133,9 +143,9 @@ class ShardedMatcher:
         dist.barrier(group=self.group)
         self.epoch += 1
         shard = _shard(self.rank, self.world, self.H, r0, n, self.xchg.data_ptr(), self.prev, self.next, self.epoch)
-        sgm_band(CL, CR, self.il, self.ir, self.D, shard, keep_volumes=False, out=(self.S[0], self.S[1], self.dlb, self.drb))
-        dist.all_gather_into_tensor(self.dl, self.dlb, group=self.group)
-        dist.all_gather_into_tensor(self.dr, self.drb, group=self.group)
+        sgm_band(CL, CR, self.il, self.ir, self.D, shard, keep_volumes=False,
+                 out=(self.S[0], self.S[1], self.f_send[0, :n], self.f_send[1, :n]))
+        self._gather(self.f_send, self.f_recv, self.dl, self.dr)
         fl, _ = eng.lr_flags(self.dl, self.dr, right=False)
         filled = eng.lrc_fill(self.dl, fl)
         return eng.median5(filled, self.dl), self.dr

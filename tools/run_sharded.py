@@ -12,7 +12,6 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W, H, D = syn.CONFIGS[cfg]
-    H -= H % world
     il, ir, _ = syn.textured_pair(H, W, D, 77)
     weights = syn.glorot_weights()
     m = sharded.ShardedMatcher(H, W, D, weights)
