@@ -52,6 +52,10 @@ typedef struct {
     float P1_red;   /* fp32(2.3 / 4)   :141 */
     float P2_red;   /* fp32(55.9 / 4)  :142 */
     int threshold;  /* 30    :1143 */
+    /* Stages the reference holds but does not run (both 0 = the reference's behaviour; their parity is unpinned): */
+    int subpixel;   /* 1: parabola refinement of the WTA index, the formula commented out at :813-819 */
+    int bilateral;  /* 1: the 9x9 bilateral filter whose launch is commented out at :1260; as in that launch it reads
+                       the filled map and overwrites the median output */
 } mccnn_sgm_params;
 
 const char* mccnn_last_error(void);
@@ -169,6 +173,12 @@ int mccnn_median5(const float* filled, const float* wta, float* out, int H, int 
 int mccnn_bilateral9(const uint8_t* image, const float* disp, float* out, int H, int W, void* stream);
 /* astype('uint8') [* scale] of match_single.py:55 / match.py:90 (truncation toward zero, wrap mod 256). */
 int mccnn_encode_u8(const float* disp, uint8_t* out, int H, int W, int scale, void* stream);
+/* 16-bit variant for disparity ranges above 255 (the reference's uint8 PNG overflows there): fixed point with
+ * `frac_bits` fractional bits, saturating. */
+int mccnn_encode_u16(const float* disp, uint16_t* out, int H, int W, int frac_bits, void* stream);
+/* Stand-alone WTA with the parabola refinement of :813-819 (own definition where the reference is silent:
+ * the index is kept when it sits on the range border or the parabola is flat). */
+int mccnn_wta_subpixel(const float* S, float* disp, int H, int W, int D, void* stream);
 /* error_calculate.py:68-83 on the device: counts[0] = bad pixels, counts[1] = valid GT pixels.
  * gt_half is the ground truth already resized and halved (fp32 [H][W]). */
 int mccnn_bad_pixels(const uint8_t* disp_u8, const float* gt_half, unsigned long long* counts2,

@@ -256,6 +256,34 @@ def wta(svol):
 
 
 @njit(parallel=True, cache=True)
+def wta_subpixel(svol):
+    """WTA + the parabola refinement the reference left commented out (:813-819): "parity unpinned". Typing as Numba
+    would infer it: fp32 differences, `2 * (...)` promotes the denominator to fp64. Own definition where the
+    reference is silent: border indices (the reference tests 0 < index < 127) and a flat parabola keep the index."""
+    rows, cols, ndisp = svol.shape
+    out = np.zeros((rows, cols), np.float32)
+    for y in prange(rows):
+        for x in range(cols):
+            min_s = svol[y, x, 0]
+            index = 0
+            for i in range(1, ndisp):
+                tmp = svol[y, x, i]
+                if min_s > tmp:
+                    min_s = tmp
+                    index = i
+            min_index = np.float64(index)
+            if index > 0 and index < ndisp - 1:
+                c = svol[y, x, index]
+                _c = svol[y, x, index - 1]
+                c_ = svol[y, x, index + 1]
+                den = 2 * (_c + c_ - 2 * c)
+                if den > 0:
+                    min_index = index - (c_ - _c) / den
+            out[y, x] = min_index
+    return out
+
+
+@njit(parallel=True, cache=True)
 def wta_dhw(vol_dhw):
     """CPU WTA1, process_functional.py:96-113: argmin with strict <, layout [D,H,W]."""
     ndisp, rows, cols = vol_dhw.shape

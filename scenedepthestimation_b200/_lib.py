@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmccnn_b200.so")
 
 class SgmParams(C.Structure):
     _fields_ = [("P1", C.c_float), ("P2", C.c_float), ("P1_red", C.c_float), ("P2_red", C.c_float),
-                ("threshold", C.c_int)]
+                ("threshold", C.c_int), ("subpixel", C.c_int), ("bilateral", C.c_int)]
 
 
 class Shard(C.Structure):
@@ -54,6 +54,8 @@ SIGNATURES = {
     "mccnn_median5": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mccnn_bilateral9": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mccnn_encode_u8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mccnn_encode_u16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mccnn_wta_subpixel": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mccnn_bad_pixels": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mccnn_pipeline_workspace_bytes": (_sz, [_i, _i, _i]),
     "mccnn_disparity_pipeline": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _PP, _i, _vp, _vp]),

@@ -45,6 +45,8 @@ extern "C" void mccnn_default_sgm_params(mccnn_sgm_params* p) {
     p->P1_red = (float)(2.3 / 4);
     p->P2_red = (float)(55.9 / 4);
     p->threshold = 30;
+    p->subpixel = 0;
+    p->bilateral = 0;
 }
 
 extern "C" int mccnn_device_supported(int device) {

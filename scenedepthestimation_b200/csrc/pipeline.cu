@@ -117,6 +117,9 @@ static int run_pipeline(const uint8_t* imageL, const uint8_t* imageR, const floa
     if (int e = mccnn_lrc_fill(dl_wta, flagL, filled, ws + l.lrc_ws, mccnn_lrc_fill_workspace_bytes(H, W), H, W, stream)) return e;
     if (int e = tm.mark()) return e;  // [5] L-R check + fill
     if (int e = mccnn_median5(filled, dl_wta, dispL_out, H, W, stream)) return e;
+    // the reference's (commented-out) bilateral launch reads the FILLED map and overwrites the median output (:1260)
+    if (params->bilateral)
+        if (int e = mccnn_bilateral9(imageL, filled, dispL_out, H, W, stream)) return e;
     if (int e = tm.mark()) return e;  // [6] filter
     return 0;
 }

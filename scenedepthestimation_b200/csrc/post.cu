@@ -34,6 +34,35 @@ __global__ void __launch_bounds__(256) wta_kernel(const float* __restrict__ S, f
     if (lane == 0) disp[pix] = (float)md;
 }
 
+// ---- WTA + parabola refinement (:813-819), same typing as sgm.cu's subpixel_refine
+__global__ void __launch_bounds__(256) wta_subpixel_kernel(const float* __restrict__ S, float* __restrict__ disp, int npix,
+                                                          int D, int Dp) {
+    const int lane = threadIdx.x & 31;
+    const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pix >= npix) return;
+    const float* row = S + (size_t)pix * Dp;
+    float best = __int_as_float(0x7f800000);
+    int bd = 0x7fffffff;
+    for (int d = lane; d < D; d += 32) {
+        const float v = row[d] + 0.0f;
+        if (v < best) { best = v; bd = d; }
+    }
+    int k = __float_as_int(best);
+    k ^= (k >> 31) & 0x7fffffff;
+    const int mk = __reduce_min_sync(0xffffffffu, k);
+    const int md = __reduce_min_sync(0xffffffffu, k == mk ? bd : 0x7fffffff);
+    if (lane == 0) {
+        float out = (float)md;
+        if (md > 0 && md < D - 1) {
+            const float cm = row[md - 1], c = row[md], cp = row[md + 1];
+            const float num = cp - cm;
+            const double den = 2.0 * ((double)(cm + cp) - 2.0 * (double)c);
+            if (den > 0.0) out = (float)((double)md - (double)num / den);
+        }
+        disp[pix] = out;
+    }
+}
+
 // ---- WTA over dense [D][H][W] (CPU WTA1): thread per pixel, coalesced along x
 __global__ void wta_dhw_kernel(const float* __restrict__ vol, float* __restrict__ disp, int npix, int D) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,6 +246,13 @@ __global__ void encode_u8_kernel(const float* __restrict__ disp, unsigned char* 
     out[i] = (unsigned char)((v & 255u) * (unsigned)scale);
 }
 
+__global__ void encode_u16_kernel(const float* __restrict__ disp, unsigned short* __restrict__ out, size_t n, float scale) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = disp[i] * scale;
+    out[i] = (unsigned short)(v <= 0.f ? 0.f : (v >= 65535.f ? 65535.f : v));
+}
+
 __global__ void bad_pixels_kernel(const unsigned char* __restrict__ disp, const float* __restrict__ gt,
                                   unsigned long long* __restrict__ counts, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -317,6 +353,26 @@ extern "C" int mccnn_encode_u8(const float* disp, uint8_t* out, int H, int W, in
     const size_t n = (size_t)H * W;
     encode_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(disp, out, n, scale);
     MCCNN_LAUNCH_CHECK("encode_u8_kernel");
+    return 0;
+}
+
+extern "C" int mccnn_encode_u16(const float* disp, uint16_t* out, int H, int W, int frac_bits, void* stream) {
+    MCCNN_REQUIRE(disp && out, MCCNN_EINVAL, "mccnn_encode_u16: null argument");
+    MCCNN_REQUIRE(frac_bits >= 0 && frac_bits <= 8, MCCNN_EINVAL, "mccnn_encode_u16: frac_bits=%d outside 0..8", frac_bits);
+    if (int e = check_hw("mccnn_encode_u16", H, W)) return e;
+    const size_t n = (size_t)H * W;
+    encode_u16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(disp, out, n, (float)(1 << frac_bits));
+    MCCNN_LAUNCH_CHECK("encode_u16_kernel");
+    return 0;
+}
+
+extern "C" int mccnn_wta_subpixel(const float* S, float* disp, int H, int W, int D, void* stream) {
+    MCCNN_REQUIRE(S && disp, MCCNN_EINVAL, "mccnn_wta_subpixel: null argument");
+    if (int e = check_hw("mccnn_wta_subpixel", H, W)) return e;
+    MCCNN_REQUIRE(D >= 1, MCCNN_EINVAL, "mccnn_wta_subpixel: D=%d", D);
+    const int npix = H * W;
+    wta_subpixel_kernel<<<ceil_div(npix, 8), 256, 0, (cudaStream_t)stream>>>(S, disp, npix, D, disp_pitch(D));
+    MCCNN_LAUNCH_CHECK("wta_subpixel_kernel");
     return 0;
 }
 

@@ -43,6 +43,7 @@ struct SgmArgs {
     int nsides;
     double P1, P2, P1r, P2r;
     int threshold;
+    int subpixel;
     int store_s;
     unsigned* counter;
     // row-band sharding (one pair split over several GPUs): this launch owns image rows [row0, row0 + Hb); the
@@ -75,6 +76,17 @@ __device__ __forceinline__ void scan_pixel(const SgmArgs& a, int line, int t, in
             col = c < 0 ? c + a.W : c;
         }
     }
+}
+
+// Parabola through (d-1, cm), (d, c), (d+1, cp), typed as the reference's commented-out expression would be by
+// Numba (:818): fp32 differences, the factor 2 promotes the denominator to fp64. Border indices and a flat
+// parabola keep the integer index (the reference is silent there).
+__device__ __forceinline__ float subpixel_refine(int idx, int D, float cm, float c, float cp) {
+    if (idx <= 0 || idx >= D - 1) return (float)idx;
+    const float num = cp - cm;
+    const double den = 2.0 * ((double)(cm + cp) - 2.0 * (double)c);
+    if (!(den > 0.0)) return (float)idx;
+    return (float)((double)idx - (double)num / den);
 }
 
 // order-preserving map double -> signed 64-bit integer
@@ -339,13 +351,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             }
 
             if constexpr (MODE == SGM_LAST_WTA) {
-                // first strict minimum over d (:805-811)
-                float best = __int_as_float(0x7f800000);
+                // first strict minimum over d (:805-811); the neighbours of the running minimum are tracked for
+                // the optional parabola refinement (:813-819)
+                float best = __int_as_float(0x7f800000), bl = 0.f, br = 0.f;
                 int bj = 0;
+                float left = __shfl_up_sync(0xffffffffu, so[NPL - 1], 1);
+                const float right_edge = __shfl_down_sync(0xffffffffu, so[0], 1);
 #pragma unroll
                 for (int j = 0; j < NPL; j++) {
                     const float v = so[j] + 0.0f;  // entries d >= D are +INF or NaN here: never selected
-                    if (v < best) { best = v; bj = j; }
+                    const float nxt = (j + 1 < NPL) ? so[j + 1 < NPL ? j + 1 : j] : right_edge;
+                    if (v < best) { best = v; bj = j; bl = left; br = nxt; }
+                    left = so[j];
                 }
                 int k = __float_as_int(best);
                 k ^= (k >> 31) & 0x7fffffff;
@@ -353,7 +370,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
                 const unsigned who = __ballot_sync(0xffffffffu, k == mk);
                 const int src = __ffs(who) - 1;
                 const int idx = __shfl_sync(0xffffffffu, d0 + bj, src);
-                if (lane == 0) a.disp[side][(size_t)(row - a.row0) * a.W + col] = (float)idx;
+                float outv = (float)idx;
+                if (a.subpixel) {
+                    const float c = __shfl_sync(0xffffffffu, best, src);
+                    const float cm = __shfl_sync(0xffffffffu, bl, src), cp = __shfl_sync(0xffffffffu, br, src);
+                    outv = subpixel_refine(idx, a.D, cm, c, cp);
+                }
+                if (lane == 0) a.disp[side][(size_t)(row - a.row0) * a.W + col] = outv;
             }
             // every lane's results (which depend on all of its cf/sf loads) are stored or reduced: refill the stage
             __syncwarp();
@@ -447,6 +470,7 @@ void set_params(SgmArgs& a, const mccnn_sgm_params* p) {
     a.P1r = (double)p->P1_red;
     a.P2r = (double)p->P2_red;
     a.threshold = p->threshold;
+    a.subpixel = p->subpixel;
 }
 
 int check_common(const void* C, int H, int W, int D) {

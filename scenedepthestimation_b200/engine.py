@@ -156,6 +156,20 @@ def wta(S: torch.Tensor, D: int) -> torch.Tensor:
     return out
 
 
+def wta_subpixel(S: torch.Tensor, D: int) -> torch.Tensor:
+    H, W, _ = S.shape
+    out = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().mccnn_wta_subpixel(_p(S), _p(out), H, W, D, _stream()), "mccnn_wta_subpixel")
+    return out
+
+
+def encode_u16(disp, frac_bits: int = 0):
+    H, W = disp.shape
+    out = torch.empty((H, W), dtype=torch.int16, device="cuda")
+    _lib.check(_lib.load().mccnn_encode_u16(_p(disp), _p(out), H, W, int(frac_bits), _stream()), "mccnn_encode_u16")
+    return out.view(torch.uint16) if hasattr(torch, "uint16") else out
+
+
 def wta_dhw(vol: torch.Tensor) -> torch.Tensor:
     D, H, W = vol.shape
     out = torch.empty((H, W), dtype=torch.float32, device="cuda")

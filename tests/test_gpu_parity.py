@@ -266,6 +266,37 @@ def test_row_band_sharded_sgm_equals_unsharded(eng, H, W, D, world):
         assert torch.equal(a[..., :D] if a.dim() == 3 else a, b[..., :D] if b.dim() == 3 else b), name
 
 
+def test_optional_stages_subpixel_bilateral_u16(eng):
+    """Stages the reference holds but does not run (commented out at :813-819 and :1260): checked against the
+    oracle's own restatement ("parity unpinned"), fused and stand-alone; plus the 16-bit encode for D > 255."""
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import _lib, synthetic as syn
+
+    H, W, D = 24, 70, 300
+    il, ir, _ = syn.textured_pair(H, W, D, 5)
+    fl, fr, _ = syn.correlated_features(H, W, D, 64, 5)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    p = _lib.default_sgm_params()
+    p.subpixel = 1
+    SL, SR, dl, dr = eng.sgm(CL, CR, dev(il), dev(ir), D, params=p, keep_volumes=True)
+    sl, sr = unpitch(SL, D), unpitch(SR, D)
+    exp_l, exp_r = st.wta_subpixel(sl), st.wta_subpixel(sr)
+    assert np.array_equal(dl.cpu().numpy(), exp_l) and np.array_equal(dr.cpu().numpy(), exp_r)
+    assert np.array_equal(eng.wta_subpixel(SL, D).cpu().numpy(), exp_l)
+    assert np.any(exp_l != np.floor(exp_l))  # the refinement really produced fractions
+    # whole pipeline with both switches: fill + bilateral on the fractional maps
+    p.bilateral = 1
+    out_l, out_r = eng.disparity_pipeline(dev(il), dev(ir), dev(fl), dev(fr), D, params=p)
+    fll, _ = st.lr_flags(exp_l, exp_r)
+    filled = st.lrc_fill(exp_l, fll)
+    assert np.array_equal(out_l.cpu().numpy(), st.bilateral9(il, filled))
+    assert np.array_equal(out_r.cpu().numpy(), exp_r)
+    # 16-bit encode with 4 fractional bits (saturating)
+    m = np.array([[0.0, 1.5, 299.9375, 5000.0, -3.0]], np.float32)
+    got = eng.encode_u16(dev(m), 4).cpu().numpy().view(np.uint16)
+    assert got.tolist() == [[0, 24, 4799, 65535, 0]]
+
+
 def test_errors_are_loud(eng):
     from scenedepthestimation_b200 import _lib
 
