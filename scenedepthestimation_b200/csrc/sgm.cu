@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
     constexpr bool kReadS = (MODE != SGM_FIRST_FUSED);
     constexpr int ROW = 32 * NPL;  // floats per row buffer
     constexpr int IN_BUFS = kReadS ? 2 : 1;
-    constexpr int OUT_BUFS = OUTB;  // 0: S is not stored; 1: one staging row (wait for the previous store); 2: double-buffered
+    constexpr int OUT_BUFS = OUTB;  // 0: S is not stored; n: ring of n staging rows (a bulk store takes ~1 us to drain)
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -335,10 +335,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             }
 
             if constexpr (STORE) {
-                float* ob = outbuf + (OUTB > 1 ? (ostep & 1u) * ROW : 0);
-                if (lane == 0) {
-                    if constexpr (OUTB > 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
-                }
+                float* ob = outbuf + (OUTB > 1 ? (ostep % OUTB) * ROW : 0);
+                if (lane == 0) bulk_wait_read<OUTB - 1>();  // the store issued OUTB steps ago has left its staging row
                 __syncwarp();
                 store_chunk<NPL>(ob, lane, so);
                 fence_proxy_async_smem();
@@ -429,7 +427,7 @@ int dispatch_scan(const SgmArgs& a, cudaStream_t stream) {
             if (!a.store_s) return launch_scan<N, (N >= 13 ? 2 : ST), MODE, 0>(a, stream);         \
         }                                                                                           \
         if constexpr (MODE == SGM_MID && N >= 13) return launch_scan<N, 2, MODE, 1>(a, stream);      \
-        return launch_scan<N, ST, MODE, 2>(a, stream);                                              \
+        return launch_scan<N, ST, MODE, (N <= 8 ? 6 : 2)>(a, stream);                               \
     }
     MCCNN_SGM_CASE(1, 6)
     MCCNN_SGM_CASE(2, 6)

@@ -41,6 +41,82 @@ def match_batch(pairs, weights, ndisp=128, scale=2, detail_time=None):
     return out
 
 
+class StreamedMatcher:
+    """match.py's loop (:46-90) as a pipeline: `depth` pairs in flight on their own CUDA streams, each with pinned
+    host buffers and its own workspace, so the H2D copy, the kernels and the D2H copy of consecutive pairs overlap
+    (and the latency-bound small-D kernels of two pairs share the SMs). Results come back in submission order."""
+
+    def __init__(self, H, W, weights, ndisp=128, scale=2, depth=2, num_layers=5):
+        import torch
+
+        from . import engine as eng
+        from . import process_functional as pf
+
+        eng._require_cuda()
+        self.torch, self.eng = torch, eng
+        self.H, self.W, self.D, self.scale, self.nl = H, W, int(ndisp), int(scale), num_layers
+        self.packed = pf._load_weights(weights, num_layers)
+        nws = eng.match_workspace_bytes(H, W, self.D, num_layers)
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append(dict(
+                stream=torch.cuda.Stream(), done=torch.cuda.Event(), busy=False, tag=None,
+                h_in=torch.empty((2, H, W), dtype=torch.uint8).pin_memory(),
+                h_out=torch.empty((H, W), dtype=torch.uint8).pin_memory(),
+                d_in=torch.empty((2, H, W), dtype=torch.uint8, device="cuda"),
+                d_out=torch.empty((H, W), dtype=torch.uint8, device="cuda"),
+                disp=(torch.empty((H, W), dtype=torch.float32, device="cuda"), torch.empty((H, W), dtype=torch.float32, device="cuda")),
+                ws=torch.empty(nws, dtype=torch.uint8, device="cuda")))
+        self.next = 0
+
+    def _collect(self, slot):
+        slot["done"].synchronize()
+        slot["busy"] = False
+        return slot["tag"], slot["h_out"].numpy().copy()
+
+    def submit(self, left_u8, right_u8, tag=None):
+        """Enqueue one pair; returns the (tag, uint8 map) of the pair that previously used the slot, or None."""
+        torch, eng = self.torch, self.eng
+        slot = self.slots[self.next]
+        self.next = (self.next + 1) % len(self.slots)
+        out = self._collect(slot) if slot["busy"] else None
+        slot["h_in"][0].copy_(torch.from_numpy(np.ascontiguousarray(left_u8)))
+        slot["h_in"][1].copy_(torch.from_numpy(np.ascontiguousarray(right_u8)))
+        with torch.cuda.stream(slot["stream"]):
+            slot["d_in"].copy_(slot["h_in"], non_blocking=True)
+            eng.match_pair(slot["d_in"][0], slot["d_in"][1], self.packed, self.D, self.nl, out=slot["disp"], workspace=slot["ws"])
+            lib = eng._lib.load()
+            eng._lib.check(lib.mccnn_encode_u8(slot["disp"][0].data_ptr(), slot["d_out"].data_ptr(), self.H, self.W, self.scale,
+                                               slot["stream"].cuda_stream), "mccnn_encode_u8")
+            slot["h_out"].copy_(slot["d_out"], non_blocking=True)
+            slot["done"].record(slot["stream"])
+        slot["busy"], slot["tag"] = True, tag
+        return out
+
+    def drain(self):
+        """Results still in flight, oldest first."""
+        out = []
+        for k in range(len(self.slots)):
+            slot = self.slots[(self.next + k) % len(self.slots)]
+            if slot["busy"]:
+                out.append(self._collect(slot))
+        return out
+
+
+def match_stream(pairs, weights, ndisp=128, scale=2, depth=2):
+    """Generator over (left_u8, right_u8) pairs of one shape -> uint8 maps in order, `depth` pairs in flight."""
+    m = None
+    for i, (left, right) in enumerate(pairs):
+        if m is None:
+            m = StreamedMatcher(left.shape[0], left.shape[1], weights, ndisp, scale, depth)
+        r = m.submit(left, right, i)
+        if r is not None:
+            yield r[1]
+    if m is not None:
+        for _, img in m.drain():
+            yield img
+
+
 def main(argv=None):
     args = parser.parse_args(argv)
     if args.gpu is not None:

@@ -297,6 +297,18 @@ def test_optional_stages_subpixel_bilateral_u16(eng):
     assert got.tolist() == [[0, 24, 4799, 65535, 0]]
 
 
+def test_streamed_batch_equals_sequential(eng):
+    """match.py's loop with several pairs in flight on separate streams == one pair at a time, in order."""
+    from scenedepthestimation_b200 import match, synthetic as syn
+
+    w = syn.glorot_weights()
+    pairs = [syn.textured_pair(30, 64, 32, 50 + i)[:2] for i in range(5)]
+    seq = match.match_batch(pairs, w, ndisp=32, scale=2)
+    for depth in (1, 2, 3):
+        got = list(match.match_stream(iter(pairs), w, ndisp=32, scale=2, depth=depth))
+        assert len(got) == len(seq) and all(np.array_equal(a, b) for a, b in zip(got, seq))
+
+
 def test_errors_are_loud(eng):
     from scenedepthestimation_b200 import _lib
 
