@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCCNN_ABI_VERSION 1
+#define MCCNN_ABI_VERSION 2
 #define MCCNN_FEATURES 64 /* num_of_feature_maps: hard-coded 64 in the reference (process_functional.py:128) */
 
 enum {
@@ -56,6 +56,11 @@ typedef struct {
     int subpixel;   /* 1: parabola refinement of the WTA index, the formula commented out at :813-819 */
     int bilateral;  /* 1: the 9x9 bilateral filter whose launch is commented out at :1260; as in that launch it reads
                        the filled map and overwrites the median output */
+    /* Cross-based cost aggregation between the cost volume and SGM: the stage north_star names and the reference
+     * only has a timing slot for (match.py:98, detail_time[2]). 0 iterations = the reference's behaviour. */
+    int cbca_iters; /* aggregation passes over both volumes (0 = off; MC-CNN uses 2) */
+    int cbca_L1;    /* maximum arm length, 1..32 (default 14) */
+    int cbca_tau;   /* arm stops where |I(q) - I(p)| >= tau on u8 grey levels (default 6) */
 } mccnn_sgm_params;
 
 const char* mccnn_last_error(void);
@@ -106,6 +111,18 @@ int mccnn_cost_volume(const float* fl, const float* fr, float* CL, float* CR,
                       int H, int W, int D, float fill, void* stream);
 /* [H][W][Dp] -> dense [D][H][W] (layout of the reference's CPU compute_cost_volume, :48-73). */
 int mccnn_volume_to_dhw(const float* vol, float* out_dhw, int H, int W, int D, void* stream);
+
+/* ---- cross-based cost aggregation (north_star kernel 3; no reference implementation: parity unpinned) -----
+ * The reference passes the raw volume into SGM under the name d_cost_volumel_after_aggr (process_functional.py:347,
+ * :1166) and keeps an unused timing slot for the stage (match.py:98); the definition is the MC-CNN paper's (see
+ * csrc/cbca.cu). arms4: u8 [H][W][4] = distance to the first excluded pixel to the left, right, up, down. */
+int mccnn_cross_arms(const uint8_t* image, uint8_t* arms4, int H, int W, int L1, int tau, void* stream);
+/* One aggregation pass: vol_out[y][x][d] = mean of vol_in over the cross-based support of (y, x, d), taken as the
+ * intersection of the supports in the volume's own image (arms_self) and in the other image at x + direction*d
+ * (arms_other); direction = -1 for the left volume, +1 for the right one. tmp is a third volume of the same size
+ * (row sums). Pad entries [D, Dp) of vol_out are +INF. */
+int mccnn_cbca(const float* vol_in, float* vol_out, float* tmp, const uint8_t* arms_self, const uint8_t* arms_other,
+               int H, int W, int D, int direction, int L1, void* stream);
 
 /* ---- semi-global matching ------------------------------------------------------------------
  * Replaces sgm_penelty_kernel (:134-262, penalties are recomputed from the images on the fly and

@@ -437,6 +437,91 @@ def bilateral9(image, disp, weights=_BILATERAL_W):
 
 
 # --------------------------------------------------------------------------- orchestration
+# --------------------------------------------------------------------------- cross-based aggregation
+# north_star names this stage; the reference has no code for it (only the label at match.py:98 and the
+# parameter name at process_functional.py:347) => PARITY UNPINNED. Definition after the MC-CNN paper
+# (Zbontar & LeCun 2016, sec. 5.1): arm rules, intersection of the supports of the pixel and of its match,
+# mean over the support, rows first and columns second; stated in full in csrc/cbca.cu.
+CBCA_L1 = 14   # maximum arm length (own default)
+CBCA_TAU = 6   # intensity threshold on u8 grey levels (own default)
+
+
+@njit(parallel=True, cache=True)
+def cross_arms(image, L1=CBCA_L1, tau=CBCA_TAU):
+    """u8 [H,W] -> u8 [H,W,4]: distance to the first excluded position to the left, right, up, down."""
+    H, W = image.shape
+    arms = np.zeros((H, W, 4), np.uint8)
+    dxs = np.array([-1, 1, 0, 0])
+    dys = np.array([0, 0, -1, 1])
+    for y in prange(H):
+        for x in range(W):
+            c = np.int64(image[y, x])
+            for k4 in range(4):
+                k = 1
+                while True:
+                    xx = x + dxs[k4] * k
+                    yy = y + dys[k4] * k
+                    if xx < 0 or xx >= W or yy < 0 or yy >= H:
+                        break
+                    if k > 1:
+                        if abs(np.int64(image[yy, xx]) - c) >= tau:
+                            break
+                        if k >= L1:
+                            break
+                    k += 1
+                arms[y, x, k4] = k
+    return arms
+
+
+@njit(parallel=True, cache=True)
+def cbca_iteration(vol, arms_self, arms_other, direction):
+    """One aggregation pass of vol [H,W,D] (direction -1: left volume, other pixel x-d; +1: right volume).
+    Row sums are rounded to fp32 (they are an fp32 volume on the device), the column sum and the mean are fp64,
+    the result is rounded once to fp32."""
+    H, W, D = vol.shape
+    rows = np.zeros((H, W, D), np.float32)
+    cnts = np.zeros((H, W, D), np.int64)
+    for y in prange(H):
+        for x in range(W):
+            for d in range(D):
+                xo = x + direction * d
+                if xo < 0 or xo >= W:
+                    continue
+                lo = x - min(arms_self[y, x, 0], arms_other[y, xo, 0])
+                hi = x + min(arms_self[y, x, 1], arms_other[y, xo, 1])
+                acc = 0.0
+                for xx in range(lo + 1, hi):
+                    acc += np.float64(vol[y, xx, d])
+                rows[y, x, d] = np.float32(acc)
+                cnts[y, x, d] = hi - lo - 1
+    out = np.empty((H, W, D), np.float32)
+    for y in prange(H):
+        for x in range(W):
+            for d in range(D):
+                xo = x + direction * d
+                if xo < 0 or xo >= W:
+                    out[y, x, d] = vol[y, x, d]
+                    continue
+                lo = y - min(arms_self[y, x, 2], arms_other[y, xo, 2])
+                hi = y + min(arms_self[y, x, 3], arms_other[y, xo, 3])
+                acc = 0.0
+                n = 0
+                for yy in range(lo + 1, hi):
+                    acc += np.float64(rows[yy, x, d])
+                    n += cnts[yy, x, d]
+                out[y, x, d] = np.float32(acc / n)
+    return out
+
+
+def cbca(cl, cr, imagel, imager, iters=2, L1=CBCA_L1, tau=CBCA_TAU):
+    """`iters` aggregation passes of both volumes."""
+    al, ar = cross_arms(imagel, L1, tau), cross_arms(imager, L1, tau)
+    for _ in range(iters):
+        cl = cbca_iteration(cl, al, ar, -1)
+        cr = cbca_iteration(cr, ar, al, 1)
+    return cl, cr
+
+
 def disparity_pipeline(imagel, imager, featuresl, featuresr, ndisp=128, keep=False):
     """disparity_compute_by_gpu, process_functional.py:1093-1267, on the CPU.
 

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libmccnn_b200.so")
 
 class SgmParams(C.Structure):
     _fields_ = [("P1", C.c_float), ("P2", C.c_float), ("P1_red", C.c_float), ("P2_red", C.c_float),
-                ("threshold", C.c_int), ("subpixel", C.c_int), ("bilateral", C.c_int)]
+                ("threshold", C.c_int), ("subpixel", C.c_int), ("bilateral", C.c_int),
+                ("cbca_iters", C.c_int), ("cbca_L1", C.c_int), ("cbca_tau", C.c_int)]
 
 
 class Shard(C.Structure):
@@ -41,6 +42,8 @@ SIGNATURES = {
     "mccnn_conv_tower_fp32": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
     "mccnn_cost_volume": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "mccnn_volume_to_dhw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mccnn_cross_arms": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "mccnn_cbca": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mccnn_sgm_workspace_bytes": (_sz, [_i, _i, _i]),
     "mccnn_sgm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _PP, _i, _i, _vp]),
     "mccnn_sgm_shard_exchange_bytes": (_sz, [_i]),

@@ -47,6 +47,9 @@ extern "C" void mccnn_default_sgm_params(mccnn_sgm_params* p) {
     p->threshold = 30;
     p->subpixel = 0;
     p->bilateral = 0;
+    p->cbca_iters = 0;  // the reference runs no aggregation
+    p->cbca_L1 = 14;
+    p->cbca_tau = 6;
 }
 
 extern "C" int mccnn_device_supported(int device) {

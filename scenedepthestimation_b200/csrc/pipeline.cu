@@ -15,7 +15,7 @@ namespace {
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct PipeLayout {
-    size_t CL, CR, SL, SR, dl_wta, filled, flagL, sgm_ws, lrc_ws, end;
+    size_t CL, CR, SL, SR, dl_wta, filled, flagL, armsL, armsR, sgm_ws, lrc_ws, end;
 };
 
 PipeLayout pipe_layout(int H, int W, int D) {
@@ -30,6 +30,8 @@ PipeLayout pipe_layout(int H, int W, int D) {
     l.dl_wta = o; o += map;
     l.filled = o; o += map;
     l.flagL = o; o += align_up((size_t)H * W);
+    l.armsL = o; o += align_up((size_t)H * W * 4);
+    l.armsR = o; o += align_up((size_t)H * W * 4);
     l.sgm_ws = o; o += align_up(mccnn_sgm_workspace_bytes(H, W, D));
     l.lrc_ws = o; o += align_up(mccnn_lrc_fill_workspace_bytes(H, W));
     l.end = o;
@@ -57,7 +59,7 @@ MatchLayout match_layout(int H, int W, int D, int nl) {
 }
 
 struct StageTimer {
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[9];
     int n = 0;
     bool on = false;
     cudaStream_t s{};
@@ -65,7 +67,7 @@ struct StageTimer {
         on = enable;
         s = stream;
         if (!on) return 0;
-        for (int i = 0; i < 8; i++) MCCNN_CUDA(cudaEventCreate(&ev[i]));
+        for (int i = 0; i < 9; i++) MCCNN_CUDA(cudaEventCreate(&ev[i]));
         return mark();
     }
     int mark() {
@@ -75,7 +77,7 @@ struct StageTimer {
     }
     void destroy() {
         if (on)
-            for (int i = 0; i < 8; i++) cudaEventDestroy(ev[i]);
+            for (int i = 0; i < 9; i++) cudaEventDestroy(ev[i]);
         on = false;
     }
 };
@@ -109,6 +111,31 @@ static int run_pipeline(const uint8_t* imageL, const uint8_t* imageR, const floa
 
     if (int e = mccnn_cost_volume(fl, fr, CL, CR, H, W, D, 1.0f, stream)) return e;
     if (int e = tm.mark()) return e;  // [1] cost volume
+    if (params->cbca_iters > 0) {
+        // the stage behind the reference's unused "aggregation" slot (match.py:98); SL / SR are free until SGM starts
+        uint8_t* armsL = reinterpret_cast<uint8_t*>(ws + l.armsL);
+        uint8_t* armsR = reinterpret_cast<uint8_t*>(ws + l.armsR);
+        if (int e = mccnn_cross_arms(imageL, armsL, H, W, params->cbca_L1, params->cbca_tau, stream)) return e;
+        if (int e = mccnn_cross_arms(imageR, armsR, H, W, params->cbca_L1, params->cbca_tau, stream)) return e;
+        float *curL = CL, *curR = CR, *altL = SL, *tmp = SR;
+        for (int it = 0; it < params->cbca_iters; it++) {
+            // left: cur -> alt (row sums in tmp); right: cur -> (old left buffer is free now)
+            if (int e = mccnn_cbca(curL, altL, tmp, armsL, armsR, H, W, D, -1, params->cbca_L1, stream)) return e;
+            float* freeL = curL;
+            curL = altL;
+            if (int e = mccnn_cbca(curR, freeL, tmp, armsR, armsL, H, W, D, 1, params->cbca_L1, stream)) return e;
+            altL = curR;
+            curR = freeL;
+        }
+        // the four buffers are interchangeable from here on: SGM reads (curL, curR) and writes the other two
+        float* others[2];
+        int n = 0;
+        float* all4[4] = {CL, CR, SL, SR};
+        for (int i = 0; i < 4; i++)
+            if (all4[i] != curL && all4[i] != curR) others[n++] = all4[i];
+        CL = curL; CR = curR; SL = others[0]; SR = others[1];
+    }
+    if (int e = tm.mark()) return e;  // [2] aggregation
     if (int e = mccnn_sgm(CL, CR, imageL, imageR, SL, SR, dl_wta, dispR_out, ws + l.sgm_ws,
                           mccnn_sgm_workspace_bytes(H, W, D), H, W, D, params, mode, 0, stream))
         return e;
@@ -147,12 +174,13 @@ extern "C" int mccnn_disparity_pipeline(const uint8_t* imageL, const uint8_t* im
         if (e != cudaSuccess) {
             rc = cuda_fail(e, "cudaEventSynchronize");
         } else {
-            float ms[4] = {0, 0, 0, 0};
-            for (int i = 0; i < 4; i++) cudaEventElapsedTime(&ms[i], tm.ev[i], tm.ev[i + 1]);
+            float ms[5] = {0, 0, 0, 0, 0};
+            for (int i = 0; i < 5; i++) cudaEventElapsedTime(&ms[i], tm.ev[i], tm.ev[i + 1]);
             stage_ms_host[1] += ms[0];  // cost volume
-            stage_ms_host[3] += ms[1];  // SGM; slot [2] ("*" aggregation) is never written by the reference either
-            stage_ms_host[5] += ms[2];  // L-R check; slot [4] (WTA) is fused into the last SGM pass
-            stage_ms_host[6] += ms[3];  // filter
+            stage_ms_host[2] += ms[1];  // "*" aggregation: a label without a stage in the reference (match.py:98); CBCA here
+            stage_ms_host[3] += ms[2];  // SGM
+            stage_ms_host[5] += ms[3];  // L-R check; slot [4] (WTA) is fused into the last SGM pass
+            stage_ms_host[6] += ms[4];  // filter
         }
     }
     tm.destroy();
@@ -198,13 +226,14 @@ extern "C" int mccnn_match_pair(const uint8_t* imageL, const uint8_t* imageR, co
         if (e != cudaSuccess) {
             rc = cuda_fail(e, "cudaEventSynchronize");
         } else {
-            float ms[5] = {0, 0, 0, 0, 0};
-            for (int i = 0; i < 5; i++) cudaEventElapsedTime(&ms[i], tm.ev[i], tm.ev[i + 1]);
+            float ms[6] = {0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < 6; i++) cudaEventElapsedTime(&ms[i], tm.ev[i], tm.ev[i + 1]);
             stage_ms_host[0] += ms[0];
             stage_ms_host[1] += ms[1];
-            stage_ms_host[3] += ms[2];
-            stage_ms_host[5] += ms[3];
-            stage_ms_host[6] += ms[4];
+            stage_ms_host[2] += ms[2];
+            stage_ms_host[3] += ms[3];
+            stage_ms_host[5] += ms[4];
+            stage_ms_host[6] += ms[5];
         }
     }
     tm.destroy();

@@ -98,6 +98,20 @@ __device__ __forceinline__ long long dkey(double v) {
 // inputs are never NaN: a plain compare-select (DSETP + 2 SEL) instead of fmin()'s NaN-propagating sequence
 __device__ __forceinline__ double dmin(double x, double y) { return x < y ? x : y; }
 
+// minimum of N values as a balanced tree: the scan is bound by dependent-instruction latency (3 warps per
+// scheduler), and a serial chain of N compare-selects is its longest one
+template <int N>
+__device__ __forceinline__ double tree_min(const double (&v)[N]) {
+    double t[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = v[i];
+#pragma unroll
+    for (int stride = 1; stride < N; stride *= 2)
+#pragma unroll
+        for (int i = 0; i + stride < N; i += 2 * stride) t[i] = dmin(t[i], t[i + stride]);
+    return t[0];
+}
+
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -311,10 +325,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
                     }
                 }
                 // minimum over d, consumed at the next pixel together with this pixel's P2 (:332-341)
-                double m = L[0];
-#pragma unroll
-                for (int j = 1; j < NPL; j++) m = dmin(m, L[j]);
-                minL = warp_min_f64(m);
+                minL = warp_min_f64(tree_min<NPL>(L));
                 minLP2 = minL + (next_full ? a.P2 : a.P2r);
             }
             edge_full = next_full;
@@ -351,16 +362,33 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             if constexpr (MODE == SGM_LAST_WTA) {
                 // first strict minimum over d (:805-811); the neighbours of the running minimum are tracked for
                 // the optional parabola refinement (:813-819)
+                // (value tree first, then the lowest index holding it: no 32*NPL-long dependent chain)
                 float best = __int_as_float(0x7f800000), bl = 0.f, br = 0.f;
                 int bj = 0;
-                float left = __shfl_up_sync(0xffffffffu, so[NPL - 1], 1);
-                const float right_edge = __shfl_down_sync(0xffffffffu, so[0], 1);
+                {
+                    float tm[NPL];  // entries d >= D are +INF or NaN here: fminf drops NaN, +INF never wins
 #pragma unroll
-                for (int j = 0; j < NPL; j++) {
-                    const float v = so[j] + 0.0f;  // entries d >= D are +INF or NaN here: never selected
-                    const float nxt = (j + 1 < NPL) ? so[j + 1 < NPL ? j + 1 : j] : right_edge;
-                    if (v < best) { best = v; bj = j; bl = left; br = nxt; }
-                    left = so[j];
+                    for (int j = 0; j < NPL; j++) tm[j] = so[j];
+#pragma unroll
+                    for (int stride = 1; stride < NPL; stride *= 2)
+#pragma unroll
+                        for (int i = 0; i + stride < NPL; i += 2 * stride) tm[i] = fminf(tm[i], tm[i + stride]);
+                    best = fminf(tm[0], best) + 0.0f;  // -0 and +0 are one value (and one key below)
+                    unsigned hit[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int j = 0; j < NPL; j++) hit[j & 3] |= (so[j] == best) ? (1u << j) : 0u;
+                    const unsigned any = (hit[0] | hit[1]) | (hit[2] | hit[3]);
+                    bj = any ? __ffs(any) - 1 : 0;
+                }
+                if (a.subpixel) {
+                    float left = __shfl_up_sync(0xffffffffu, so[NPL - 1], 1);
+                    const float right_edge = __shfl_down_sync(0xffffffffu, so[0], 1);
+#pragma unroll
+                    for (int j = 0; j < NPL; j++) {
+                        const float nxt = (j + 1 < NPL) ? so[j + 1 < NPL ? j + 1 : j] : right_edge;
+                        if (j == bj) { bl = left; br = nxt; }
+                        left = so[j];
+                    }
                 }
                 int k = __float_as_int(best);
                 k ^= (k >> 31) & 0x7fffffff;

@@ -124,6 +124,28 @@ def volume_to_dhw(vol: torch.Tensor, D: int) -> torch.Tensor:
     return out
 
 
+def cross_arms(image_u8: torch.Tensor, L1: int = 14, tau: int = 6) -> torch.Tensor:
+    """u8 [H,W] -> u8 [H,W,4] arm lengths (left, right, up, down) for the cross-based aggregation."""
+    H, W = image_u8.shape
+    arms = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.load().mccnn_cross_arms(_p(image_u8), _p(arms), H, W, int(L1), int(tau), _stream()), "mccnn_cross_arms")
+    return arms
+
+
+def cbca(CL, CR, imageL, imageR, D: int, iters: int = 2, L1: int = 14, tau: int = 6):
+    """`iters` cross-based aggregation passes of both volumes (north_star stage 3; absent from the reference)."""
+    lib = _lib.load()
+    H, W, _ = CL.shape
+    al, ar = cross_arms(imageL, L1, tau), cross_arms(imageR, L1, tau)
+    tmp = torch.empty_like(CL)
+    for _ in range(int(iters)):
+        nl, nr = torch.empty_like(CL), torch.empty_like(CR)
+        _lib.check(lib.mccnn_cbca(_p(CL), _p(nl), _p(tmp), _p(al), _p(ar), H, W, D, -1, int(L1), _stream()), "mccnn_cbca")
+        _lib.check(lib.mccnn_cbca(_p(CR), _p(nr), _p(tmp), _p(ar), _p(al), H, W, D, 1, int(L1), _stream()), "mccnn_cbca")
+        CL, CR = nl, nr
+    return CL, CR
+
+
 def sgm(CL, CR, imageL, imageR, D: int, params=None, keep_volumes: bool = True):
     """8-path SGM + fused WTA. Returns (SL, SR, dispL, dispR)."""
     lib = _lib.load()

@@ -9,7 +9,9 @@ C ABI (engine.py -> libmccnn_b200.so). Differences a caller can see:
   * the device is the current torch CUDA device, not the reference's cuda.select_device(1) (:1095);
   * the returned right map is the raw right WTA map (the reference returns the median of an
     uninitialised buffer there, App. A6);
-  * no per-disparity prints.
+  * no per-disparity prints;
+  * `params` (optional, a _lib.SgmParams from `sgm_params(...)`) switches on the stages the reference names but
+    does not run: cross-based aggregation (cbca_iters), sub-pixel refinement, bilateral filter. Default = reference.
 """
 from __future__ import annotations
 
@@ -21,6 +23,19 @@ import torch
 from . import engine as _e
 
 NDISP = 128  # process_functional.py:125
+
+
+def sgm_params(**overrides):
+    """The reference's constants (process_functional.py:1141-1144) with optional overrides, e.g.
+    sgm_params(cbca_iters=2, subpixel=1)."""
+    from . import _lib
+
+    p = _lib.default_sgm_params()
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise TypeError(f"unknown parameter {k!r}")
+        setattr(p, k, v)
+    return p
 
 _weights_cache: dict = {}
 
@@ -88,7 +103,7 @@ def WTA1(left_cost_volume):
     return _e.wta_dhw(_e._dev(left_cost_volume, torch.float32)).cpu().numpy()
 
 
-def disparity_compute_by_gpu(imagel, imager, featuresl, featuresr, detail_time, ndisp=None):
+def disparity_compute_by_gpu(imagel, imager, featuresl, featuresr, detail_time, ndisp=None, params=None):
     """process_functional.py:1093-1267: u8 images + features -> (left disparity, right disparity, detail_time)."""
     _e._require_cuda()
     assert imagel.shape == imager.shape
@@ -96,13 +111,13 @@ def disparity_compute_by_gpu(imagel, imager, featuresl, featuresr, detail_time, 
     il, ir = _e._dev(imagel, torch.uint8), _e._dev(imager, torch.uint8)
     fl, fr = _e._dev(featuresl, torch.float32), _e._dev(featuresr, torch.float32)
     stage = np.zeros(7, np.float32)
-    dl, dr = _e.disparity_pipeline(il, ir, fl, fr, D, stage_ms=stage)
+    dl, dr = _e.disparity_pipeline(il, ir, fl, fr, D, params=params, stage_ms=stage)
     if detail_time is not None:
         detail_time += (stage / 1000.0).astype(detail_time.dtype)  # the reference accumulates seconds
     return dl.cpu().numpy(), dr.cpu().numpy(), detail_time
 
 
-def match_pair(left_u8, right_u8, checkpoint, ndisp=None, patch=11, detail_time=None):
+def match_pair(left_u8, right_u8, checkpoint, ndisp=None, patch=11, detail_time=None, params=None):
     """Fused match_single.py:34-55: u8 pair -> (left disparity f32, right raw WTA f32), one C call."""
     _e._require_cuda()
     D = int(NDISP if ndisp is None else ndisp)
@@ -110,7 +125,7 @@ def match_pair(left_u8, right_u8, checkpoint, ndisp=None, patch=11, detail_time=
     packed = _load_weights(checkpoint, nl)
     il, ir = _e._dev(left_u8, torch.uint8), _e._dev(right_u8, torch.uint8)
     stage = np.zeros(7, np.float32) if detail_time is not None else None
-    dl, dr = _e.match_pair(il, ir, packed, D, nl, stage_ms=stage)
+    dl, dr = _e.match_pair(il, ir, packed, D, nl, params=params, stage_ms=stage)
     if detail_time is not None:
         detail_time += (stage / 1000.0).astype(detail_time.dtype)
     return dl.cpu().numpy(), dr.cpu().numpy()

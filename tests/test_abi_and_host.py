@@ -40,12 +40,14 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_constants_and_sizes(lib):
     from scenedepthestimation_b200 import _lib
 
-    assert lib.mccnn_abi_version() == 1
+    assert lib.mccnn_abi_version() == 2
     assert [lib.mccnn_disp_pitch(d) for d in (1, 4, 80, 81, 228, 800)] == [4, 4, 80, 84, 228, 800]
     p = _lib.default_sgm_params()
     # process_functional.py:1141-1144, stored as fp32 (:149), reduced pair computed in fp64 then rounded (:141-142)
     assert p.P1 == np.float32(2.3) and p.P2 == np.float32(55.9)
     assert p.P1_red == np.float32(2.3 / 4) and p.P2_red == np.float32(55.9 / 4) and p.threshold == 30
+    assert (p.subpixel, p.bilateral, p.cbca_iters) == (0, 0, 0)  # stages the reference does not run stay off
+    assert (p.cbca_L1, p.cbca_tau) == (14, 6)
     fp32_bytes = 4 * (9 * 64 + 64 + 4 * (9 * 64 * 64 + 64))
     # fp32 section (padded to 1 KB) + per 64->64 layer the fp16 hi/lo tensor-core tiles (2 x 9 taps x 8 KB)
     assert lib.mccnn_conv_packed_weight_bytes(5) == ((fp32_bytes + 1023) // 1024) * 1024 + 4 * 2 * 9 * 8192

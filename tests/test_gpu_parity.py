@@ -309,6 +309,134 @@ def test_streamed_batch_equals_sequential(eng):
         assert len(got) == len(seq) and all(np.array_equal(a, b) for a, b in zip(got, seq))
 
 
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("H,W,D,kind", [(6, 700, 256, "unit"), (3, 900, 800, "corr"), (4, 300, 128, "scaled")])
+def test_cost_volume_bits_at_scale(eng, H, W, D, kind):
+    """Millions of evaluations, compared BIT for bit (sign of zero included): enough volume that the
+    rounding-boundary re-evaluation path of the cost-volume kernel (about 1 evaluation in 10^4) is exercised."""
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import synthetic as syn
+
+    if kind == "corr":
+        fl, fr, _ = syn.correlated_features(H, W, D, 64, 77)
+    else:
+        fl, fr = syn.unit_features(H, W, 64, 78)
+    if kind == "scaled":  # not unit-norm: the error bound must follow the norms
+        rng = np.random.default_rng(5)
+        fl = (fl * rng.uniform(1e-3, 1e3, (H, W, 1))).astype(np.float32)
+        fr = (fr * rng.uniform(1e-3, 1e3, (H, W, 1))).astype(np.float32)
+    cl, cr = st.cost_volume(fl, fr, D)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    assert np.array_equal(_bits(unpitch(CL, D)), _bits(cl)) and np.array_equal(_bits(unpitch(CR, D)), _bits(cr))
+
+
+def test_cost_volume_non_finite_and_extreme(eng):
+    """NaN / Inf / huge / denormal-range features: every such pixel takes the literal sequential loop."""
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import synthetic as syn
+
+    H, W, D = 3, 140, 70
+    fl, fr = syn.unit_features(H, W, 64, 9)
+    fl[0, 3, 5] = np.inf
+    fl[0, 9, 1] = np.nan
+    fr[0, 20, 2] = -np.inf
+    fr[1, 7, :] = np.float32(3e37)     # products overflow to inf
+    fl[1, 30, :] = np.float32(-2e37)
+    fl[2, 11, :] = np.float32(1e-30)   # norm underflows
+    fr[2, 13, :] = np.float32(1e-25)
+    fl[2, 50, 0::2] = 0.0
+    fr[2, 60, :] = np.float32(1e-44)   # denormal features
+    with np.errstate(all="ignore"):
+        cl, cr = st.cost_volume(fl, fr, D)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    for got, exp in ((unpitch(CL, D), cl), (unpitch(CR, D), cr)):
+        nan = np.isnan(exp)
+        assert np.array_equal(np.isnan(got), nan)
+        assert np.array_equal(_bits(got)[~nan], _bits(exp)[~nan])
+
+
+@pytest.mark.parametrize("H,W,D,L1,tau", [(21, 47, 24, 6, 8), (30, 70, 37, 14, 6), (40, 33, 9, 20, 12), (5, 9, 12, 3, 255)])
+def test_cbca_vs_oracle(eng, H, W, D, L1, tau):
+    """Cross-based aggregation (no reference implementation; own oracle, parity unpinned): arms exact, aggregated
+    costs within north_star's 1e-4 relative (measured ~1e-7: fp64 prefix sums against fp64 direct sums)."""
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import synthetic as syn
+
+    il, ir, _ = syn.textured_pair(H, W, max(D, 8), 31 + H)
+    fl, fr = syn.unit_features(H, W, 64, 32 + W)
+    cl, cr = st.cost_volume(fl, fr, D)
+    al, ar = st.cross_arms(il, L1, tau), st.cross_arms(ir, L1, tau)
+    assert np.array_equal(eng.cross_arms(dev(il), L1, tau).cpu().numpy(), al)
+    assert np.array_equal(eng.cross_arms(dev(ir), L1, tau).cpu().numpy(), ar)
+    assert al.min() >= 1 and al.max() <= L1
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    for iters in (1, 2):
+        exp_l, exp_r = st.cbca(cl, cr, il, ir, iters, L1, tau)
+        GL, GR = eng.cbca(CL, CR, dev(il), dev(ir), D, iters, L1, tau)
+        np.testing.assert_allclose(unpitch(GL, D), exp_l, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(unpitch(GR, D), exp_r, rtol=1e-5, atol=1e-6)
+        if GL.shape[-1] > D:
+            assert torch.isinf(GL[..., D:]).all() and torch.isinf(GR[..., D:]).all()
+
+
+def test_cbca_properties(eng):
+    """Size-independent properties: a constant volume is a fixed point; the aggregated right volume is the shear
+    of the aggregated left one (as the raw volumes are); tau = 0 leaves only the 3x3 minimum cross."""
+    from scenedepthestimation_b200 import synthetic as syn
+
+    H, W, D = 64, 300, 100
+    il, ir, _ = syn.textured_pair(H, W, D, 5)
+    fl, fr = syn.unit_features(H, W, 64, 6)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    GL, GR = eng.cbca(CL, CR, dev(il), dev(ir), D, 2)
+    gl, gr = unpitch(GL, D), unpitch(GR, D)
+    x = np.arange(W)[:, None]
+    d = np.arange(D)[None, :]
+    ok = (x + d) < W
+    xs = np.minimum(x + d, W - 1)
+    sheared = gl[:, xs, d]  # CR[y, x, d] = CL[y, x + d, d]
+    np.testing.assert_allclose(gr[:, ok], sheared[:, ok], rtol=1e-5, atol=1e-6)
+    const = torch.full_like(CL, 0.25)
+    const[..., D:] = float("inf")
+    KL, KR = eng.cbca(const, const.clone(), dev(il), dev(ir), D, 1)
+    assert np.array_equal(unpitch(KL, D), np.full((H, W, D), 0.25, np.float32))
+    assert np.array_equal(unpitch(KR, D), np.full((H, W, D), 0.25, np.float32))
+    arms = eng.cross_arms(dev(il), 14, 0).cpu().numpy()
+    assert arms[1:-1, 1:-1].max() == 2 and arms[1:-1, 1:-1].min() == 2 and arms[0, 0, 0] == 1 and arms[0, 0, 2] == 1
+
+
+def test_pipeline_with_cbca_equals_stage_composition(eng):
+    """mccnn_match_pair / mccnn_disparity_pipeline with cbca_iters = 2: same result as the stages called one by one,
+    and the 'aggregation' slot of detail_time (never written by the reference, match.py:98) is filled."""
+    from scenedepthestimation_b200 import process_functional as pf, synthetic as syn
+
+    H, W, D = 40, 90, 32
+    il, ir, _ = syn.textured_pair(H, W, D, 77)
+    fl, fr, _ = syn.correlated_features(H, W, D, 64, 78)
+    prm = pf.sgm_params(cbca_iters=2, cbca_L1=9, cbca_tau=10)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    GL, GR = eng.cbca(CL, CR, dev(il), dev(ir), D, 2, 9, 10)
+    _, _, dl, dr = eng.sgm(GL, GR, dev(il), dev(ir), D, keep_volumes=False)
+    flag, _ = eng.lr_flags(dl, dr, right=False)
+    exp = eng.median5(eng.lrc_fill(dl, flag), dl).cpu().numpy()
+    dt = np.zeros(7, np.float32)
+    got_l, got_r, dt = pf.disparity_compute_by_gpu(il, ir, fl, fr, dt, ndisp=D, params=prm)
+    assert np.array_equal(got_l, exp) and np.array_equal(got_r, dr.cpu().numpy())
+    assert dt[2] > 0
+    for iters in (1, 3):  # odd counts end in another buffer
+        prm = pf.sgm_params(cbca_iters=iters, cbca_L1=9, cbca_tau=10)
+        GL, GR = eng.cbca(CL, CR, dev(il), dev(ir), D, iters, 9, 10)
+        _, _, dl, dr = eng.sgm(GL, GR, dev(il), dev(ir), D, keep_volumes=False)
+        got_l, got_r, _ = pf.disparity_compute_by_gpu(il, ir, fl, fr, None, ndisp=D, params=prm)
+        flag, _ = eng.lr_flags(dl, dr, right=False)
+        assert np.array_equal(got_l, eng.median5(eng.lrc_fill(dl, flag), dl).cpu().numpy())
+    base_l, _, _ = pf.disparity_compute_by_gpu(il, ir, fl, fr, None, ndisp=D)
+    assert not np.array_equal(base_l, exp)  # the stage does something
+
+
 def test_errors_are_loud(eng):
     from scenedepthestimation_b200 import _lib
 

@@ -70,3 +70,47 @@ def test_cpu_reference_cost_volume_agrees():
     vol = st.cost_volume_cpu_reference(fl, fr, 24)
     for d in range(24):
         np.testing.assert_allclose(vol[d, :, d:], cl[:, d:, d], rtol=0, atol=2e-6)
+
+
+def test_cbca_oracle_self_consistency():
+    """Cross-based aggregation has no reference code (parity unpinned): the oracle is checked against a literal
+    NumPy restatement of its own definition on a tiny case, and for its fixed point / shear properties."""
+    from scenedepthestimation_b200 import synthetic as syn
+
+    H, W, D, L1, tau = 9, 17, 6, 4, 12
+    il, ir, _ = syn.textured_pair(H, W, 8, 3)
+    fl, fr = syn.unit_features(H, W, 64, 4)
+    cl, cr = st.cost_volume(fl, fr, D)
+    al, ar = st.cross_arms(il, L1, tau), st.cross_arms(ir, L1, tau)
+    assert al.dtype == np.uint8
+    al_i, ar_i = al, ar
+    al, ar = al.astype(np.int64), ar.astype(np.int64)
+    # arms, literally
+    for (y, x) in [(0, 0), (4, 8), (8, 16), (3, 1)]:
+        for k4, (dy, dx) in enumerate([(0, -1), (0, 1), (-1, 0), (1, 0)]):
+            k = 1
+            while True:
+                yy, xx = y + dy * k, x + dx * k
+                if not (0 <= yy < H and 0 <= xx < W):
+                    break
+                if k > 1 and (abs(int(il[yy, xx]) - int(il[y, x])) >= tau or k >= L1):
+                    break
+                k += 1
+            assert al[y, x, k4] == k
+    out = st.cbca_iteration(cl, al_i, ar_i, -1)
+    for (y, x, d) in [(4, 8, 2), (0, 3, 3), (8, 16, 5), (2, 1, 4)]:
+        xo = x - d
+        if xo < 0:
+            assert out[y, x, d] == cl[y, x, d]
+            continue
+        rows, n = [], 0
+        for yy in range(y - min(al[y, x, 2], ar[y, xo, 2]) + 1, y + min(al[y, x, 3], ar[y, xo, 3])):
+            lo, hi = x - min(al[yy, x, 0], ar[yy, xo, 0]), x + min(al[yy, x, 1], ar[yy, xo, 1])
+            rows.append(np.float32(np.sum(cl[yy, lo + 1:hi, d].astype(np.float64))))
+            n += hi - lo - 1
+        np.testing.assert_allclose(out[y, x, d], np.float32(np.sum(np.array(rows, np.float64)) / n), rtol=1e-6)
+    const = np.full((H, W, D), 0.5, np.float32)
+    assert np.array_equal(st.cbca_iteration(const, al_i, ar_i, -1), const)
+    gl, gr = st.cbca(cl, cr, il, ir, 2, L1, tau)
+    for d in range(D):
+        np.testing.assert_allclose(gr[:, :W - d, d], gl[:, d:, d], rtol=1e-6, atol=1e-7)

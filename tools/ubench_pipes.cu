@@ -31,6 +31,20 @@ __global__ void __launch_bounds__(256) k(double* out, float* outf, double seed, 
             if (OP == 7) a[i] = (a[i] < a[(i + 3) % NCH]) ? a[i] : a[(i + 3) % NCH] ; // DSETP+SEL
             if (OP == 8) f[i] = fminf(f[i], f[(i + 1) % NCH]) + 1.0f;        // FMNMX + FADD
             if (OP == 9) f[i] = fmaf(f[i], 1.0001f, 0.5f);        // FFMA
+            if (OP == 10 && (i & 1) == 0) {                       // FFMA2 (one packed op = 2 flops-pairs)
+                float2 r = __ffma2_rn(make_float2(f[i], f[i + 1]), make_float2(1.0001f, 1.0002f), make_float2(0.5f, 0.25f));
+                f[i] = r.x; f[i + 1] = r.y;
+            }
+            if (OP >= 11 && (i & 1) == 0) {                       // product-residual trio: FMUL2, FFMA2, FADD2 (+2 DFMA, + F2F)
+                const float2 x = make_float2(f[(i + 2) % NCH], f[(i + 3) % NCH]);
+                const float sc = __int_as_float(0x3f800000 + it);
+                const float2 pr = __fmul2_rn(x, make_float2(sc, sc));
+                const float2 e = __ffma2_rn(x, make_float2(sc, sc), make_float2(-pr.x, -pr.y));
+                const float2 r = __fadd2_rn(make_float2(f[i], f[i + 1]), e);
+                f[i] = r.x; f[i + 1] = r.y;
+                if (OP >= 12) { a[i] = fma(a[i], p, 0.25); a[i + 1] = fma(a[i + 1], p, 0.25); }
+                if (OP == 13 && (i & 2) == 0) { a[i] += (double)sc; }   // 1 widening per 4 products (kernel: 0.375)
+            }
         }
     }
     double s = 0; float sf = 0;
@@ -77,5 +91,9 @@ int main() {
     run<6>("SHFL.BFLY (+IADD)", 1);
     run<8>("FMNMX+FADD", 1);
     run<9>("FFMA", 1);
+    run<10>("FFMA2 (flops pairs; x2 lanes)", 1);
+    run<11>("FMUL2+FFMA2+FADD2 products", 1);
+    run<12>(" + 1 DFMA per product", 1);
+    run<13>(" + 0.25 F2F(+DADD) per product", 1);
     return 0;
 }
