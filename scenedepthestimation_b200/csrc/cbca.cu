@@ -73,10 +73,26 @@ __global__ void __launch_bounds__(CB_THREADS) cbca_row_kernel(const float* __res
     double run = 0.0;
     ring[0] = 0.0;  // prefix before element 0 sits in slot 0; prefix including element x in slot (x + 1) % RING
     const int la = L1 - 1;  // an arm reaches at most x + L1 - 1
-    for (int s0 = 0; s0 < W + la; s0 += 8) {
-        float v[8];
+    // software pipeline: the loads of chunk k+1 (8 cost rows, the arms of the 8 pixels it emits) are in flight
+    // while chunk k runs through the dependent prefix / ring updates
+    float v[8], vn[8];
+    uchar4 ea[8], eb[8], ean[8], ebn[8];
+    auto fetch = [&](int s0, float (&vv)[8], uchar4 (&aa)[8], uchar4 (&bb)[8]) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) v[u] = (s0 + u < W) ? __ldg(vrow + (size_t)(s0 + u) * Dp) : 0.0f;
+        for (int u = 0; u < 8; u++) {
+            const int s = s0 + u;
+            vv[u] = (s < W) ? __ldg(vrow + (size_t)s * Dp) : 0.0f;
+            const int x = min(max(s - la, 0), W - 1);
+            const int xo = min(max(x + dir * d, 0), W - 1);
+            aa[u] = aA[x];
+            bb[u] = aB[xo];
+        }
+    };
+    fetch(0, vn, ean, ebn);
+    for (int s0 = 0; s0 < W + la; s0 += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) { v[u] = vn[u]; ea[u] = ean[u]; eb[u] = ebn[u]; }
+        if (s0 + 8 < W + la) fetch(s0 + 8, vn, ean, ebn);
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             const int s = s0 + u;
@@ -87,13 +103,10 @@ __global__ void __launch_bounds__(CB_THREADS) cbca_row_kernel(const float* __res
             const int x = s - la;
             if (x >= 0 && x < W) {
                 const int xo = x + dir * d;
-                float out;
-                if (xo < 0 || xo >= W) {
-                    out = 0.0f;  // never used: the column pass passes the original entry through
-                } else {
-                    const uchar4 a = aA[x], b = aB[xo];
-                    const int lo = x - min((int)a.x, (int)b.x);      // exclusive
-                    const int hi = x + min((int)a.y, (int)b.y) - 1;  // inclusive
+                float out = 0.0f;  // no B-pixel: never used, the column pass passes the original entry through
+                if (xo >= 0 && xo < W) {
+                    const int lo = x - min((int)ea[u].x, (int)eb[u].x);      // exclusive
+                    const int hi = x + min((int)ea[u].y, (int)eb[u].y) - 1;  // inclusive
                     out = (float)(ring[((hi + 1) & (RING - 1)) * CB_THREADS] - ring[((lo + 1) & (RING - 1)) * CB_THREADS]);
                 }
                 hrow[(size_t)x * Dp] = out;
@@ -134,16 +147,26 @@ __global__ void __launch_bounds__(CB_THREADS) cbca_col_kernel(const float* __res
     ring[0] = 0.0;
     ringn[0] = 0;
     const int la = L1 - 1;
-    for (int s0 = 0; s0 < H + la; s0 += 8) {
-        float v[8];
-        uchar4 a[8], b[8];
+    float v[8], vn[8];
+    uchar4 a[8], b[8], an[8], bn[8], ea[8], eb[8], ean[8], ebn[8];
+    auto fetch = [&](int s0, float (&vv)[8], uchar4 (&aa)[8], uchar4 (&bb)[8], uchar4 (&eaa)[8], uchar4 (&ebb)[8]) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const bool in = s0 + u < H;
-            v[u] = in ? __ldg(hcol + (size_t)(s0 + u) * rstride) : 0.0f;
-            a[u] = in ? aA[(size_t)(s0 + u) * W] : make_uchar4(1, 1, 1, 1);
-            b[u] = in ? aB[(size_t)(s0 + u) * W] : make_uchar4(1, 1, 1, 1);
+            const int s = s0 + u;
+            const int sc = min(s, H - 1);
+            vv[u] = (s < H) ? __ldg(hcol + (size_t)s * rstride) : 0.0f;
+            aa[u] = aA[(size_t)sc * W];
+            bb[u] = aB[(size_t)sc * W];
+            const int y = min(max(s - la, 0), H - 1);
+            eaa[u] = aA[(size_t)y * W];
+            ebb[u] = aB[(size_t)y * W];
         }
+    };
+    fetch(0, vn, an, bn, ean, ebn);
+    for (int s0 = 0; s0 < H + la; s0 += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) { v[u] = vn[u]; a[u] = an[u]; b[u] = bn[u]; ea[u] = ean[u]; eb[u] = ebn[u]; }
+        if (s0 + 8 < H + la) fetch(s0 + 8, vn, an, bn, ean, ebn);
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             const int s = s0 + u;
@@ -155,9 +178,8 @@ __global__ void __launch_bounds__(CB_THREADS) cbca_col_kernel(const float* __res
             }
             const int y = s - la;
             if (y >= 0 && y < H) {
-                const uchar4 ay = aA[(size_t)y * W], by = aB[(size_t)y * W];
-                const int lo = y - min((int)ay.z, (int)by.z);      // exclusive
-                const int hi = y + min((int)ay.w, (int)by.w) - 1;  // inclusive
+                const int lo = y - min((int)ea[u].z, (int)eb[u].z);      // exclusive
+                const int hi = y + min((int)ea[u].w, (int)eb[u].w) - 1;  // inclusive
                 const int ih = ((hi + 1) & (RING - 1)) * CB_THREADS, il = ((lo + 1) & (RING - 1)) * CB_THREADS;
                 const double sum = ring[ih] - ring[il];
                 const int cnt = ringn[ih] - ringn[il];

@@ -78,6 +78,18 @@ __device__ __forceinline__ void scan_pixel(const SgmArgs& a, int line, int t, in
     }
 }
 
+// one step along the scanline (the incremental form of scan_pixel: no modulo in the inner loop)
+__device__ __forceinline__ void scan_advance(const SgmArgs& a, int& row, int& col) {
+    if (a.horizontal) {
+        col += a.dx;
+    } else {
+        row += a.dy;
+        col += a.dx;
+        if (col >= a.W) col -= a.W;
+        if (col < 0) col += a.W;
+    }
+}
+
 // Parabola through (d-1, cm), (d, c), (d+1, cp), typed as the reference's commented-out expression would be by
 // Numba (:818): fp32 differences, the factor 2 promotes the denominator to fp64. Border indices and a flat
 // parabola keep the integer index (the reference is silent there).
@@ -172,11 +184,12 @@ __device__ __forceinline__ void store_chunk(float* buf, int lane, const float (&
 // that pass is latency-bound (it carries the WTA reductions), not bandwidth-bound.
 template <int NPL, int STAGES, int MODE, int OUTB>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmArgs a) {
-    constexpr bool STORE = OUTB > 0;
+    constexpr bool STORE = OUTB != 0;
+    constexpr bool DIRECT = OUTB < 0;  // short rows: S leaves straight from the registers (vector stores), no staging
     constexpr bool kReadS = (MODE != SGM_FIRST_FUSED);
     constexpr int ROW = 32 * NPL;  // floats per row buffer
     constexpr int IN_BUFS = kReadS ? 2 : 1;
-    constexpr int OUT_BUFS = OUTB;  // 0: S is not stored; n: ring of n staging rows (a bulk store takes ~1 us to drain)
+    constexpr int OUT_BUFS = OUTB > 0 ? OUTB : 0;  // 0: S is not staged; n: ring of n staging rows (a bulk store takes ~1 us to drain)
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,10 +245,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
         }
         if (t_begin >= t_end) continue;
 
-        auto issue_load = [&](int t, uint32_t g) {
-            int row, col;
-            scan_pixel(a, line, t, row, col);
-            const size_t off = ((size_t)(row - a.row0) * a.W + col) * pix_stride;
+        int lrow, lcol;  // pixel of the next row to prefetch (loads are issued in scanline order)
+        scan_pixel(a, line, t_begin, lrow, lcol);
+        auto issue_load = [&](uint32_t g) {
+            const size_t off = ((size_t)(lrow - a.row0) * a.W + lcol) * pix_stride;
             const int st = g % STAGES;
             float* dst = inbuf + (size_t)st * IN_BUFS * ROW;
             mbar_expect_tx(&bars[st], copy_bytes * IN_BUFS);
@@ -248,9 +261,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             return (int)img[(size_t)row * a.W + col];
         };
 
-        if (lane == 0) {
+        {
             const int pre = min(STAGES, t_end - t_begin);
-            for (int k = 0; k < pre; k++) issue_load(t_begin + k, gstep + k);
+            for (int k = 0; k < pre; k++) {
+                if (lane == 0) issue_load(gstep + k);
+                scan_advance(a, lrow, lcol);
+            }
         }
         // image values: lane l of blk_cur holds I[pixel tb + 1 + l]
         int i_cur = image_at(t_begin);
@@ -278,9 +294,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             minLP2 = minL + (edge_full ? a.P2 : a.P2r);
         }
 
-        for (int t = t_begin; t < t_end; t++) {
-            int row, col;
-            scan_pixel(a, line, t, row, col);
+        int row, col;
+        scan_pixel(a, line, t_begin, row, col);
+        for (int t = t_begin; t < t_end; t++, scan_advance(a, row, col)) {
             const int st = gstep % STAGES;
             mbar_wait(&bars[st], (gstep / STAGES) & 1u);
             float cf[NPL], sf[NPL];
@@ -345,7 +361,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
                 }
             }
 
-            if constexpr (STORE) {
+            if constexpr (DIRECT) {
+                float* dstp = Sv + ((size_t)(row - a.row0) * a.W + col) * pix_stride + d0;
+                if constexpr (NPL % 4 == 0) {
+#pragma unroll
+                    for (int j = 0; j < NPL; j += 4)
+                        if (d0 + j < a.Dp) *reinterpret_cast<float4*>(dstp + j) = make_float4(so[j], so[j + 1], so[j + 2], so[j + 3]);
+                } else if constexpr (NPL % 2 == 0) {
+#pragma unroll
+                    for (int j = 0; j < NPL; j += 2)
+                        if (d0 + j < a.Dp) *reinterpret_cast<float2*>(dstp + j) = make_float2(so[j], so[j + 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NPL; j++)
+                        if (d0 + j < a.Dp) dstp[j] = so[j];
+                }
+            } else if constexpr (STORE) {
                 float* ob = outbuf + (OUTB > 1 ? (ostep % OUTB) * ROW : 0);
                 if (lane == 0) bulk_wait_read<OUTB - 1>();  // the store issued OUTB steps ago has left its staging row
                 __syncwarp();
@@ -406,7 +437,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             }
             // every lane's results (which depend on all of its cf/sf loads) are stored or reduced: refill the stage
             __syncwarp();
-            if (lane == 0 && t + STAGES < t_end) issue_load(t + STAGES, gstep + STAGES);
+            if (t + STAGES < t_end) {
+                if (lane == 0) issue_load(gstep + STAGES);
+                scan_advance(a, lrow, lcol);
+            }
             gstep++;
         }
         if (a.hand_out != nullptr && t_end < a.nsteps_dp) {
@@ -427,7 +461,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
 template <int NPL, int STAGES, int MODE, int OUTB>
 int launch_scan(const SgmArgs& a, cudaStream_t stream) {
     constexpr int IN_BUFS = (MODE != SGM_FIRST_FUSED) ? 2 : 1;
-    const size_t smem = (size_t)WARPS_PER_CTA * (32 * NPL * (STAGES * IN_BUFS + OUTB)) * sizeof(float) +
+    const size_t smem = (size_t)WARPS_PER_CTA * (32 * NPL * (STAGES * IN_BUFS + (OUTB > 0 ? OUTB : 0))) * sizeof(float) +
                         (size_t)WARPS_PER_CTA * STAGES * sizeof(uint64_t);
     auto kern = sgm_scan_kernel<NPL, STAGES, MODE, OUTB>;
     MCCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -455,7 +489,7 @@ int dispatch_scan(const SgmArgs& a, cudaStream_t stream) {
             if (!a.store_s) return launch_scan<N, (N >= 13 ? 2 : ST), MODE, 0>(a, stream);         \
         }                                                                                           \
         if constexpr (MODE == SGM_MID && N >= 13) return launch_scan<N, 2, MODE, 1>(a, stream);      \
-        return launch_scan<N, ST, MODE, (N <= 8 ? 6 : 2)>(a, stream);                               \
+        return launch_scan<N, ST, MODE, (N <= 8 ? -1 : 2)>(a, stream);                               \
     }
     MCCNN_SGM_CASE(1, 6)
     MCCNN_SGM_CASE(2, 6)
