@@ -179,6 +179,7 @@ def main():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local % torch.cuda.device_count())
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     from scenedepthestimation_b200 import engine as eng
 
