@@ -35,6 +35,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c4", help="c1..c5 (SURVEY.md App. B); the metric is quoted on c4")
+    ap.add_argument("--batch", type=int, default=0, help="pairs per step per GPU (default 1; 32 for c5 = 256 pairs over 8 ranks), "
+                    "kept in flight on --depth CUDA streams like match.py's streamed loop")
+    ap.add_argument("--depth", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -137,10 +140,13 @@ def main():
 
     W, H, D = syn.CONFIGS[a.config]
     evals = H * W * D
-    config = {"workload": f"{a.config}: synthetic Middlebury-2014-shaped full-res pair {W}x{H}, {D} disparities, MC-CNN-fast "
+    batch = a.batch if a.batch > 0 else (32 if a.config == "c5" else 1)
+    shape_name = {"c1": "Middlebury-2006 third-size", "c2": "Middlebury-2005/2006 half-size", "c3": "Middlebury-2014 half-size",
+                  "c4": "Middlebury-2014-shaped full-res", "c5": "KITTI-shaped"}[a.config]
+    config = {"workload": f"{a.config}: synthetic {shape_name} pair {W}x{H}, {D} disparities, MC-CNN-fast "
                           "(5x 3x3 conv, 64 maps, random-init) + 8-path SGM + WTA + L-R check/fill + 5x5 median",
-              "pairs_per_step_per_gpu": 1, "parallelism": f"pair-per-rank x{world}",
-              "l2": "per-step working set (4 fp32 volumes, 73 GB) exceeds the 126 MB L2 by >500x; no flush needed",
+              "pairs_per_step_per_gpu": batch, "parallelism": f"pair-per-rank x{world}" + (f", {a.depth} pairs in flight per GPU" if batch > 1 else ""),
+              "l2": f"per-step working set (4 fp32 volumes per pair in flight, {4 * evals * 4 / 1e9:.1f} GB each set) exceeds the 126 MB L2; no flush needed",
               "arithmetic": "reference-exact (fp64 SGM state and cost accumulator, fp32 S rounded per path in reference order)"}
 
     if a.impl == "reference":
@@ -189,9 +195,24 @@ def main():
     d_il, d_ir = torch.from_numpy(il).cuda(), torch.from_numpy(ir).cuda()
     ws = torch.empty(eng.match_workspace_bytes(H, W, D, 5), dtype=torch.uint8, device="cuda")
     out = (torch.empty((H, W), device="cuda"), torch.empty((H, W), device="cuda"))
+    slots = []
+    if batch > 1:  # pair-batch per rank: `depth` pairs in flight, each on its own stream with its own workspace
+        for _ in range(a.depth):
+            slots.append((torch.cuda.Stream(), torch.empty_like(ws), (torch.empty_like(out[0]), torch.empty_like(out[1]))))
 
     def step():
-        eng.match_pair(d_il, d_ir, packed, D, 5, out=out, workspace=ws)
+        if batch == 1:
+            eng.match_pair(d_il, d_ir, packed, D, 5, out=out, workspace=ws)
+            return
+        cur = torch.cuda.current_stream()
+        for st, _, _ in slots:
+            st.wait_stream(cur)
+        for i in range(batch):
+            st, w_, o_ = slots[i % len(slots)]
+            with torch.cuda.stream(st):
+                eng.match_pair(d_il, d_ir, packed, D, 5, out=o_, workspace=w_)
+        for st, _, _ in slots:
+            cur.wait_stream(st)
 
     def barrier():
         if world > 1:
@@ -214,13 +235,25 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    value = world * a.steps / (total_ms / 1e3)
+    value = world * batch * a.steps / (total_ms / 1e3)
 
     # ---- end to end through the public host-buffer API: pinned host images in, host disparity out, every step
     h_il, h_ir = torch.from_numpy(il).pin_memory(), torch.from_numpy(ir).pin_memory()
     h_dl, h_dr = torch.empty((H, W), dtype=torch.float32).pin_memory(), torch.empty((H, W), dtype=torch.float32).pin_memory()
 
+    streamed = None
+    if batch > 1:
+        from scenedepthestimation_b200 import match as match_mod
+
+        del slots[:]
+        streamed = match_mod.StreamedMatcher(H, W, weights, ndisp=D, scale=1, depth=a.depth)
+
     def e2e_step():
+        if streamed is not None:  # match.py's loop: host u8 pairs in, host u8 disparity maps out, `depth` pairs in flight
+            for i in range(batch):
+                streamed.submit(il, ir, i)
+            streamed.drain()
+            return
         dl_, dr_ = eng.match_pair(h_il.cuda(non_blocking=True), h_ir.cuda(non_blocking=True), packed, D, 5, out=out, workspace=ws)
         h_dl.copy_(dl_, non_blocking=True)
         h_dr.copy_(dr_, non_blocking=True)
@@ -236,7 +269,7 @@ def main():
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * a.steps / float(e2e_s.item())
+    e2e_value = world * batch * a.steps / float(e2e_s.item())
 
     # ---- roofline of the dominant kernel (the SGM scanline kernel, 7 launches per pair), timed alone with
     # CUDA events on the launching stream; algorithmic bytes per pair = 16 * H*W*D (both sides,
@@ -261,7 +294,7 @@ def main():
                 "stage_ms": {"features": float(stage[0]), "cost_volume": float(stage[1]), "sgm": float(stage[3]),
                              "lr_check_fill": float(stage[5]), "median": float(stage[6])}}
     tr = os.path.join(ROOT, "profiles", "sgm_traffic.json")
-    if os.path.exists(tr):
+    if os.path.exists(tr) and a.config == "c4":  # the ncu capture is of the c4 launch
         with open(tr) as f:
             t = json.load(f)
         roofline["traffic"] = t.get("dram_bytes_per_launch")
@@ -270,7 +303,7 @@ def main():
     # ---- N > 1: the same pair ALSO split by rows over all ranks (strong scaling of one pair): NVLink
     # peer-memory hand-off of the SGM path state inside the scan kernels, all_gather of the image / WTA bands
     sharded = None
-    if world > 1:
+    if world > 1 and batch == 1:
         from scenedepthestimation_b200 import sharded as sh
 
         del ws
@@ -306,9 +339,11 @@ def main():
             "warmup": max(3, a.warmup), "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "gdisp_evals_per_sec": value * evals / 1e9,
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * H * W, "d2h_bytes_per_step": 2 * H * W * 4,
-                    "api": "engine.match_pair (mccnn_match_pair) with pinned host u8 images in, host fp32 maps out"},
-            "gpu_launches": KERNELS_PER_STEP * a.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * H * W * batch,
+                    "d2h_bytes_per_step": (2 * H * W * 4 if batch == 1 else H * W) * batch,
+                    "api": "engine.match_pair (mccnn_match_pair) with pinned host u8 images in, host fp32 maps out" if batch == 1 else
+                           "match.StreamedMatcher (match.py's loop): host u8 pairs in, host u8 disparity maps out"},
+            "gpu_launches": KERNELS_PER_STEP * a.steps * batch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "single_pair_sharded": sharded}))
     if world > 1:
         dist.destroy_process_group()
