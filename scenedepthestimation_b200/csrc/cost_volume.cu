@@ -19,8 +19,11 @@
 //
 // The exact contract costs one fp32->fp64 widening per product. F2F.F64.F32 issues at 16/clk/SM on
 // B200 (profiles/r01_ubench_pipes.txt), which bounds a straightforward kernel far below HBM speed, so
-// half of the products are widened on the integer pipe instead (4 ALU ops, bit-exact for normal
-// numbers). A CTA whose staged features are not all comfortably normal falls back to F2F for all.
+// half of the products are widened on the integer pipe instead (3 ALU ops, bit-exact for normal
+// numbers below 2), and the multiplies are issued two at a time (FMUL2). A CTA whose staged features are not all
+// comfortably normal falls back to F2F for all. The kernel is issue-bound (ncu: 82 % issue slots busy); the
+// alternatives measured in tools/ubench_cv_inner.cu (residual + DFMA formulation, DMMA) sit within 10 % of it
+// because DFMA / DMMA share the FP32 FMA datapath on B200 (profiles/r01c_ubench_cv_inner.txt).
 #include "common.cuh"
 
 namespace mccnn {
@@ -42,18 +45,20 @@ struct CvSmem {
     };
 };
 
-// bit-exact fp32 -> fp64 widening of a NORMAL, finite fp32 number on the integer pipe
+// bit-exact fp32 -> fp64 widening of a NORMAL fp32 number with |p| < 2 on the integer pipe, 3 ALU operations:
+// the biased exponent is <= 127, so its top bit is clear and the rebias 127 -> 1023 (+0x380) is a plain OR
 __device__ __forceinline__ double widen_normal(float p) {
     const uint32_t x = __float_as_uint(p);
     const int32_t t = (int32_t)x >> 3;  // sign copies | exponent | mantissa >> 3
-    const uint32_t hi = ((uint32_t)t & 0x8fffffffu) + 0x38000000u;  // rebias 127 -> 1023
-    return __hiloint2double((int)hi, (int)(x << 29));
+    const uint32_t hi = ((uint32_t)t & 0x8fffffffu) | 0x38000000u;
+    return __hiloint2double((int)hi, (int)__funnelshift_l(0u, x, 29));
 }
 
-// features whose pairwise products are guaranteed normal and finite: 2^-60 <= |v| < 2^64
+// features whose pairwise products are guaranteed normal, non-zero and below 1: 2^-60 <= |v| < 1
+// (unit-norm features always are, unless one of them is exactly +-1 or 0)
 __device__ __forceinline__ bool comfortably_normal(float v) {
     const uint32_t e = (__float_as_uint(v) >> 23) & 0xffu;
-    return e >= 67u && e <= 190u;
+    return e >= 67u && e <= 126u;
 }
 
 // Stage 64 pixels x 64 features: global [pixel][k] -> shared [k][pixel], 4-pixel chunks XOR-swizzled by k/4.
@@ -84,18 +89,22 @@ __device__ __forceinline__ void tile_products(const CvSmem& sm, int tx, int ty, 
         const int key = (k >> 2) & 15;
         const float4 av = *reinterpret_cast<const float4*>(&sm.op.a[k][((tx ^ key) & 15) << 2]);
         const float4 bv = *reinterpret_cast<const float4*>(&sm.op.b[k][((ty ^ key) & 15) << 2]);
-        const float a[4] = {av.x, av.y, av.z, av.w};
+        const float2 a01 = make_float2(av.x, av.y), a23 = make_float2(av.z, av.w);
         const float b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            // two fp32 products per FMUL2 (each lane is an IEEE round-to-nearest multiply, like FMUL)
+            const float2 p01 = __fmul2_rn(a01, make_float2(b[j], b[j]));
+            const float2 p23 = __fmul2_rn(a23, make_float2(b[j], b[j]));
+            const float p[4] = {p01.x, p01.y, p23.x, p23.y};
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float p = __fmul_rn(a[i], b[j]);
+            for (int i = 0; i < 4; i++) {
                 if (SPLIT && ((i + j) & 1))
-                    acc[i][j] += widen_normal(p);  // integer pipe
+                    acc[i][j] += widen_normal(p[i]);  // integer pipe
                 else
-                    acc[i][j] += (double)p;  // F2F.F64.F32
+                    acc[i][j] += (double)p[i];  // F2F.F64.F32
             }
+        }
     }
 }
 

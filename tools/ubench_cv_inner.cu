@@ -16,6 +16,15 @@ __device__ __forceinline__ double widen3(float p) {  // |p| < 2, normal, non-zer
     return __hiloint2double((int)hi, (int)__funnelshift_l(0u, x, 29));
 }
 
+__device__ __forceinline__ double widen3m(float p) {  // left shift on the FMA pipe (IMAD), one SHF left
+    const uint32_t x = __float_as_uint(p);
+    const int32_t t = (int32_t)x >> 3;
+    const uint32_t hi = ((uint32_t)t & 0x8fffffffu) | 0x38000000u;
+    uint32_t lo;
+    asm("mad.lo.u32 %0, %1, 536870912, 0;" : "=r"(lo) : "r"(x));
+    return __hiloint2double((int)hi, (int)lo);
+}
+
 // MODE: 0 S3 packed, 1 S3 scalar, 2 S1, 3 S1/S2 checkerboard, 4 S2, 5 S3 packed rows 0..5 + S1 rows 6,7, 6: S1 on (i+j)%3==0 else S2
 template <int MODE>
 __global__ void __launch_bounds__(128, 3) inner(float* out, int reps) {
@@ -83,8 +92,10 @@ __global__ void __launch_bounds__(128, 3) inner(float* out, int reps) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const float p = __fmul_rn(av[i], bb[j]);
-                        bool f2f = MODE == 2 || (MODE == 3 && ((i + j) & 1)) || (MODE == 6 && ((i + j) % 3 == 0)) || (MODE == 7 && ((i + 2 * j) % 5 < 2));
-                        acc[i][j] += f2f ? (double)p : widen3(p);
+                        bool f2f = MODE == 2 || (MODE == 3 && ((i + j) & 1)) || (MODE == 6 && ((i + j) % 3 == 0)) || (MODE == 7 && ((i + 2 * j) % 5 < 2)) ||
+                                   (MODE == 8 && ((i + j) & 1)) || (MODE == 9 && ((i + 3 * j) % 8 < 3)) || (MODE == 10 && ((i + j) % 3 == 0)) ||
+                                   (MODE == 11 && ((i + j) % 4 == 0));
+                        acc[i][j] += f2f ? (double)p : (MODE >= 8 ? widen3m(p) : widen3(p));
                     }
             }
         }
@@ -122,5 +133,10 @@ int main() {
     run<7>("S1/S2 2:3");
     run<4>("S2 all 3-op bit widening");
     run<5>("S3 packed rows 0-5 + S1 rows 6-7");
+    run<8>("S1/S2m (IMAD left shift) 1:1");
+    run<9>("S1/S2m 3:5");
+    run<10>("S1/S2m 1:2");
+    run<11>("S1/S2m 1:3");
+    run<12>("S2m all");
     return 0;
 }
