@@ -41,6 +41,7 @@ struct SgmArgs {
     int nsteps_dp;     // pixels visited by the dynamic program
     int nsteps_total;  // >= nsteps_dp: FIRST_FUSED / LAST_WTA also touch the pixel the path skips
     int nsides;
+    int side0;         // first side handled by this launch (single-side launches of the sharded schedule)
     double P1, P2, P1r, P2r;
     int threshold;
     int subpixel;
@@ -226,8 +227,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
         if (lane == 0) q = atomicAdd(a.counter, 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= (unsigned)(a.nsides * a.nlines)) break;
-        const int side = (int)q / a.nlines;
-        const int line = (int)q - side * a.nlines;
+        const int side = a.side0 + (int)q / a.nlines;
+        const int line = (int)q - (side - a.side0) * a.nlines;
         const float* __restrict__ Cv = a.C[side];
         float* __restrict__ Sv = a.S[side];
         const unsigned char* __restrict__ img = a.img[side];
@@ -572,12 +573,14 @@ static int run_sgm(const float* CL, const float* CR, const uint8_t* imageL, cons
     // down-left, 6 = up-left + winner-takes-all (also visits row 0, which the path skips)
     static const int kPassPath[7] = {0, 2, 3, 4, 5, 6, 7};
     const size_t slot_doubles = (size_t)2 * W * HAND_STRIDE;
-    for (int pass = 0; pass < 7; pass++) {
-        if (!(pass_mask & (1 << pass))) continue;
+    // one launch: pass `pass` of side `side0` .. `side0 + nsides - 1`
+    auto launch = [&](int pass, int side0, int nsides) -> int {
         set_path(a, kPassPath[pass]);
         if (pass == 0 || pass == 6) a.nsteps_total = H;
         a.store_s = (pass == 6 && !keep_volumes) ? 0 : 1;
-        a.counter = counters + pass;
+        a.side0 = side0;
+        a.nsides = nsides;
+        a.counter = counters + 2 * pass + side0;
         a.hand_in = nullptr; a.flag_in = nullptr; a.hand_out = nullptr; a.flag_out = nullptr;
         if (sh && sh->world > 1 && !a.horizontal) {
             // a rank receives from the rank the path comes from and publishes to the rank it runs into
@@ -597,10 +600,43 @@ static int run_sgm(const float* CL, const float* CR, const uint8_t* imageL, cons
                 a.flag_out = reinterpret_cast<unsigned*>(to_peer + flags_off) + (size_t)pass * 2 * W;
             }
         }
-        int e = pass == 0 ? dispatch_scan<SGM_FIRST_FUSED>(a, stream)
-                : pass == 6 ? dispatch_scan<SGM_LAST_WTA>(a, stream)
-                            : dispatch_scan<SGM_MID>(a, stream);
-        if (e) return e;
+        return pass == 0 ? dispatch_scan<SGM_FIRST_FUSED>(a, stream)
+               : pass == 6 ? dispatch_scan<SGM_LAST_WTA>(a, stream)
+                           : dispatch_scan<SGM_MID>(a, stream);
+    };
+
+    // (measured on c4: 2 ranks 113 -> 106 ms per pair. With more ranks the fill of a launch, world-1 waves, outweighs
+    // a single-side launch of 1.6 waves and the sequential single-side launches do not win: 4 ranks 67 -> 73 ms. There
+    // both sides stay in one launch until the two launches of a step can share the SMs.)
+    if (!(sh && sh->world == 2)) {
+        for (int pass = 0; pass < 7; pass++)
+            if (pass_mask & (1 << pass))
+                if (int e = launch(pass, 0, 2)) return e;
+        return 0;
+    }
+    // Two ranks: a vertical / diagonal pass is a pipeline over the ranks (rank r resumes a scanline when rank
+    // r-1, or r+1 for the upward passes, has finished its part), so with both sides in one launch every rank idles
+    // for one wave of scanlines per rank boundary and pass. The two sides are independent chains: run the right
+    // volume ONE PASS AHEAD of the left one. Consecutive passes either run in opposite directions (3..6: down, up,
+    // down, up) or are band-local (1, 2), so in every step {left pass k-1, right pass k} each rank has a launch that
+    // is fed early: it runs the one whose first scanlines arrive sooner first. Same order of steps on all ranks; within
+    // a step the first launches form wait-free chains from the two ends of the rank line, so no cycle of waits.
+    auto arrival = [&](int pass) -> int {  // in waves: how long until this rank's first scanline of `pass` can start
+        const int path = kPassPath[pass];
+        if (kPathDy[path] == 0) return 0;
+        return kPathDy[path] > 0 ? sh->rank : sh->world - 1 - sh->rank;
+    };
+    for (int step = 0; step <= 7; step++) {
+        const int pl = step - 1, pr = step;  // left pass, right pass of this step
+        const bool do_l = pl >= 0 && pl < 7 && (pass_mask & (1 << pl));
+        const bool do_r = pr < 7 && (pass_mask & (1 << pr));
+        const bool left_first = do_l && (!do_r || arrival(pl) <= arrival(pr));
+        if (do_l && left_first)
+            if (int e = launch(pl, 0, 1)) return e;
+        if (do_r)
+            if (int e = launch(pr, 1, 1)) return e;
+        if (do_l && !left_first)
+            if (int e = launch(pl, 0, 1)) return e;
     }
     return 0;
 }
@@ -668,6 +704,7 @@ extern "C" int mccnn_sgm_single_path(const float* C, const uint8_t* image, float
     a.C[1] = C; a.S[1] = S; a.img[1] = image; a.disp[1] = nullptr;
     a.H = H; a.W = W; a.D = D; a.Dp = disp_pitch(D);
     a.nsides = 1;
+    a.side0 = 0;
     a.store_s = 1;
     set_params(a, params);
     if (path == 1) {  // penalty channels 0/1 are never written by the reference: P1 = P2 = 0
