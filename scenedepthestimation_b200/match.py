@@ -23,6 +23,8 @@ parser.add_argument("--image-dir", type=str, default="./test/")
 parser.add_argument("--out-dir", type=str, default="./disparity/")
 parser.add_argument("--first", type=int, default=1)
 parser.add_argument("--last", type=int, default=18)
+parser.add_argument("--depth", type=int, default=3, help="pairs in flight on separate CUDA streams (1 = the reference's "
+                    "strictly sequential loop, with the per-stage times of match.py:95-103 printed at the end)")
 
 
 def shard(ids, rank: int, world: int):
@@ -132,16 +134,41 @@ def main(argv=None):
     weights = synthetic.glorot_weights() if args.weights == 'random' else args.weights
     detail_time = np.zeros(shape=[7], dtype=np.float32)
     os.makedirs(args.out_dir, exist_ok=True)
-    for i in shard(range(args.first, args.last + 1), rank, world):
+    ids = shard(range(args.first, args.last + 1), rank, world)
+
+    def read(i):
         left = cv2.imread(os.path.join(args.image_dir, 'left_{}.jpg'.format(i)), cv2.IMREAD_GRAYSCALE)
         right = cv2.imread(os.path.join(args.image_dir, 'right_{}.jpg'.format(i)), cv2.IMREAD_GRAYSCALE)
         if left is None or right is None:
             raise FileNotFoundError(f"pair {i} under {args.image_dir}")
-        out = match_batch([(left, right)], weights, args.ndisp, 2, detail_time)[0]
+        return left, right
+
+    def write(i, out):
         cv2.imwrite(os.path.join(args.out_dir, 'ld{}.png'.format(i)), out)
-    names = ["features", "cost volume", '"*" cost aggregation', "SGM", "WTA & Subpixel refinement", "LR Check", "Filtering"]
-    for n, t in zip(names, detail_time):
-        print('time of {}: {}s'.format(n, t))
+
+    if args.depth <= 1:
+        for i in ids:
+            write(i, match_batch([read(i)], weights, args.ndisp, 2, detail_time)[0])
+        names = ["features", "cost volume", '"*" cost aggregation', "SGM", "WTA & Subpixel refinement", "LR Check", "Filtering"]
+        for n, t in zip(names, detail_time):
+            print('time of {}: {}s'.format(n, t))
+        return
+    # streamed: imread of pair k+1, the copies and the kernels of the pairs in flight, and imwrite of pair k-1 overlap;
+    # a new matcher (streams, pinned buffers, workspaces) whenever the image shape changes
+    m, shape = None, None
+    for i in ids:
+        left, right = read(i)
+        if left.shape != shape:
+            if m is not None:
+                for tag, img in m.drain():
+                    write(tag, img)
+            m, shape = StreamedMatcher(left.shape[0], left.shape[1], weights, args.ndisp, 2, args.depth), left.shape
+        done = m.submit(left, right, i)
+        if done is not None:
+            write(*done)
+    if m is not None:
+        for tag, img in m.drain():
+            write(tag, img)
 
 
 if __name__ == "__main__":

@@ -437,6 +437,39 @@ def test_pipeline_with_cbca_equals_stage_composition(eng):
     assert not np.array_equal(base_l, exp)  # the stage does something
 
 
+def test_cli_drop_ins_end_to_end(eng, tmp_path, monkeypatch):
+    """match_single.py / match.py / error_calculate.py as a user runs them: image files in, PNG out (match_single.py:30-55,
+    match.py:46-90, error_calculate.py:58-83), against the in-memory API on the same decoded images."""
+    cv2 = pytest.importorskip("cv2")
+    from scenedepthestimation_b200 import error_calculate as ec, match, match_single, synthetic as syn
+
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("eval"), os.makedirs("test")
+    w = syn.glorot_weights()
+    il, ir, gt = syn.textured_pair(60, 96, 32, 5)
+    cv2.imwrite("eval/left_3.png", il), cv2.imwrite("eval/right_3.png", ir)
+    match_single.main(["-i", "3", "-f", "11_11", "--weights", "random", "--ndisp", "32"])
+    got = cv2.imread("result/11_11/ld3.png", cv2.IMREAD_GRAYSCALE)
+    assert np.array_equal(got, match_single.match_images(il, ir, w, 32, 1))
+    pairs = {}
+    for i in (1, 2, 3, 4):
+        a, b, _ = syn.textured_pair(48 if i < 4 else 40, 80, 32, 10 + i)  # the last pair has another shape
+        cv2.imwrite(f"test/left_{i}.jpg", a), cv2.imwrite(f"test/right_{i}.jpg", b)
+        pairs[i] = (cv2.imread(f"test/left_{i}.jpg", cv2.IMREAD_GRAYSCALE), cv2.imread(f"test/right_{i}.jpg", cv2.IMREAD_GRAYSCALE))
+    for depth in (1, 3):
+        match.main(["--weights", "random", "--ndisp", "32", "--first", "1", "--last", "4", "--depth", str(depth),
+                    "--out-dir", f"./disparity{depth}/"])
+        for i, (a, b) in pairs.items():
+            out = cv2.imread(f"disparity{depth}/ld{i}.png", cv2.IMREAD_GRAYSCALE)
+            assert np.array_equal(out, match.match_batch([(a, b)], w, ndisp=32, scale=2)[0]), (depth, i)
+    # the reference's metric on its own output convention: GT at full resolution, halved after the resize (:65-66)
+    full = cv2.resize(gt.astype(np.float32) * 2.0, (96, 60))
+    rate_gpu = ec.error_rate(got, full)
+    d, t = got.astype(np.float64), full / 2.0
+    valid = np.isfinite(t) & (t != 0)
+    assert rate_gpu == pytest.approx(float(np.sum(valid & (np.abs(d - t) > 1))) / d.size)
+
+
 def test_errors_are_loud(eng):
     from scenedepthestimation_b200 import _lib
 
