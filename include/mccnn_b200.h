@@ -109,6 +109,13 @@ int mccnn_conv_tower_fp32(const float* padded, const void* packed_weights, float
  * accumulator, entries never written = fill (1.0 in the reference). CR may be NULL. */
 int mccnn_cost_volume(const float* fl, const float* fr, float* CL, float* CR,
                       int H, int W, int D, float fill, void* stream);
+/* Tensor-core variant, same contract and the same bits out: the exact sum of f*g is taken from tcgen05 MMAs on 8-bit
+ * slices of the features, the fp32 rounding residuals of the reference's products from the CUDA cores, and every
+ * evaluation whose rounding cannot be proven is redone with the literal loop (csrc/cost_volume_tc.cu).
+ * workspace: mccnn_cost_volume_tc_workspace_bytes(H, W) bytes, 256-byte aligned. */
+size_t mccnn_cost_volume_tc_workspace_bytes(int H, int W);
+int mccnn_cost_volume_tc(const float* fl, const float* fr, float* CL, float* CR, void* workspace, size_t workspace_bytes,
+                         int H, int W, int D, float fill, void* stream);
 /* [H][W][Dp] -> dense [D][H][W] (layout of the reference's CPU compute_cost_volume, :48-73). */
 int mccnn_volume_to_dhw(const float* vol, float* out_dhw, int H, int W, int D, void* stream);
 

@@ -41,6 +41,8 @@ SIGNATURES = {
     "mccnn_conv_tower": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
     "mccnn_conv_tower_fp32": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
     "mccnn_cost_volume": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "mccnn_cost_volume_tc_workspace_bytes": (_sz, [_i, _i]),
+    "mccnn_cost_volume_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp]),
     "mccnn_volume_to_dhw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mccnn_cross_arms": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "mccnn_cbca": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -117,6 +117,21 @@ def cost_volume(fl: torch.Tensor, fr: torch.Tensor, D: int, fill: float = 1.0, r
     return CL, CR
 
 
+def cost_volume_tc(fl: torch.Tensor, fr: torch.Tensor, D: int, fill: float = 1.0, right: bool = True):
+    """Tensor-core variant of cost_volume: same contract, same bits."""
+    lib = _lib.load()
+    H, W, F = fl.shape
+    assert F == FEATURES and fr.shape == fl.shape
+    Dp = disp_pitch(D)
+    CL = torch.empty((H, W, Dp), dtype=torch.float32, device="cuda")
+    CR = torch.empty((H, W, Dp), dtype=torch.float32, device="cuda") if right else None
+    nws = lib.mccnn_cost_volume_tc_workspace_bytes(H, W)
+    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mccnn_cost_volume_tc(_p(fl), _p(fr), _p(CL), _p(CR), _p(ws), nws, H, W, D, float(fill), _stream()),
+               "mccnn_cost_volume_tc")
+    return CL, CR
+
+
 def volume_to_dhw(vol: torch.Tensor, D: int) -> torch.Tensor:
     H, W, _ = vol.shape
     out = torch.empty((D, H, W), dtype=torch.float32, device="cuda")

@@ -477,3 +477,41 @@ def test_errors_are_loud(eng):
     with pytest.raises(RuntimeError):
         eng.sgm(t, t, torch.zeros((2, 2), dtype=torch.uint8, device="cuda"), torch.zeros((2, 2), dtype=torch.uint8, device="cuda"), 4)
     assert b"too small" in _lib.load().mccnn_last_error()
+
+
+@pytest.mark.parametrize("H,W,D,kind", [(3, 200, 150, "unit"), (2, 65, 64, "unit"), (4, 129, 7, "unit"), (2, 64, 300, "unit"),
+                                        (5, 700, 256, "unit"), (3, 900, 800, "corr"), (4, 300, 128, "scaled"), (2, 140, 70, "wild")])
+def test_cost_volume_tensor_core_variant_is_bit_identical(eng, H, W, D, kind):
+    """mccnn_cost_volume_tc (exact slice-pair sums on tcgen05 + fp32 residuals + literal re-evaluation of the ambiguous
+    roundings) against mccnn_cost_volume and the oracle: the same bits, fills and pads included."""
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import synthetic as syn
+
+    if kind == "corr":
+        fl, fr, _ = syn.correlated_features(H, W, D, 64, 177)
+    else:
+        fl, fr = syn.unit_features(H, W, 64, 178 + H)
+    if kind == "scaled":
+        rng = np.random.default_rng(5)
+        fl = (fl * rng.uniform(1e-3, 1e3, (H, W, 1))).astype(np.float32)
+        fr = (fr * rng.uniform(1e-3, 1e3, (H, W, 1))).astype(np.float32)
+    if kind == "wild":
+        fl[0, 3, 5] = np.inf; fl[0, 9, 1] = np.nan; fr[0, 20, 2] = -np.inf
+        fr[1, 7, :] = np.float32(3e37); fl[1, 30, :] = np.float32(-2e37)
+        fl[1, 11, :] = np.float32(1e-30); fr[1, 13, :] = np.float32(1e-25)
+        fl[1, 50, 0::2] = 0.0; fr[1, 60, :] = np.float32(1e-44); fl[0, 70, :] = 0.0
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    TL, TR = eng.cost_volume_tc(dev(fl), dev(fr), D)
+    for got, exp in ((TL, CL), (TR, CR)):
+        g, e = got.cpu().numpy(), exp.cpu().numpy()
+        nan = np.isnan(e)
+        assert np.array_equal(np.isnan(g), nan)
+        assert np.array_equal(_bits(g)[~nan], _bits(e)[~nan])
+    if kind != "wild":
+        cl, cr = st.cost_volume(fl, fr, D)
+        assert np.array_equal(_bits(unpitch(TL, D)), _bits(cl)) and np.array_equal(_bits(unpitch(TR, D)), _bits(cr))
+    only_left, none = eng.cost_volume_tc(dev(fl), dev(fr), D, fill=-0.0, right=False)
+    ref_left, _ = eng.cost_volume(dev(fl), dev(fr), D, fill=-0.0, right=False)
+    g, e = only_left.cpu().numpy(), ref_left.cpu().numpy()
+    nan = np.isnan(e)
+    assert none is None and np.array_equal(_bits(g)[~nan], _bits(e)[~nan])
