@@ -116,12 +116,11 @@ __global__ void __launch_bounds__(CV_THREADS) cost_volume_band_kernel(const floa
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int y = blockIdx.z;
     const int x0 = blockIdx.y * T;
-    // u tiles of this x tile: aligned to multiples of T (negative allowed), from the one holding x0-(D-1)
-    const int first_ut = (x0 - (D - 1) >= 0) ? (x0 - (D - 1)) / T : -((-(x0 - (D - 1)) + T - 1) / T);
-    const int ut = first_ut + (int)blockIdx.x;
+    // u tiles of this x tile hang off the diagonal: [x0 - T*t, +T), t = 0 .. ceil((D-1+T)/T)-1. Their union
+    // [x0 - T*(nut-1), x0 + T) holds every u = x - d, 0 <= d < D, of the x tile with the fewest tiles (the staging
+    // takes any start pixel), e.g. 14 instead of 15 tiles at D = 800 and 3 instead of 4 at D = 128.
     (void)ut_min;
-    const int u0 = ut * T;
-    if (u0 > x0 + T - 1) return;                  // entirely above the diagonal: d < 0
+    const int u0 = x0 - T * (int)blockIdx.x;
     if (CR == nullptr && x0 >= W) return;         // nothing to write
     const bool has_left = x0 < W, has_right = (u0 + T - 1 >= 0) && (u0 < W);
     const bool compute = has_left && has_right;
@@ -222,7 +221,7 @@ extern "C" int mccnn_cost_volume(const float* fl, const float* fr, float* CL, fl
     // x tiles cover [0, W + D - 1) when CR is written (the tiles past the image edge write CR's fill entries);
     // each x tile meets at most ceil((D - 1 + 2T - 1) / T) u tiles of the band
     const int nxt = ceil_div(CR ? (W + D - 1) : W, T);
-    const int nut = (D - 1 + T - 1) / T + 2;
+    const int nut = (D - 1 + T + T - 1) / T;
     MCCNN_REQUIRE(nxt <= 65535, MCCNN_EINVAL, "mccnn_cost_volume: image too wide");
     dim3 grid(nut, nxt, H);
     cost_volume_band_kernel<<<grid, CV_THREADS, 0, stream>>>(fl, fr, CL, CR, H, W, D, Dp, fill, 0);

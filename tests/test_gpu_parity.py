@@ -515,3 +515,52 @@ def test_cost_volume_tensor_core_variant_is_bit_identical(eng, H, W, D, kind):
     g, e = only_left.cpu().numpy(), ref_left.cpu().numpy()
     nan = np.isnan(e)
     assert none is None and np.array_equal(_bits(g)[~nan], _bits(e)[~nan])
+
+
+@pytest.mark.parametrize("kind", ["constant", "two_minima", "quantised", "identical_images"])
+def test_exact_cost_ties_and_degenerate_inputs(eng, kind):
+    """Exact-cost ties (north_star's one allowed source of disparity differences) resolve exactly as in the reference:
+    first strict minimum (:805-811). Volumes are built by hand so that many disparities tie in every pixel."""
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import synthetic as syn
+
+    H, W, D = 17, 45, 52
+    rng = np.random.default_rng(11)
+    il, ir = syn.noise_pair(H, W, 12)
+    if kind == "constant":
+        cl = np.full((H, W, D), 0.25, np.float32)
+        cr = cl.copy()
+    elif kind == "two_minima":
+        cl = np.ones((H, W, D), np.float32)
+        a = rng.integers(0, D, (H, W))
+        b = rng.integers(0, D, (H, W))
+        np.put_along_axis(cl, a[..., None], -0.5, axis=2)
+        np.put_along_axis(cl, b[..., None], -0.5, axis=2)
+        cr = cl[:, ::-1].copy()
+    elif kind == "quantised":
+        cl = (rng.integers(0, 4, (H, W, D)) * 0.25).astype(np.float32)
+        cr = (rng.integers(0, 4, (H, W, D)) * 0.25).astype(np.float32)
+    else:  # identical images and features: the true match is d = 0 everywhere, with -1 + rounding on the diagonal
+        ir = il.copy()
+        f, _ = syn.unit_features(H, W, 64, 13)
+        cl, cr = st.cost_volume(f, f, D)
+    Dp = eng.disp_pitch(D)
+    def pitched(v):
+        t = torch.full((H, W, Dp), float("inf"), device="cuda")
+        t[..., :D] = dev(v)
+        return t
+    pl, pr = st.sgm_penalties(il), st.sgm_penalties(ir)
+    sl, sr = st.sgm_all_paths(cl, cr, pl, pr)
+    exp_l, exp_r = st.wta(sl), st.wta(sr)
+    SL, SR, dl, dr = eng.sgm(pitched(cl), pitched(cr), dev(il), dev(ir), D, keep_volumes=True)
+    assert np.array_equal(unpitch(SL, D), sl) and np.array_equal(unpitch(SR, D), sr)
+    assert np.array_equal(dl.cpu().numpy(), exp_l) and np.array_equal(dr.cpu().numpy(), exp_r)
+    assert np.array_equal(eng.wta(SL, D).cpu().numpy(), exp_l)
+    if kind == "constant":
+        assert (exp_l == 0).all()
+    fl_o, _ = st.lr_flags(exp_l, exp_r)
+    flag, _ = eng.lr_flags(dl, dr, right=False)
+    assert np.array_equal(flag.cpu().numpy(), fl_o)
+    filled = st.lrc_fill(exp_l, fl_o)
+    assert np.array_equal(eng.lrc_fill(dl, flag).cpu().numpy(), filled)
+    assert np.array_equal(eng.median5(dev(filled), dl).cpu().numpy(), st.median5(filled, exp_l))
