@@ -451,6 +451,12 @@ def test_cli_drop_ins_end_to_end(eng, tmp_path, monkeypatch):
     match_single.main(["-i", "3", "-f", "11_11", "--weights", "random", "--ndisp", "32"])
     got = cv2.imread("result/11_11/ld3.png", cv2.IMREAD_GRAYSCALE)
     assert np.array_equal(got, match_single.match_images(il, ir, w, 32, 1))
+    from scenedepthestimation_b200 import match_single_ui
+
+    os.makedirs("UI_use")
+    cv2.imwrite("UI_use/left_7.png", il), cv2.imwrite("UI_use/right_7.png", ir)
+    match_single_ui.main(["-i", "7", "-f", "ui", "--weights", "random", "--ndisp", "32"])  # match_single_ui.py:30,55
+    assert np.array_equal(cv2.imread("result/ui/ld7.png", cv2.IMREAD_GRAYSCALE), match_single.match_images(il, ir, w, 32, 2))
     pairs = {}
     for i in (1, 2, 3, 4):
         a, b, _ = syn.textured_pair(48 if i < 4 else 40, 80, 32, 10 + i)  # the last pair has another shape
