@@ -30,19 +30,27 @@ namespace {
 constexpr int NF = MCCNN_FEATURES;
 constexpr int NS = 6;                     // slices per feature
 constexpr int NACC = 6;                   // accumulators: weight classes s + t = 0..5
-constexpr int TM = 128, TN = 64;          // tile: x pixels, u pixels
+constexpr int TM = 128, TN = 32;          // tile: x pixels, u pixels
 constexpr int A_SLICE = TM * 128, B_SLICE = TN * 128;  // bytes of one fp16 slice tile (128-byte rows)
-constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + NS * A_SLICE;            // 98304
-constexpr int OFF_A32 = OFF_B + NS * B_SLICE;          // 147456: two k-halves of [128 px][32 floats]
-constexpr int OFF_B32 = OFF_A32 + 2 * TM * 128;        // 180224: two k-halves of [64 px][32 floats]
-constexpr int RES_PITCH = 66;
-constexpr int OFF_RES = OFF_B32 + 2 * TN * 128;        // 196608
-constexpr int OFF_SB = OFF_RES + TM * RES_PITCH * 4;   // 230400: scale, norm of the 64 u pixels
-constexpr int OFF_BAR = OFF_SB + 2 * TN * 8;           // 231424 (scale, norm * 2^-41 as doubles)
-constexpr int TC_SMEM = OFF_BAR + 64 + 960;            // barriers + alignment slack = 232448, the sm_100 maximum
-constexpr int NCW = 16;            // compute warps
-constexpr int CVT_THREADS = 32 * (NCW + 1);  // + 1 control warp
+constexpr int OFF_A = 0;                               // six slices of the x block
+constexpr int OFF_A32 = OFF_A + NS * A_SLICE;          // 98304: two k-halves of [128 px][32 floats]
+constexpr int OFF_B = OFF_A32 + 2 * TM * 128;          // 131072: two stages of {six slices, two k-halves of [32 px][32 floats]}
+constexpr int OFF_B32 = NS * B_SLICE;                  // fp32 rows inside a B stage
+constexpr int B_STAGE = OFF_B32 + 2 * TN * 128;        // 32768
+constexpr int OFF_RES = OFF_B + 2 * B_STAGE;           // 196608: two stages of [128][32] floats (column ^ (row & 31))
+constexpr int RES_STAGE = TM * TN * 4;                 // 16384
+constexpr int OFF_SB = OFF_RES + 2 * RES_STAGE;        // 229376: two stages of {scale, norm * 2^-41} of the 32 u pixels (doubles)
+constexpr int OFF_BAR = OFF_SB + 2 * 2 * TN * 8;       // 230400
+constexpr int TC_SMEM = OFF_BAR + 128 + 1024;          // barriers + alignment slack
+#ifndef MCCNN_CVTC_NRW
+#define MCCNN_CVTC_NRW 8
+#endif
+constexpr int NRW = MCCNN_CVTC_NRW;  // residual warps (8 or 16)
+constexpr int NWX = NRW / 4;       // residual warps along x; a warp covers 128 / NWX tile rows x 8 tile columns
+constexpr int XW = TM / NWX;       // tile rows per residual warp
+constexpr int TI = XW / 8;         // evaluations along x per residual thread
+constexpr int NEW = 8;             // epilogue warps
+constexpr int CVT_THREADS = 32 * (NRW + NEW + 1);  // + 1 control warp
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);  // f16 x f16 -> f32
 constexpr int PADPIX = 128;               // per-pixel arrays carry this many entries of padding on both ends
@@ -86,6 +94,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
                  : "r"(taddr));
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -218,11 +234,44 @@ __global__ void __launch_bounds__(128) cv_fixup_kernel(const float* __restrict__
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NCW) : "memory"); }  // the compute warps
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NEW) : "memory"); }  // the epilogue warps
 
-// Warp roles: warps 0..7 compute (residuals, epilogue, stores), warp 8 = control (TMA loads, MMA issue, TMEM allocation).
-// Barriers (one phase per tile unless noted): b_full (TMA bytes), mma (tcgen05.commit), b_free (one arrival per compute warp: the compute
-// warps have read the fp32 B rows), t_free (one per compute warp: TMEM has been read), a_full (TMA bytes, one phase per item).
+// position in the tile sequence of one CTA: items (image row y, block of TM x pixels), each with its run of u tiles
+struct TileCursor {
+    int item, stride, nitems;
+    int y, x0, ut, ut_last;
+    bool first;  // first tile of its item (the A operand changes)
+    __device__ void enter(const CvTcArgs& a) {
+        if (item >= nitems) return;
+        y = item / a.tiles_x;
+        x0 = (item % a.tiles_x) * TM;
+        ut = max(x0 - (a.D - 1), 0) / TN;
+        ut_last = min(x0 + TM - 1, a.W - 1) / TN;
+        first = true;
+    }
+    __device__ void start(const CvTcArgs& a, int first_item, int step) {
+        item = first_item; stride = step; nitems = a.nitems;
+        enter(a);
+    }
+    __device__ bool valid() const { return item < nitems; }
+    __device__ void next(const CvTcArgs& a) {
+        if (ut < ut_last) {
+            ut++;
+            first = false;
+        } else {
+            item += stride;
+            enter(a);
+        }
+    }
+};
+
+// Warp roles: warps 0..15 residuals (FP32 pipe), warps 16..23 epilogue (TMEM -> fp64 -> rounding test -> stores; warp 16+e owns
+// TMEM lanes 32(e&3).. = tile rows x and the 16 tile columns u of half e>>2), warp 24 = control (TMA loads, MMA issue, TMEM allocation). The B operands, the
+// TMEM accumulators and the residual / result tile are double-buffered (stage = tile & 1), so the residual loop of tile
+// n + 1 runs while the epilogue warps finish tile n: the kernel is bound by the FP32 pipe alone.
+// Barriers, per stage unless noted: b_full (TMA bytes), mma (tcgen05.commit), b_free (16 arrivals: the residual warps have read
+// the fp32 B rows), t_free (8: TMEM has been read), res_full (16: residual sums are in shared memory), res_free (8: the
+// result tile has been stored), a_full (TMA bytes, one phase per item).
 __global__ void __launch_bounds__(CVT_THREADS, 1)
 cost_volume_tc_kernel(const __grid_constant__ CUtensorMap tmSL, const __grid_constant__ CUtensorMap tmSR,
                       const __grid_constant__ CUtensorMap tmFL, const __grid_constant__ CUtensorMap tmFR, const CvTcArgs a) {
@@ -231,24 +280,28 @@ cost_volume_tc_kernel(const __grid_constant__ CUtensorMap tmSL, const __grid_con
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - raw);
     uint64_t* bar_a_full = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
-    uint64_t* bar_b_full = bar_a_full + 1;
-    uint64_t* bar_mma = bar_a_full + 2;
-    uint64_t* bar_b_free = bar_a_full + 3;
-    uint64_t* bar_t_free = bar_a_full + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_a_full + 5);
-    float* res = reinterpret_cast<float*>(sm + OFF_RES);  // [128][RES_PITCH]: residual sums, then the results
-    double* sbd = reinterpret_cast<double*>(sm + OFF_SB);  // [0..63] scale, [64..127] norm * 2^-41 of the u pixels
+    uint64_t* bar_b_full = bar_a_full + 1;    // [2]
+    uint64_t* bar_mma = bar_a_full + 3;       // [2]
+    uint64_t* bar_b_free = bar_a_full + 5;    // [2]
+    uint64_t* bar_t_free = bar_a_full + 7;    // [2]
+    uint64_t* bar_res_full = bar_a_full + 9;  // [2]
+    uint64_t* bar_res_free = bar_a_full + 11; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_a_full + 13);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         mbar_init(bar_a_full, 1);
-        mbar_init(bar_b_full, 1);
-        mbar_init(bar_mma, 1);
-        mbar_init(bar_b_free, NCW);
-        mbar_init(bar_t_free, NCW);
+        for (int s = 0; s < 2; s++) {
+            mbar_init(bar_b_full + s, 1);
+            mbar_init(bar_mma + s, 1);
+            mbar_init(bar_b_free + s, NRW);
+            mbar_init(bar_t_free + s, NEW);
+            mbar_init(bar_res_full + s, NRW);
+            mbar_init(bar_res_free + s, NEW);
+        }
         mbar_fence_init();
     }
-    if (warp == NCW) {
+    if (warp == NRW + NEW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -258,208 +311,253 @@ cost_volume_tc_kernel(const __grid_constant__ CUtensorMap tmSL, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == NCW) {
+    if (warp == NRW + NEW) {
         // ================================================================= control warp
         if (lane == 0) {
-            uint32_t n_item = 0, n_tile = 0;  // items / tiles issued so far (barrier phases)
-            for (int item = blockIdx.x; item < a.nitems; item += gridDim.x, n_item++) {
-                const int y = item / a.tiles_x, x0 = (item % a.tiles_x) * TM;
-                const long long prow = (long long)y * a.W;
-                const int u_lo = max(x0 - (a.D - 1), 0), u_hi = min(x0 + TM - 1, a.W - 1);
-                bool a_pending = true;
-                for (int ut = u_lo / TN; ut <= u_hi / TN; ut++, n_tile++) {
-                    const int u0 = ut * TN;
-                    if (n_tile > 0) {  // the previous tile has left the operand buffers
-                        mbar_wait(bar_b_free, (n_tile - 1) & 1u);
-                        mbar_wait(bar_mma, (n_tile - 1) & 1u);
-                    }
-                    if (a_pending) {
+            TileCursor ld, mm;  // load cursor runs up to two tiles ahead of the MMA cursor
+            ld.start(a, blockIdx.x, gridDim.x);
+            mm.start(a, blockIdx.x, gridDim.x);
+            uint32_t nl = 0, nm = 0, n_item = 0;
+            // tile k has left its operand stage: its fp32 rows are read and its MMAs are complete
+            auto wait_tile_done = [&](uint32_t k) {
+                mbar_wait(bar_b_free + (k & 1u), (k >> 1) & 1u);
+                mbar_wait(bar_mma + (k & 1u), (k >> 1) & 1u);
+            };
+            while (mm.valid()) {
+                while (ld.valid() && nl < nm + 2) {
+                    if (ld.first && nl != nm) break;  // the A operand changes: every MMA of the previous item must be issued
+                    const uint32_t s = nl & 1u;
+                    const long long prow = (long long)ld.y * a.W;
+                    if (ld.first) {
+                        if (nl >= 1) wait_tile_done(nl - 1);
+                        if (nl >= 2) wait_tile_done(nl - 2);
                         mbar_expect_tx(bar_a_full, NS * A_SLICE + 2 * TM * 128);
-                        for (int s = 0; s < NS; s++)
-                            tma_load_2d(base + OFF_A + s * A_SLICE, &tmSL, 0, (int)((long long)s * a.P + prow + x0), bar_a_full);
-                        tma_load_2d(base + OFF_A32, &tmFL, 0, (int)(prow + x0), bar_a_full);
-                        tma_load_2d(base + OFF_A32 + TM * 128, &tmFL, 32, (int)(prow + x0), bar_a_full);
+                        for (int sl = 0; sl < NS; sl++)
+                            tma_load_2d(base + OFF_A + sl * A_SLICE, &tmSL, 0, (int)((long long)sl * a.P + prow + ld.x0), bar_a_full);
+                        tma_load_2d(base + OFF_A32, &tmFL, 0, (int)(prow + ld.x0), bar_a_full);
+                        tma_load_2d(base + OFF_A32 + TM * 128, &tmFL, 32, (int)(prow + ld.x0), bar_a_full);
+                    } else if (nl >= 2) {
+                        wait_tile_done(nl - 2);
                     }
-                    mbar_expect_tx(bar_b_full, NS * B_SLICE + 2 * TN * 128);
-                    for (int s = 0; s < NS; s++)
-                        tma_load_2d(base + OFF_B + s * B_SLICE, &tmSR, 0, (int)((long long)s * a.P + prow + u0), bar_b_full);
-                    tma_load_2d(base + OFF_B32, &tmFR, 0, (int)(prow + u0), bar_b_full);
-                    tma_load_2d(base + OFF_B32 + TN * 128, &tmFR, 32, (int)(prow + u0), bar_b_full);
-                    if (a_pending) {
-                        mbar_wait(bar_a_full, n_item & 1u);
-                        a_pending = false;
-                    }
-                    mbar_wait(bar_b_full, n_tile & 1u);
-                    if (n_tile > 0) mbar_wait(bar_t_free, (n_tile - 1) & 1u);  // the accumulators have been read
-                    tc_fence_after();
+                    const int u0 = ld.ut * TN;
+                    const uint32_t bst = base + OFF_B + s * B_STAGE;
+                    mbar_expect_tx(bar_b_full + s, NS * B_SLICE + 2 * TN * 128);
+                    for (int sl = 0; sl < NS; sl++)
+                        tma_load_2d(bst + sl * B_SLICE, &tmSR, 0, (int)((long long)sl * a.P + prow + u0), bar_b_full + s);
+                    tma_load_2d(bst + OFF_B32, &tmFR, 0, (int)(prow + u0), bar_b_full + s);
+                    tma_load_2d(bst + OFF_B32 + TN * 128, &tmFR, 32, (int)(prow + u0), bar_b_full + s);
+                    ld.next(a);
+                    nl++;
+                }
+                const uint32_t s = nm & 1u;
+                if (mm.first) {
+                    mbar_wait(bar_a_full, n_item & 1u);
+                    n_item++;
+                }
+                mbar_wait(bar_b_full + s, (nm >> 1) & 1u);
+                if (nm >= 2) mbar_wait(bar_t_free + s, ((nm - 2) >> 1) & 1u);  // the accumulators of tile nm - 2 have been read
+                tc_fence_after();
+                const uint32_t bst = base + OFF_B + s * B_STAGE;
 #pragma unroll 1
-                    for (int v = 0; v < NACC; v++) {
-                        for (int s = 0; s <= v; s++) {
-                            const int t = v - s;
-                            const uint64_t ad = sw128_desc(base + OFF_A + s * A_SLICE);
-                            const uint64_t bd = sw128_desc(base + OFF_B + t * B_SLICE);
+                for (int v = 0; v < NACC; v++) {
+                    for (int sl = 0; sl <= v; sl++) {
+                        const int t = v - sl;
+                        const uint64_t ad = sw128_desc(base + OFF_A + sl * A_SLICE);
+                        const uint64_t bd = sw128_desc(bst + t * B_SLICE);
 #pragma unroll
-                            for (int k = 0; k < 4; k++)
-                                umma_f16(tmem_base + (uint32_t)v * TN, ad + 2 * k, bd + 2 * k, (s | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < 4; k++)
+                            umma_f16(tmem_base + s * (NACC * TN) + (uint32_t)v * TN, ad + 2 * k, bd + 2 * k, (sl | k) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(bar_mma + s);
+                mm.next(a);
+                nm++;
+            }
+        }
+    } else if (warp < NRW) {
+        // ================================================================= residual warps
+        // residual tile of a thread: x = XW*wx + tx + 8i (i < TI), u = 8*wy + tyl + 4j (j < 2)
+        const int tx = lane & 7, tyl = lane >> 3, wx = warp % NWX, wy = warp / NWX;
+        const int ub = 8 * wy + tyl;
+        TileCursor tc;
+        tc.start(a, blockIdx.x, gridDim.x);
+        uint32_t n = 0, n_item = 0;
+        for (; tc.valid(); tc.next(a), n++) {
+            const uint32_t s = n & 1u;
+            const int x0 = tc.x0, u0 = tc.ut * TN;
+            if (tc.first) {
+                mbar_wait(bar_a_full, n_item & 1u);
+                n_item++;
+            }
+            mbar_wait(bar_b_full + s, (n >> 1) & 1u);
+            // ---- fp32 rounding residuals of the 64 products of each of the TI x 2 evaluations of this thread
+            float2 es[TI][2];
+#pragma unroll
+            for (int i = 0; i < TI; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) es[i][j] = make_float2(0.f, 0.f);
+            // this warp's block is x in [XW wx, +XW) x u in [8 wy, +8): skipped when it lies outside the band 0 <= d < D
+            const int wd_max = (x0 + XW * wx + XW - 1) - (u0 + 8 * wy), wd_min = (x0 + XW * wx) - (u0 + 8 * wy + 7);
+            if (wd_max >= 0 && wd_min < a.D && x0 + XW * wx < a.W && u0 + 8 * wy < a.W) {
+                const unsigned char* ap = sm + OFF_A32 + (XW * wx + tx) * 128;  // + i * 1024: rows tx + 8i keep (row & 7) = tx
+                const unsigned char* bp = sm + OFF_B + s * B_STAGE + OFF_B32 + ub * 128;  // + j * 512: rows ub + 4j, (row & 7) = tyl + 4j
+#pragma unroll 4
+                for (int kc = 0; kc < 16; kc++) {  // 4 features per step: 16-byte chunk kc & 7 of k half kc >> 3
+                    const int c = kc & 7;
+                    const unsigned char* apk = ap + (kc >> 3) * (TM * 128) + ((c ^ tx) << 4);
+                    const unsigned char* bpk = bp + (kc >> 3) * (TN * 128);
+                    float4 bv[2];
+#pragma unroll
+                    for (int j = 0; j < 2; j++) bv[j] = *reinterpret_cast<const float4*>(bpk + j * 512 + ((c ^ (tyl + 4 * j)) << 4));
+#pragma unroll
+                    for (int i = 0; i < TI; i++) {
+                        const float4 av = *reinterpret_cast<const float4*>(apk + i * 1024);
+                        const float2 a01 = make_float2(av.x, av.y), a23 = make_float2(av.z, av.w);
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const float2 b01 = make_float2(bv[j].x, bv[j].y), b23 = make_float2(bv[j].z, bv[j].w);
+                            const float2 p0 = __fmul2_rn(a01, b01), p1 = __fmul2_rn(a23, b23);
+                            const float2 e0 = __ffma2_rn(a01, b01, make_float2(-p0.x, -p0.y));
+                            const float2 e1 = __ffma2_rn(a23, b23, make_float2(-p1.x, -p1.y));
+                            es[i][j] = __fadd2_rn(es[i][j], __fadd2_rn(e0, e1));
                         }
                     }
-                    umma_commit(bar_mma);
                 }
+            }
+            if (n >= 2) mbar_wait(bar_res_free + s, ((n - 2) >> 1) & 1u);  // the results of tile n - 2 have left the buffer
+            float* res = reinterpret_cast<float*>(sm + OFF_RES + s * RES_STAGE);
+#pragma unroll
+            for (int i = 0; i < TI; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int r = XW * wx + tx + 8 * i;
+                    res[r * TN + ((ub + 4 * j) ^ (r & 31))] = es[i][j].x + es[i][j].y;
+                }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_res_full + s);  // residual sums of this warp are in shared memory
+                mbar_arrive(bar_b_free + s);    // the fp32 rows of this tile are no longer read
             }
         }
     } else {
-        // ================================================================= compute warps
-        // residual tile of a thread: x = 64*wx + tx + 8i (i < 8), u = 8*wy + tyl + 4j (j < 2)
-        const int tx = lane & 7, tyl = lane >> 3, wx = warp & 1, wy = warp >> 1;
-        const int ub = 8 * wy + tyl;
-        // epilogue row / columns of a thread (TMEM lane = tile row): x = 32*q + lane, u = 16*part + 0..15
-        const int q = warp & 3, part = warp >> 2;
+        // ================================================================= epilogue warps
+        // row / columns of a thread (TMEM lane = tile row): x = x0 + 32*q + lane, u = u0 + 16*half + 0..15
+        const int ew = warp - NRW, q = ew & 3, half = ew >> 2, et = tid - 32 * NRW;
         const int xl = 32 * q + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + 16u * part;
-        uint32_t n_item = 0, n_tile = 0;
-
-        for (int item = blockIdx.x; item < a.nitems; item += gridDim.x, n_item++) {
-            const int y = item / a.tiles_x, x0 = (item % a.tiles_x) * TM;
-            const long long prow = (long long)y * a.W;
+        TileCursor tc;
+        tc.start(a, blockIdx.x, gridDim.x);
+        uint32_t n = 0;
+        double sa = 0.0, na = 0.0;
+        for (; tc.valid(); tc.next(a), n++) {
+            const uint32_t s = n & 1u;
+            const int x0 = tc.x0, u0 = tc.ut * TN;
+            const long long prow = (long long)tc.y * a.W;
             const int x = x0 + xl;
             const bool x_ok = x < a.W;
-            const double sa = (double)a.scaleL[PADPIX + prow + min(x, a.W - 1)];
-            const double na = (double)a.normL[PADPIX + prow + min(x, a.W - 1)];
-            const int u_lo = max(x0 - (a.D - 1), 0), u_hi = min(x0 + TM - 1, a.W - 1);
-            bool first = true;
-            for (int ut = u_lo / TN; ut <= u_hi / TN; ut++, n_tile++) {
-                const int u0 = ut * TN;
-                if (tid < 2 * TN) {
-                    const float vv = (tid < TN ? a.scaleR : a.normR)[PADPIX + prow + u0 + (tid & (TN - 1))];
-                    sbd[tid] = tid < TN ? (double)vv : (double)vv * 0x1p-41;
-                }
-                if (first) {
-                    mbar_wait(bar_a_full, n_item & 1u);
-                    first = false;
-                }
-                mbar_wait(bar_b_full, n_tile & 1u);
-                // ---- fp32 rounding residuals of the 64 products of each of the 8 x 2 evaluations of this thread
-                float2 es[8][2];
+            if (tc.first) {
+                sa = (double)a.scaleL[PADPIX + prow + min(x, a.W - 1)];
+                na = (double)a.normL[PADPIX + prow + min(x, a.W - 1)];
+            }
+            double* sbd = reinterpret_cast<double*>(sm + OFF_SB) + s * (2 * TN);  // [0..31] scale, [32..63] norm * 2^-41 of the u pixels
+            if (et < 2 * TN) {
+                const float vv = (et < TN ? a.scaleR : a.normR)[PADPIX + prow + u0 + (et & (TN - 1))];
+                sbd[et] = et < TN ? (double)vv : (double)vv * 0x1p-41;
+            }
+            mbar_wait(bar_res_full + s, (n >> 1) & 1u);
+            mbar_wait(bar_mma + s, (n >> 1) & 1u);
+            tc_fence_after();
+            epi_sync();  // sbd is complete
+            float* res = reinterpret_cast<float*>(sm + OFF_RES + s * RES_STAGE);
+            float* myrow = res + xl * TN;  // entry jj lives at column jj ^ lane
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + s * (NACC * TN);
+            // evaluations jj of this thread with 0 <= d < D and u < W: jj in [j_first, j_last]; d = dbase - jj
+            const int dbase = x - u0;
+            const int j_first = x_ok ? max(0, dbase - (a.D - 1)) : TN;
+            const int j_last = min(TN - 1, min(dbase, a.W - 1 - u0));
+            float* crp = a.CR ? a.CR + (prow + u0) * a.Dp + dbase : nullptr;  // CR[y][u][d] of jj = 0; +Dp-1 per jj
+            unsigned unproven = 0;
+#pragma unroll 1
+            for (int c = 4 * half; c < 4 * half + 4; c++) {
+                // nothing of this chunk is inside the band for any lane (tcgen05.ld is warp-collective: uniform test)
+                if (__all_sync(0xffffffffu, j_last < 4 * c || j_first > 4 * c + 3)) continue;
+                float r[NACC][4];
 #pragma unroll
-                for (int i = 0; i < 8; i++)
+                for (int v = 0; v < NACC; v++) tmem_ld4(taddr + (uint32_t)v * TN + 4u * c, r[v]);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 2; j++) es[i][j] = make_float2(0.f, 0.f);
-                // this warp's block is x in [64 wx, +64) x u in [8 wy, +8): skipped when it lies outside the band 0 <= d < D
-                const int wd_max = (x0 + 64 * wx + 63) - (u0 + 8 * wy), wd_min = (x0 + 64 * wx) - (u0 + 8 * wy + 7);
-                if (wd_max >= 0 && wd_min < a.D && x0 + 64 * wx < a.W && u0 + 8 * wy < a.W) {
-                    const unsigned char* ap = sm + OFF_A32 + (64 * wx + tx) * 128;  // + i * 1024: rows tx + 8i keep (row & 7) = tx
-                    const unsigned char* bp = sm + OFF_B32 + ub * 128;              // + j * 512: rows ub + 4j, (row & 7) = tyl + 4j
-#pragma unroll 4
-                    for (int kc = 0; kc < 16; kc++) {  // 4 features per step: 16-byte chunk kc & 7 of k half kc >> 3
-                        const int c = kc & 7;
-                        const unsigned char* apk = ap + (kc >> 3) * (TM * 128) + ((c ^ tx) << 4);
-                        const unsigned char* bpk = bp + (kc >> 3) * (TN * 128);
-                        float4 bv[2];
+                for (int j = 0; j < 4; j++) {
+                    // the six accumulators hold exact integers below 2^23: made int32 by a magic-number add, merged pairwise
+                    // (hi * 256 + lo), int32 -> fp64 by bit pasting (2^52 + 2^31 + n): no conversion-pipe instruction
+                    double dsum = 0.0;
 #pragma unroll
-                        for (int j = 0; j < 2; j++) bv[j] = *reinterpret_cast<const float4*>(bpk + j * 512 + ((c ^ (tyl + 4 * j)) << 4));
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const float4 av = *reinterpret_cast<const float4*>(apk + i * 1024);
-                            const float2 a01 = make_float2(av.x, av.y), a23 = make_float2(av.z, av.w);
-#pragma unroll
-                            for (int j = 0; j < 2; j++) {
-                                const float2 b01 = make_float2(bv[j].x, bv[j].y), b23 = make_float2(bv[j].z, bv[j].w);
-                                const float2 p0 = __fmul2_rn(a01, b01), p1 = __fmul2_rn(a23, b23);
-                                const float2 e0 = __ffma2_rn(a01, b01, make_float2(-p0.x, -p0.y));
-                                const float2 e1 = __ffma2_rn(a23, b23, make_float2(-p1.x, -p1.y));
-                                es[i][j] = __fadd2_rn(es[i][j], __fadd2_rn(e0, e1));
-                            }
-                        }
+                    for (int g = NACC / 2 - 1; g >= 0; g--) {  // smallest weight first
+                        const float mh = r[2 * g][j] + 12582912.0f, ml = r[2 * g + 1][j] + 12582912.0f;
+                        const int nn = (__float_as_int(mh) - 0x4B400000) * 256 + (__float_as_int(ml) - 0x4B400000);
+                        const double nd = __hiloint2double(0x43300000, nn ^ (int)0x80000000) - 4503601774854144.0;  // 2^52 + 2^31
+                        const double wg = __longlong_as_double((long long)(1023 - 8 * (2 * g + 3)) << 52);       // 2^-8(2g+3)
+                        dsum = fma(nd, wg, dsum);
                     }
+                    const int jj = 4 * c + j;
+                    const double sc = sa * sbd[jj];  // 2^(Ea+Eb), NaN for a wild pixel
+                    const double T = fma(dsum, sc, -(double)myrow[jj ^ lane]);
+                    const double eps = fma(na, sbd[TN + jj], fma(sc, 0x1p-40, 0x1p-140));
+                    const float lo = __double2float_rn(T - eps), hi = __double2float_rn(T + eps);
+                    const bool valid = jj >= j_first && jj <= j_last;
+                    if (valid && !(lo == hi)) unproven |= 1u << jj;  // no branch here: the four fp64 chains of a chunk interleave
+                    myrow[jj ^ lane] = -lo;
+                    // CR[y][u][d]: for a fixed u the lanes of a warp hold consecutive x = consecutive d
+                    if (valid && crp != nullptr) crp[(long long)jj * (a.Dp - 1)] = -lo;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_b_free);  // the fp32 rows of this tile are no longer read
+            }
+            // roundings that could not be proven (about 3 in 10^4): queued for the literal loop of cv_fixup_kernel, which
+            // patches both volumes after this kernel (the value stored above is then a placeholder)
+            while (unproven) {
+                const int jj = __ffs(unproven) - 1;
+                unproven &= unproven - 1;
+                const unsigned slot = atomicAdd(a.queue_count, 1u);
+                if (slot < a.queue_cap) {
+                    a.queue[slot] = ((unsigned long long)(prow + x) << 12) | (unsigned)(dbase - jj);
+                } else {
+                    const float outv = exact_dot_global(a.fl + (prow + x) * NF, a.fr + (prow + x - (dbase - jj)) * NF);
+                    myrow[jj ^ lane] = outv;
+                    if (crp != nullptr) crp[(long long)jj * (a.Dp - 1)] = outv;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_t_free + s);  // TMEM stage may take tile n + 2
+            epi_sync();                                   // results complete in shared memory
+            // ---- CL[y][x][d], d = x - u: for a fixed x the tile's u range is a contiguous run of d
+            {
+                const bool interior = x0 + TM <= a.W && u0 + TN <= a.W && x0 - (u0 + TN - 1) >= 0 && (x0 + TM - 1) - u0 < a.D;
+                const int ul = (TN - 1) - lane;
+                if (interior) {
+                    // row r of the tile: CL[y][x0 + r][x0 + r - u0 - ul]; r = ew + 8k, so (r & 31) = (ew + 8k) & 31
+                    float* p = a.CL + (prow + x0 + ew) * a.Dp + (x0 + ew - u0 - ul);
+                    const float* rp = res + ew * TN;
+                    const size_t step = (size_t)NEW * (a.Dp + 1);
 #pragma unroll
-                for (int i = 0; i < 8; i++)
-#pragma unroll
-                    for (int j = 0; j < 2; j++)
-                        res[(64 * wx + tx + 8 * i) * RES_PITCH + ub + 4 * j] = es[i][j].x + es[i][j].y;
-                compute_sync();  // residual sums and sbd are in shared memory
-
-                // ---- epilogue: integers from TMEM -> fp64 sum, minus the residuals, rounding-interval test
-                mbar_wait(bar_mma, n_tile & 1u);
-                tc_fence_after();
-                float* myrow = res + xl * RES_PITCH + 16 * part;
-                // evaluations jj of this thread with 0 <= d < D and u < W: jj in [j_first, j_last]; d = dbase - jj
-                const int dbase = x - (u0 + 16 * part);
-                const int j_first = x_ok ? max(0, dbase - (a.D - 1)) : 16;
-                const int j_last = min(15, min(dbase, a.W - 1 - (u0 + 16 * part)));
-                float* crp = a.CR ? a.CR + (prow + u0 + 16 * part) * a.Dp + dbase : nullptr;  // CR[y][u][d] of jj = 0; +Dp-1 per jj
-#pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    // nothing of this chunk is inside the band for any lane (tcgen05.ld is warp-collective: uniform test)
-                    if (__all_sync(0xffffffffu, j_last < 8 * c || j_first > 8 * c + 7)) continue;
-                    float r[NACC][8];
-#pragma unroll
-                    for (int v = 0; v < NACC; v++) tmem_ld8(taddr + (uint32_t)v * TN + 8u * c, r[v]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        // the six accumulators hold exact integers below 2^23: pairs are merged in int32 (hi * 256 + lo),
-                        // int32 -> fp64 by bit pasting (2^52 + 2^31 + n), no conversion-pipe instruction
-                        double dsum = 0.0;
-#pragma unroll
-                        for (int g = NACC / 2 - 1; g >= 0; g--) {  // smallest weight first
-                            const float2 m2 = __fadd2_rn(make_float2(r[2 * g][j], r[2 * g + 1][j]), make_float2(12582912.0f, 12582912.0f));
-                            const int n = (__float_as_int(m2.x) - 0x4B400000) * 256 + (__float_as_int(m2.y) - 0x4B400000);
-                            const double nd = __hiloint2double(0x43300000, n ^ (int)0x80000000) - 4503601774854144.0;  // 2^52 + 2^31
-                            const double wg = __longlong_as_double((long long)(1023 - 8 * (2 * g + 3)) << 52);       // 2^-8(2g+3)
-                            dsum = fma(nd, wg, dsum);
-                        }
-                        const int jj = 8 * c + j, ul = 16 * part + jj;
-                        const double sc = sa * sbd[ul];  // 2^(Ea+Eb), NaN for a wild pixel
-                        const double T = fma(dsum, sc, -(double)myrow[jj]);
-                        const double eps = fma(na, sbd[TN + ul], fma(sc, 0x1p-40, 0x1p-140));
-                        const float lo = __double2float_rn(T - eps), hi = __double2float_rn(T + eps);
-                        float outv = -lo;
-                        const bool valid = jj >= j_first && jj <= j_last;
-                        if (valid && !(lo == hi)) {  // cannot be proven: queue it for the literal loop
-                            const unsigned slot = atomicAdd(a.queue_count, 1u);
-                            if (slot < a.queue_cap)
-                                a.queue[slot] = ((unsigned long long)(prow + x) << 12) | (unsigned)(dbase - jj);
-                            else
-                                outv = exact_dot_global(a.fl + (prow + x) * NF, a.fr + (prow + x - (dbase - jj)) * NF);
-                        }
-                        myrow[jj] = outv;
-                        // CR[y][u][d]: for a fixed u the lanes of a warp hold consecutive x = consecutive d
-                        if (valid && crp != nullptr) crp[(long long)jj * (a.Dp - 1)] = outv;
+                    for (int k = 0; k < TM / NEW; k++) {
+                        *p = rp[ul ^ ((ew + NEW * k) & 31)];
+                        p += step;
+                        rp += NEW * TN;
                     }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_t_free);  // TMEM may take the next tile
-                compute_sync();                           // results complete in shared memory
-                // ---- CL[y][x][d], d = x - u: for a fixed x the tile's u range is a contiguous run of d
-                {
-                    const bool interior = x0 + TM <= a.W && u0 + TN <= a.W && x0 - (u0 + TN - 1) >= 0 && (x0 + TM - 1) - u0 < a.D;
-                    const int ul0 = (TN - 1) - lane, ul1 = (TN - 1) - (lane + 32);
-                    for (int r = warp; r < TM; r += NCW) {
+                } else {
+                    for (int r = ew; r < TM; r += NEW) {
                         const int xr = x0 + r;
                         if (xr >= a.W) break;
-                        float* row = a.CL + (prow + xr) * a.Dp + (xr - u0);
-                        const float v0 = res[r * RES_PITCH + ul0], v1 = res[r * RES_PITCH + ul1];
-                        if (interior) {
-                            row[-ul0] = v0;
-                            row[-ul1] = v1;
-                        } else {
-                            const int d0 = xr - u0 - ul0, d1 = xr - u0 - ul1;
-                            if (d0 >= 0 && d0 < a.D && u0 + ul0 < a.W) row[-ul0] = v0;
-                            if (d1 >= 0 && d1 < a.D && u0 + ul1 < a.W) row[-ul1] = v1;
-                        }
+                        const int d0 = xr - u0 - ul;
+                        if (d0 >= 0 && d0 < a.D && u0 + ul < a.W) a.CL[(prow + xr) * a.Dp + d0] = res[r * TN + (ul ^ (r & 31))];
                     }
                 }
-                compute_sync();  // the result tile may be overwritten
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_res_free + s);  // the result tile may be overwritten
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == NCW) {
+    if (warp == NRW + NEW) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }

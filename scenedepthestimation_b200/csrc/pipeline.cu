@@ -109,7 +109,15 @@ static int run_pipeline(const uint8_t* imageL, const uint8_t* imageR, const floa
     float* filled = reinterpret_cast<float*>(ws + l.filled);
     uint8_t* flagL = reinterpret_cast<uint8_t*>(ws + l.flagL);
 
-    if (int e = mccnn_cost_volume(fl, fr, CL, CR, H, W, D, 1.0f, stream)) return e;
+    // Exact cost volume, two bit-identical implementations (tests/test_gpu_parity.py): the band GEMM on the CUDA cores and
+    // the tensor-core variant, which wins once the disparity band is wide enough to fill its 128 x 32 tiles (measured on
+    // B200: c4, D = 800: 56.3 vs 59.9 ms; c3, D = 400: 9.2 vs 8.6 ms). Its workspace borrows the S volumes, idle until SGM.
+    const size_t tc_ws = mccnn_cost_volume_tc_workspace_bytes(H, W);
+    if (D >= 512 && tc_ws <= l.dl_wta - l.SL) {
+        if (int e = mccnn_cost_volume_tc(fl, fr, CL, CR, ws + l.SL, l.dl_wta - l.SL, H, W, D, 1.0f, stream)) return e;
+    } else {
+        if (int e = mccnn_cost_volume(fl, fr, CL, CR, H, W, D, 1.0f, stream)) return e;
+    }
     if (int e = tm.mark()) return e;  // [1] cost volume
     if (params->cbca_iters > 0) {
         // the stage behind the reference's unused "aggregation" slot (match.py:98); SL / SR are free until SGM starts
