@@ -25,7 +25,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-KERNELS_PER_STEP = 2 * 2 + 2 * 5 + 1 + 7 + 4  # standardise(2x2) + conv(2x5) + cost volume + SGM passes + lr flags, fill (2), median
+def kernels_per_step(D: int) -> int:
+    """standardise (2x2) + conv (2x5) + cost volume + SGM passes + L-R flags, fill (2), median. The cost volume is one band-GEMM
+    launch, or for D >= 512 the tensor-core variant: 2 slice kernels, fill, main kernel, fix-up (pipeline.cu)."""
+    return 2 * 2 + 2 * 5 + (5 if D >= 512 else 1) + 7 + 4
 
 
 def parse():
@@ -346,7 +349,7 @@ def main():
                     "d2h_bytes_per_step": (2 * H * W * 4 if batch == 1 else H * W) * batch,
                     "api": "engine.match_pair (mccnn_match_pair) with pinned host u8 images in, host fp32 maps out" if batch == 1 else
                            "match.StreamedMatcher (match.py's loop): host u8 pairs in, host u8 disparity maps out"},
-            "gpu_launches": KERNELS_PER_STEP * a.steps * batch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": kernels_per_step(D) * a.steps * batch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "single_pair_sharded": sharded}))
     if world > 1:
         dist.destroy_process_group()
