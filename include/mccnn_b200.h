@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCCNN_ABI_VERSION 2
+#define MCCNN_ABI_VERSION 3
 #define MCCNN_FEATURES 64 /* num_of_feature_maps: hard-coded 64 in the reference (process_functional.py:128) */
 
 enum {
@@ -116,6 +116,34 @@ int mccnn_cost_volume(const float* fl, const float* fr, float* CL, float* CR,
 size_t mccnn_cost_volume_tc_workspace_bytes(int H, int W);
 int mccnn_cost_volume_tc(const float* fl, const float* fr, float* CL, float* CR, void* workspace, size_t workspace_bytes,
                          int H, int W, int D, float fill, void* stream);
+
+/* ---- MC-CNN-accurate decision head (BASELINE.json config 3; north_star names the net) ------------
+ * The reference holds only the layer helper fc() (xw_plus_b + ReLU, weights [num_in][num_out], mc_cnn_brunch.py:95-106)
+ * and never builds the head: parity is UNPINNED, the architecture follows the MC-CNN paper (3 hidden layers of
+ * MCCNN_FC_UNITS, one sigmoid output) and results are checked against oracle/fc_head.py.
+ *   h1 = relu([fl(y,x) ; fr(y,x-d)] W1 + b1), h2 = relu(h1 W2 + b2), h3 = relu(h2 W3 + b3),
+ *   CL[y][x][d] = CR[y][x-d][d] = -sigmoid(h3 . w4 + b4); entries never written = fill, pads +INF (as mccnn_cost_volume).
+ * fc2 / fc3 run on tcgen05 with fp16 operands and fp32 accumulation (csrc/fc_head.cu); |error| of a cost is a few 1e-4.
+ * All pointers are device pointers:
+ *   w1_left / w1_right: fp32 [64][384], rows 0..63 / 64..127 of fc1/weights (the layer is split per image)
+ *   w2t_f16 / w3t_f16 : fp16 [384 out][384 in], the TRANSPOSE of fc2/weights, fc3/weights (K-major for the MMA)
+ *   b1, b2, b3, w4    : fp32 [384]; b4: the scalar fc4 bias
+ * workspace: mccnn_fc_head_workspace_bytes(H, W) bytes, 256-byte aligned. */
+#define MCCNN_FC_UNITS 384
+typedef struct {
+    const float* w1_left;
+    const float* w1_right;
+    const float* b1;
+    const void* w2t_f16;
+    const float* b2;
+    const void* w3t_f16;
+    const float* b3;
+    const float* w4;
+    float b4;
+} mccnn_fc_weights;
+size_t mccnn_fc_head_workspace_bytes(int H, int W);
+int mccnn_cost_volume_accurate(const float* fl, const float* fr, const mccnn_fc_weights* weights, float* CL, float* CR,
+                               void* workspace, size_t workspace_bytes, int H, int W, int D, float fill, void* stream);
 /* [H][W][Dp] -> dense [D][H][W] (layout of the reference's CPU compute_cost_volume, :48-73). */
 int mccnn_volume_to_dhw(const float* vol, float* out_dhw, int H, int W, int D, void* stream);
 

@@ -1,0 +1,483 @@
+// MC-CNN-accurate decision head: the cost of an evaluation is a small fully-connected network on the two feature
+// vectors instead of their dot product (BASELINE.json config 3).
+//
+// The reference holds only the layer helper (fc: xw_plus_b + ReLU, weights [num_in][num_out], mc_cnn_brunch.py:95-106)
+// and never builds the head, so PARITY IS UNPINNED: the architecture follows the MC-CNN paper (Zbontar & LeCun, JMLR
+// 2016, "accurate" Middlebury net: 3 hidden layers of 384 units, one sigmoid output) on top of the tower this repo
+// already runs, and results are checked against this repo's own oracle (oracle/fc_head.py):
+//   h1 = relu(W1^T [fl(y,x) ; fr(y,x-d)] + b1)        W1 [128][384]   (fc1)
+//   h2 = relu(W2^T h1 + b2)                            W2 [384][384]   (fc2)
+//   h3 = relu(W3^T h2 + b3)                            W3 [384][384]   (fc3)
+//   CL[y][x][d] = CR[y][x-d][d] = -sigmoid(w4 . h3 + b4)               (fc4), `fill` where x - d < 0, +INF pads
+//
+// 0.59 MFLOP per evaluation (c3, 1440x994x400: 338 TFLOP): the one tensor-pipe-bound stage of the repo besides the tower.
+//   * fc1 is linear in the concatenation, so it is split per image and done once per PIXEL on the CUDA cores:
+//     A1 = fl W1[:64] + b1, B1 = fr W1[64:], stored as fp16 [P][384]; per evaluation h1 = relu(A1[x] + B1[x-d]).
+//   * fc2 / fc3: tcgen05.mma kind::f16 (fp16 operands, fp32 accumulation in TMEM). A tile is 128 consecutive x of one
+//     image row at one disparity: the A1 and B1 rows of the tile are two contiguous [128][384] blocks, fetched by TMA in
+//     six K chunks of 64 straight into the 128-byte-swizzled K-major layout; the activation warps add + ReLU them in
+//     place. W2 / W3 stream through a two-stage ring of [384 n][64 k] chunks (48 KB, TMA from L2), two N = 192 MMAs per
+//     k-step. The 128 x 384 fp32 accumulator (384 TMEM columns) is drained by the activation warps: bias + ReLU + fp16
+//     back into the same shared-memory tile as the A operand of fc3; after fc3: bias + ReLU, dot with w4, sigmoid, store.
+//   * Warp roles: 4 activation / epilogue warps (thread = tile row = TMEM lane), 1 TMA warp for the A1 / B1 chunks, 1 TMA
+//     warp for the weight ring, 1 MMA warp. Persistent, one CTA of 225 KB per SM.
+// Precision: fp16 operands give |d cost| of a few 1e-4 against the fp32 network (tests: 2e-3 absolute).
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+namespace mccnn {
+namespace {
+
+constexpr int NF = MCCNN_FEATURES;
+constexpr int FC = MCCNN_FC_UNITS;            // 384
+constexpr int TM = 128;                        // evaluations (consecutive x) per tile
+constexpr int KC = 64;                         // K chunk: 64 fp16 = one 128-byte swizzled row
+constexpr int NKC = FC / KC;                   // 6
+constexpr int NH = FC / 2;                     // 192: N of one MMA
+constexpr int H_CHUNK = TM * 128;              // 16384 bytes: [128 rows][64 fp16]
+constexpr int W_HALF = NH * 128;               // 24576 bytes: [192 n][64 fp16]
+constexpr int W_STAGE = 2 * W_HALF;            // 49152
+constexpr int OFF_H = 0;                       // 6 chunks: h1, then h2
+constexpr int OFF_W = OFF_H + NKC * H_CHUNK;   // 98304: 2 stages
+constexpr int OFF_SB = OFF_W + 2 * W_STAGE;    // 196608: 2 staging chunks for the B1 rows
+constexpr int OFF_BAR = OFF_SB + 2 * H_CHUNK;  // 229376
+constexpr int FC_SMEM = OFF_BAR + 256 + 1024;  // barriers + alignment slack
+constexpr int NAW = 4;                         // activation warps
+constexpr int FC_THREADS = 32 * (NAW + 3);
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NH >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);  // f16 x f16 -> f32, M128 N192
+constexpr float kInfF = __builtin_huge_valf();
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_dst),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------- fc1, split per image (CUDA cores, fp32 -> fp16)
+// out[p][j] = sum_i feat[p][i] * w[i][j] (+ bias[j]); block = 32 pixels x 384 outputs, thread = 3 outputs x 32 pixels.
+__global__ void __launch_bounds__(128) fc1_half_kernel(const float* __restrict__ feat, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, __half* __restrict__ out, long long P) {
+    __shared__ float fs[32][NF + 1];
+    const long long p0 = (long long)blockIdx.x * 32;
+    for (int i = threadIdx.x; i < 32 * NF; i += 128) {
+        const long long p = p0 + i / NF;
+        fs[i / NF][i % NF] = p < P ? feat[p * NF + (i % NF)] : 0.f;
+    }
+    __syncthreads();
+    float acc[3][32];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float b = bias ? __ldg(bias + threadIdx.x + 128 * c) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 32; q++) acc[c][q] = b;
+    }
+    for (int i = 0; i < NF; i++) {
+        float wv[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) wv[c] = __ldg(w + (size_t)i * FC + threadIdx.x + 128 * c);
+#pragma unroll
+        for (int q = 0; q < 32; q++) {
+            const float f = fs[q][i];
+#pragma unroll
+            for (int c = 0; c < 3; c++) acc[c][q] = fmaf(f, wv[c], acc[c][q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+        const long long p = p0 + q;
+        if (p < P)
+#pragma unroll
+            for (int c = 0; c < 3; c++) out[p * FC + threadIdx.x + 128 * c] = __float2half_rn(acc[c][q]);
+    }
+}
+
+// entries no evaluation writes: fill where the match falls outside the other image, +INF pads
+__global__ void __launch_bounds__(256) fc_fill_kernel(float* __restrict__ CL, float* __restrict__ CR, int W, int D, int Dp,
+                                                     long long P, float fill) {
+    const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pix >= P) return;
+    const int x = (int)(pix % W);
+    float* rl = CL + pix * Dp;
+    for (int d = x + 1 + lane; d < D; d += 32) rl[d] = fill;  // x - d < 0
+    if (Dp > D && lane < Dp - D) rl[D + lane] = kInfF;
+    if (CR != nullptr) {
+        float* rr = CR + pix * Dp;
+        for (int d = max(W - x, 0) + lane; d < D; d += 32) rr[d] = fill;  // x + d >= W
+        if (Dp > D && lane < Dp - D) rr[D + lane] = kInfF;
+    }
+}
+
+struct FcArgs {
+    const float* b2;
+    const float* b3;
+    const float* w4;
+    float b4;
+    float* CL;
+    float* CR;
+    int H, W, D, Dp;
+    int tiles_x;
+    long long nitems;  // H * tiles_x * D
+};
+
+// work items of one CTA: (y, x block, d), d fastest so that concurrently running CTAs share the B1 rows in L2;
+// items whose 128 pixels all have x < d hold no valid evaluation and are skipped by every role
+struct ItemCursor {
+    long long item, stride, nitems;
+    int y, x0, d;
+    __device__ void decode(const FcArgs& a) {
+        for (; item < nitems; item += stride) {
+            const long long per_row = (long long)a.tiles_x * a.D;
+            y = (int)(item / per_row);
+            const int rem = (int)(item - (long long)y * per_row);
+            x0 = (rem / a.D) * TM;
+            d = rem % a.D;
+            if (x0 + TM - 1 >= d) return;
+        }
+    }
+    __device__ void start(const FcArgs& a, int first, int step) {
+        item = first; stride = step; nitems = a.nitems;
+        decode(a);
+    }
+    __device__ bool valid() const { return item < nitems; }
+    __device__ void next(const FcArgs& a) {
+        item += stride;
+        decode(a);
+    }
+};
+
+// Barriers: ab_full[2] (TMA bytes of an A1 chunk + B1 staging chunk), sb_free[2] (4 arrivals: staging chunk consumed),
+// h_full[6] (4 arrivals: chunk kc of the A operand is in shared memory; used twice per tile: h1, h2), w_full[2] (TMA bytes),
+// w_free[2] (tcgen05.commit: the MMAs reading the stage are done), acc_full (commit; twice per tile), acc_free (4 arrivals:
+// the accumulator has been drained after fc3), l3_done (commit: fc3 no longer reads the h tile).
+__global__ void __launch_bounds__(FC_THREADS, 1)
+fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3, const FcArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* sm = smem_raw + (base - raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
+    uint64_t* ab_full = bars;        // [2]
+    uint64_t* sb_free = bars + 2;    // [2]
+    uint64_t* h_full = bars + 4;     // [6]
+    uint64_t* w_full = bars + 10;    // [2]
+    uint64_t* w_free = bars + 12;    // [2]
+    uint64_t* acc_full = bars + 14;
+    uint64_t* acc_free = bars + 15;
+    uint64_t* l3_done = bars + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < 2; s++) {
+            mbar_init(ab_full + s, 1);
+            mbar_init(sb_free + s, NAW);
+            mbar_init(w_full + s, 1);
+            mbar_init(w_free + s, 1);
+        }
+        for (int k = 0; k < NKC; k++) mbar_init(h_full + k, NAW);
+        mbar_init(acc_full, 1);
+        mbar_init(acc_free, NAW);
+        mbar_init(l3_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == NAW + 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == NAW) {
+        // ================================================================= TMA: A1 chunks into the h tile, B1 chunks into staging
+        if (lane == 0) {
+            ItemCursor it;
+            it.start(a, blockIdx.x, gridDim.x);
+            uint32_t t = 0, c_ab = 0;
+            for (; it.valid(); it.next(a), t++) {
+                if (t > 0) mbar_wait(l3_done, (t - 1) & 1u);  // fc3 of the previous tile has read the h tile
+                const long long prow = (long long)it.y * a.W;
+                for (int kc = 0; kc < NKC; kc++, c_ab++) {
+                    const uint32_t st = c_ab & 1u;
+                    if (c_ab >= 2) mbar_wait(sb_free + st, ((c_ab - 2) >> 1) & 1u);
+                    mbar_expect_tx(ab_full + st, 2 * H_CHUNK);
+                    tma_load_2d(base + OFF_H + kc * H_CHUNK, &tmA, kc * KC, (int)(prow + it.x0), ab_full + st);
+                    tma_load_2d(base + OFF_SB + st * H_CHUNK, &tmB, kc * KC, (int)(prow + it.x0 - it.d), ab_full + st);
+                }
+            }
+        }
+    } else if (warp == NAW + 1) {
+        // ================================================================= TMA: weight ring, W2 chunks 0..5 then W3 chunks 0..5 per tile
+        if (lane == 0) {
+            ItemCursor it;
+            it.start(a, blockIdx.x, gridDim.x);
+            uint32_t g = 0;
+            for (; it.valid(); it.next(a)) {
+                for (int layer = 0; layer < 2; layer++)
+                    for (int kc = 0; kc < NKC; kc++, g++) {
+                        const uint32_t st = g & 1u;
+                        if (g >= 2) mbar_wait(w_free + st, ((g - 2) >> 1) & 1u);
+                        mbar_expect_tx(w_full + st, W_STAGE);
+                        const CUtensorMap* tw = layer ? &tmW3 : &tmW2;
+                        tma_load_2d(base + OFF_W + st * W_STAGE, tw, kc * KC, 0, w_full + st);
+                        tma_load_2d(base + OFF_W + st * W_STAGE + W_HALF, tw, kc * KC, NH, w_full + st);
+                    }
+            }
+        }
+    } else if (warp == NAW + 2) {
+        // ================================================================= MMA issue
+        if (lane == 0) {
+            ItemCursor it;
+            it.start(a, blockIdx.x, gridDim.x);
+            uint32_t t = 0, g = 0;
+            for (; it.valid(); it.next(a), t++) {
+                if (t > 0) mbar_wait(acc_free, (t - 1) & 1u);  // the previous tile's accumulator has been drained
+                for (int layer = 0; layer < 2; layer++) {
+                    for (int kc = 0; kc < NKC; kc++, g++) {
+                        const uint32_t st = g & 1u;
+                        mbar_wait(h_full + kc, layer);  // first completion of the tile: h1, second: h2 (parity = 2t + layer)
+                        mbar_wait(w_full + st, (g >> 1) & 1u);
+                        tc_fence_after();
+                        const uint64_t ad = sw128_desc(base + OFF_H + kc * H_CHUNK);
+                        const uint64_t bd0 = sw128_desc(base + OFF_W + st * W_STAGE);
+                        const uint64_t bd1 = sw128_desc(base + OFF_W + st * W_STAGE + W_HALF);
+#pragma unroll
+                        for (int k = 0; k < KC / 16; k++) {
+                            umma_f16(tmem_base, ad + 2 * k, bd0 + 2 * k, (kc | k) != 0 ? 1u : 0u);
+                            umma_f16(tmem_base + NH, ad + 2 * k, bd1 + 2 * k, (kc | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(w_free + st);
+                    }
+                    umma_commit(acc_full);
+                }
+                umma_commit(l3_done);
+            }
+        }
+    } else {
+        // ================================================================= activation / epilogue warps: thread = tile row
+        const int r = tid;  // 0..127 = TMEM lane
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+        const uint32_t row_off = (uint32_t)r * 128u, rsw = (uint32_t)(r & 7);
+        ItemCursor it;
+        it.start(a, blockIdx.x, gridDim.x);
+        uint32_t t = 0, c_ab = 0;
+        for (; it.valid(); it.next(a), t++) {
+            // ---- h1 = relu(A1 + B1), in place in the swizzled tile (the swizzle is the same for both operands)
+            for (int kc = 0; kc < NKC; kc++, c_ab++) {
+                const uint32_t st = c_ab & 1u;
+                mbar_wait(ab_full + st, (c_ab >> 1) & 1u);
+                uint4* hp = reinterpret_cast<uint4*>(sm + OFF_H + kc * H_CHUNK + row_off);
+                const uint4* bp = reinterpret_cast<const uint4*>(sm + OFF_SB + st * H_CHUNK + row_off);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    uint4 x = hp[u];
+                    const uint4 y = bp[u];
+                    const __half2 z = __float2half2_rn(0.f);
+                    __half2* xh = reinterpret_cast<__half2*>(&x);
+                    const __half2* yh = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) xh[q] = __hmax2(__hadd2(xh[q], yh[q]), z);
+                    hp[u] = x;
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(h_full + kc);
+                    mbar_arrive(sb_free + st);
+                }
+            }
+            // ---- fc2 epilogue: h2 = relu(acc + b2) as fp16 into the same tile (fc2 has finished reading it)
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < FC / 16; c++) {
+                float v[16];
+                tmem_ld16(taddr + 16u * c, v);
+                tmem_ld_wait();
+                __align__(16) __half2 hv[8];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.b2 + 16 * c) + q);
+                    hv[2 * q] = __floats2half2_rn(fmaxf(v[4 * q] + b.x, 0.f), fmaxf(v[4 * q + 1] + b.y, 0.f));
+                    hv[2 * q + 1] = __floats2half2_rn(fmaxf(v[4 * q + 2] + b.z, 0.f), fmaxf(v[4 * q + 3] + b.w, 0.f));
+                }
+                // columns 16c..16c+15 = K chunk c / 4, 16-byte units 2 (c & 3) and 2 (c & 3) + 1 of row r
+                unsigned char* hrow = sm + OFF_H + (c >> 2) * H_CHUNK + row_off;
+                const uint32_t u0 = 2u * (c & 3);
+                *reinterpret_cast<uint4*>(hrow + ((u0 ^ rsw) << 4)) = *reinterpret_cast<const uint4*>(&hv[0]);
+                *reinterpret_cast<uint4*>(hrow + (((u0 + 1) ^ rsw) << 4)) = *reinterpret_cast<const uint4*>(&hv[4]);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0)
+                for (int kc = 0; kc < NKC; kc++) mbar_arrive(h_full + kc);  // also: the accumulator may be overwritten
+            // ---- fc3 epilogue + fc4: z = w4 . relu(acc + b3) + b4, cost = -sigmoid(z)
+            mbar_wait(acc_full, 1);
+            tc_fence_after();
+            float z = a.b4;
+#pragma unroll 1
+            for (int c = 0; c < FC / 16; c++) {
+                float v[16];
+                tmem_ld16(taddr + 16u * c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.b3 + 16 * c) + q);
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(a.w4 + 16 * c) + q);
+                    z = fmaf(fmaxf(v[4 * q] + b.x, 0.f), w.x, z);
+                    z = fmaf(fmaxf(v[4 * q + 1] + b.y, 0.f), w.y, z);
+                    z = fmaf(fmaxf(v[4 * q + 2] + b.z, 0.f), w.z, z);
+                    z = fmaf(fmaxf(v[4 * q + 3] + b.w, 0.f), w.w, z);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_free);
+            const int x = it.x0 + r;
+            if (x < a.W && x >= it.d) {
+                const float cost = -1.0f / (1.0f + expf(-z));
+                const long long prow = (long long)it.y * a.W;
+                a.CL[(prow + x) * a.Dp + it.d] = cost;
+                if (a.CR != nullptr) a.CR[(prow + x - it.d) * a.Dp + it.d] = cost;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NAW + 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// fp16 [rows][FC] row-major, box = 64 columns x box_rows rows, 128-byte swizzle
+int make_map(CUtensorMap* tm, const void* ptr, size_t rows, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    MCCNN_REQUIRE(enc != nullptr, MCCNN_EINVAL, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)FC, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)FC * sizeof(__half)};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MCCNN_REQUIRE(r == CUDA_SUCCESS, MCCNN_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+inline size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+}  // namespace mccnn
+
+using namespace mccnn;
+
+extern "C" size_t mccnn_fc_head_workspace_bytes(int H, int W) {
+    if (H < 1 || W < 1) return 0;
+    return 2 * a256((size_t)H * W * FC * sizeof(__half));
+}
+
+extern "C" int mccnn_cost_volume_accurate(const float* fl, const float* fr, const mccnn_fc_weights* w, float* CL, float* CR,
+                                          void* workspace, size_t workspace_bytes, int H, int W, int D, float fill,
+                                          void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MCCNN_REQUIRE(fl && fr && w && CL && workspace, MCCNN_EINVAL, "mccnn_cost_volume_accurate: null argument");
+    MCCNN_REQUIRE(w->w1_left && w->w1_right && w->b1 && w->w2t_f16 && w->b2 && w->w3t_f16 && w->b3 && w->w4, MCCNN_EINVAL,
+                  "mccnn_cost_volume_accurate: null weight pointer");
+    MCCNN_REQUIRE(H >= 1 && W >= 1 && D >= 1 && D <= 4096, MCCNN_EINVAL, "mccnn_cost_volume_accurate: bad shape H=%d W=%d D=%d", H, W, D);
+    MCCNN_REQUIRE((long long)H * W + TM < 0x7fffffffLL, MCCNN_EINVAL, "mccnn_cost_volume_accurate: image too large for 32-bit tile rows");
+    MCCNN_REQUIRE(aligned16(fl) && aligned16(fr) && aligned16(w->w2t_f16) && aligned16(w->w3t_f16) && aligned16(w->b2) &&
+                      aligned16(w->b3) && aligned16(w->w4) && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+                  MCCNN_EALIGN, "mccnn_cost_volume_accurate: features / weights must be 16-byte, the workspace 256-byte aligned");
+    MCCNN_REQUIRE(workspace_bytes >= mccnn_fc_head_workspace_bytes(H, W), MCCNN_EWORKSPACE,
+                  "mccnn_cost_volume_accurate: workspace too small");
+    const long long P = (long long)H * W;
+    const int Dp = disp_pitch(D);
+    char* ws = reinterpret_cast<char*>(workspace);
+    __half* A1 = reinterpret_cast<__half*>(ws);
+    __half* B1 = reinterpret_cast<__half*>(ws + a256((size_t)P * FC * sizeof(__half)));
+
+    const unsigned nb = (unsigned)((P + 31) / 32);
+    fc1_half_kernel<<<nb, 128, 0, stream>>>(fl, w->w1_left, w->b1, A1, P);
+    MCCNN_LAUNCH_CHECK("fc1_half_kernel");
+    fc1_half_kernel<<<nb, 128, 0, stream>>>(fr, w->w1_right, nullptr, B1, P);
+    MCCNN_LAUNCH_CHECK("fc1_half_kernel");
+    fc_fill_kernel<<<(unsigned)((P + 7) / 8), 256, 0, stream>>>(CL, CR, W, D, Dp, P, fill);
+    MCCNN_LAUNCH_CHECK("fc_fill_kernel");
+
+    CUtensorMap tmA, tmB, tmW2, tmW3;
+    if (int e = make_map(&tmA, A1, (size_t)P, TM)) return e;
+    if (int e = make_map(&tmB, B1, (size_t)P, TM)) return e;
+    if (int e = make_map(&tmW2, w->w2t_f16, FC, NH)) return e;
+    if (int e = make_map(&tmW3, w->w3t_f16, FC, NH)) return e;
+    FcArgs a{};
+    a.b2 = w->b2; a.b3 = w->b3; a.w4 = w->w4; a.b4 = w->b4;
+    a.CL = CL; a.CR = CR;
+    a.H = H; a.W = W; a.D = D; a.Dp = Dp;
+    a.tiles_x = ceil_div(W, TM);
+    a.nitems = (long long)H * a.tiles_x * D;
+    MCCNN_CUDA(cudaFuncSetAttribute(fc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
+    long long grid = sm_count();
+    if (grid > a.nitems) grid = a.nitems;
+    fc_head_kernel<<<(unsigned)grid, FC_THREADS, FC_SMEM, stream>>>(tmA, tmB, tmW2, tmW3, a);
+    MCCNN_LAUNCH_CHECK("fc_head_kernel");
+    return 0;
+}

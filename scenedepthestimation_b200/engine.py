@@ -13,6 +13,7 @@ import torch
 from . import _lib
 
 FEATURES = 64
+FC_UNITS = 384  # MCCNN_FC_UNITS: hidden width of the MC-CNN-accurate head
 EXACT = 0  # MCCNN_SGM_EXACT
 
 
@@ -129,6 +130,48 @@ def cost_volume_tc(fl: torch.Tensor, fr: torch.Tensor, D: int, fill: float = 1.0
     ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
     _lib.check(lib.mccnn_cost_volume_tc(_p(fl), _p(fr), _p(CL), _p(CR), _p(ws), nws, H, W, D, float(fill), _stream()),
                "mccnn_cost_volume_tc")
+    return CL, CR
+
+
+class FcHeadWeights:
+    """Device copy of the MC-CNN-accurate head's weights in the layout mccnn_cost_volume_accurate wants
+    (fc1 split per image, fc2 / fc3 transposed to fp16 [out][in]); keeps the tensors alive for the ctypes struct."""
+
+    def __init__(self, weights: dict):
+        _require_cuda()
+
+        def get(name):
+            for k in (name, name + ":0"):
+                if k in weights:
+                    return np.asarray(weights[k], dtype=np.float32)
+            raise KeyError(f"{name} missing from the weights dict (keys: {sorted(weights)[:8]} ...)")
+
+        w1, w2, w3, w4 = (get(f"fc{i}/weights") for i in (1, 2, 3, 4))
+        if w1.shape != (2 * FEATURES, FC_UNITS) or w2.shape != (FC_UNITS, FC_UNITS) or w3.shape != (FC_UNITS, FC_UNITS) \
+                or w4.reshape(-1).shape != (FC_UNITS,):
+            raise ValueError(f"head must be fc1 [{2 * FEATURES},{FC_UNITS}], fc2/fc3 [{FC_UNITS},{FC_UNITS}], fc4 [{FC_UNITS},1]")
+        dev = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt).contiguous()
+        self.t = dict(w1_left=dev(w1[:FEATURES]), w1_right=dev(w1[FEATURES:]), b1=dev(get("fc1/biases")),
+                      w2t=dev(w2.T, torch.float16), b2=dev(get("fc2/biases")), w3t=dev(w3.T, torch.float16),
+                      b3=dev(get("fc3/biases")), w4=dev(w4.reshape(-1)))
+        t = self.t
+        self.c = _lib.FcWeights(t["w1_left"].data_ptr(), t["w1_right"].data_ptr(), t["b1"].data_ptr(), t["w2t"].data_ptr(),
+                                t["b2"].data_ptr(), t["w3t"].data_ptr(), t["b3"].data_ptr(), t["w4"].data_ptr(),
+                                float(get("fc4/biases").reshape(-1)[0]))
+
+
+def cost_volume_accurate(fl: torch.Tensor, fr: torch.Tensor, head: FcHeadWeights, D: int, fill: float = 1.0, right: bool = True):
+    """MC-CNN-accurate matching cost (fully-connected head on tcgen05) -> (CL, CR) like cost_volume."""
+    lib = _lib.load()
+    H, W, F = fl.shape
+    assert F == FEATURES and fr.shape == fl.shape
+    Dp = disp_pitch(D)
+    CL = torch.empty((H, W, Dp), dtype=torch.float32, device="cuda")
+    CR = torch.empty((H, W, Dp), dtype=torch.float32, device="cuda") if right else None
+    nws = lib.mccnn_fc_head_workspace_bytes(H, W)
+    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mccnn_cost_volume_accurate(_p(fl), _p(fr), C.byref(head.c), _p(CL), _p(CR), _p(ws), nws, H, W, D, float(fill),
+                                              _stream()), "mccnn_cost_volume_accurate")
     return CL, CR
 
 

@@ -90,6 +90,21 @@ def glorot_weights(num_layers: int = 5, num_features: int = 64, ksize: int = 3, 
     return out
 
 
+def glorot_fc_weights(num_features: int = 64, units: int = 384, seed: int = 11, gain: float = 1.0) -> dict:
+    """Random-init weights of the MC-CNN-accurate head in the reference's variable naming (fc(), mc_cnn_brunch.py:95-106):
+    fc1 [2*features, units], fc2 / fc3 [units, units], fc4 [units, 1], Glorot-uniform like every tf.get_variable default.
+    `gain` scales the weight matrices (tests use > 1 so that the sigmoid leaves its linear range)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    shapes = [(2 * num_features, units), (units, units), (units, units), (units, 1)]
+    for i, (fi, fo) in enumerate(shapes, 1):
+        lim = np.sqrt(6.0 / (fi + fo)) * gain
+        out[f"fc{i}/weights:0"] = rng.uniform(-lim, lim, (fi, fo)).astype(np.float32)
+        blim = np.sqrt(6.0 / (fo + fo))
+        out[f"fc{i}/biases:0"] = rng.uniform(-blim, blim, (fo,)).astype(np.float32)
+    return out
+
+
 def standardise(image_u8: np.ndarray) -> np.ndarray:
     """(I - mean) / std with population std, as match_single.py:34-43; returns [H,W,1] f32."""
     img = image_u8.astype(np.float32)

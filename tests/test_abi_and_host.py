@@ -40,7 +40,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_constants_and_sizes(lib):
     from scenedepthestimation_b200 import _lib
 
-    assert lib.mccnn_abi_version() == 2
+    assert lib.mccnn_abi_version() == 3
     assert [lib.mccnn_disp_pitch(d) for d in (1, 4, 80, 81, 228, 800)] == [4, 4, 80, 84, 228, 800]
     p = _lib.default_sgm_params()
     # process_functional.py:1141-1144, stored as fp32 (:149), reduced pair computed in fp64 then rounded (:141-142)

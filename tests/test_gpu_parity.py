@@ -570,3 +570,31 @@ def test_exact_cost_ties_and_degenerate_inputs(eng, kind):
     filled = st.lrc_fill(exp_l, fl_o)
     assert np.array_equal(eng.lrc_fill(dl, flag).cpu().numpy(), filled)
     assert np.array_equal(eng.median5(dev(filled), dl).cpu().numpy(), st.median5(filled, exp_l))
+
+
+@pytest.mark.parametrize("H,W,D,gain", [(3, 200, 70, 1.0), (2, 128, 128, 2.5), (5, 131, 40, 2.5), (2, 70, 90, 1.5), (4, 300, 33, 2.5)])
+def test_accurate_head_vs_oracle(eng, H, W, D, gain):
+    """MC-CNN-accurate decision head (fc1 split per image on CUDA cores, fc2 / fc3 on tcgen05 with fp16 operands, fc4 +
+    sigmoid in the epilogue) against oracle/fc_head.py. The reference never builds the head (only fc(), mc_cnn_brunch.py:
+    95-106): own oracle, parity unpinned. Two bars: against the oracle rounding to fp16 exactly where the kernel does
+    (isolates data movement / layout: 5e-4; an fp16 rounding of h2 can flip on the accumulation order), and against the fp32 network (operand precision: 2e-3 absolute on a cost)."""
+    from oracle import fc_head as fh
+    from scenedepthestimation_b200 import synthetic as syn
+
+    fl, fr = syn.unit_features(H, W, 64, 900 + H + W)
+    w = syn.glorot_fc_weights(seed=5 + H, gain=gain)
+    head = eng.FcHeadWeights(w)
+    CL, CR = eng.cost_volume_accurate(dev(fl), dev(fr), head, D)
+    el, er = fh.head_cost_volume(fl, fr, w, D, emulate_fp16=True)
+    fl32, fr32 = fh.head_cost_volume(fl, fr, w, D)
+    gl, gr = unpitch(CL, D), unpitch(CR, D)
+    assert np.isfinite(gl).all() and np.isfinite(gr).all()
+    assert np.abs(gl - el).max() <= 5e-4 and np.abs(gr - er).max() <= 5e-4
+    assert np.abs(gl - fl32).max() <= 2e-3 and np.abs(gr - fr32).max() <= 2e-3
+    valid = np.arange(W)[:, None] >= np.arange(D)[None, :]
+    assert np.array_equal(gl[:, ~valid], np.ones_like(gl[:, ~valid]))  # fill where x - d < 0
+    assert (gl[:, valid] < 0).all() and (gl[:, valid] > -1).all() and gl[:, valid].std() > 1e-3
+    if CL.shape[-1] > D:
+        assert torch.isinf(CL[..., D:]).all() and torch.isinf(CR[..., D:]).all()
+    only_left, none = eng.cost_volume_accurate(dev(fl), dev(fr), head, D, right=False)
+    assert none is None and torch.equal(only_left, CL)
