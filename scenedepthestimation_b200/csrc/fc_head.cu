@@ -14,13 +14,14 @@
 //   * fc1 is linear in the concatenation, so it is split per image and done once per PIXEL on the CUDA cores:
 //     A1 = fl W1[:64] + b1, B1 = fr W1[64:], stored as fp16 [P][384]; per evaluation h1 = relu(A1[x] + B1[x-d]).
 //   * fc2 / fc3: tcgen05.mma kind::f16 (fp16 operands, fp32 accumulation in TMEM). A tile is 128 consecutive x of one
-//     image row at one disparity: the A1 and B1 rows of the tile are two contiguous [128][384] blocks, fetched by TMA in
-//     six K chunks of 64 straight into the 128-byte-swizzled K-major layout; the activation warps add + ReLU them in
-//     place. W2 / W3 stream through a two-stage ring of [384 n][64 k] chunks (48 KB, TMA from L2), two N = 192 MMAs per
-//     k-step. The 128 x 384 fp32 accumulator (384 TMEM columns) is drained by the activation warps: bias + ReLU + fp16
-//     back into the same shared-memory tile as the A operand of fc3; after fc3: bias + ReLU, dot with w4, sigmoid, store.
-//   * Warp roles: 4 activation / epilogue warps (thread = tile row = TMEM lane), 1 TMA warp for the A1 / B1 chunks, 1 TMA
-//     warp for the weight ring, 1 MMA warp. Persistent, one CTA of 225 KB per SM.
+//     image row at one disparity: the A1 and B1 rows of the tile are two contiguous [128][384] blocks. A1 comes by TMA
+//     in six K chunks of 64 straight into the 128-byte-swizzled K-major layout; the activation warps add the B1 rows
+//     (held in registers, loaded one tile ahead) + ReLU in place. W2 / W3 stream through a five-stage ring of
+//     [192 n][64 k] blocks (24 KB each, TMA from L2), four K = 16 MMAs of N = 192 per block. The 128 x 384 fp32 accumulator
+//     (384 TMEM columns) is drained by the activation warps: bias + ReLU + fp16 back into the same shared-memory tile as
+//     the A operand of fc3; after fc3: bias + ReLU, dot with w4, sigmoid, store.
+//   * Warp roles: 8 activation / epilogue warps (TMEM lane quarter x column half), 1 TMA warp for the A1 chunks, 1 TMA
+//     warp for the weight ring, 1 MMA warp. Persistent, one CTA of 222 KB per SM.
 // Precision: fp16 operands give |d cost| of a few 1e-4 against the fp32 network (tests: 2e-3 absolute).
 #include "common.cuh"
 #include <cuda.h>
@@ -36,14 +37,15 @@ constexpr int KC = 64;                         // K chunk: 64 fp16 = one 128-byt
 constexpr int NKC = FC / KC;                   // 6
 constexpr int NH = FC / 2;                     // 192: N of one MMA
 constexpr int H_CHUNK = TM * 128;              // 16384 bytes: [128 rows][64 fp16]
-constexpr int W_HALF = NH * 128;               // 24576 bytes: [192 n][64 fp16]
-constexpr int W_STAGE = 2 * W_HALF;            // 49152
+constexpr int W_HALF = NH * 128;               // 24576 bytes: [192 n][64 fp16], one stage of the weight ring
+constexpr int NWS = 5;                         // weight ring stages (120 KB in flight: the kernel is bound by this stream)
 constexpr int OFF_H = 0;                       // 6 chunks: h1, then h2
-constexpr int OFF_W = OFF_H + NKC * H_CHUNK;   // 98304: 2 stages
-constexpr int OFF_SB = OFF_W + 2 * W_STAGE;    // 196608: 2 staging chunks for the B1 rows
-constexpr int OFF_BAR = OFF_SB + 2 * H_CHUNK;  // 229376
-constexpr int FC_SMEM = OFF_BAR + 256 + 1024;  // barriers + alignment slack
-constexpr int NAW = 4;                         // activation warps
+constexpr int OFF_W = OFF_H + NKC * H_CHUNK;   // 98304
+constexpr int OFF_BIAS = OFF_W + NWS * W_HALF; // 221184: b2, b3, w4 (3 x 384 floats)
+constexpr int OFF_Z = OFF_BIAS + 3 * FC * 4;   // 225792: partial fc4 sums of the upper column half (128 floats)
+constexpr int OFF_BAR = OFF_Z + TM * 4;        // 226304
+constexpr int FC_SMEM = OFF_BAR + 256 + 1024;  // barriers + alignment slack = 227584
+constexpr int NAW = 8;                         // activation / epilogue warps: warp w owns TMEM lanes 32 (w & 3).. and column half w >> 2
 constexpr int FC_THREADS = 32 * (NAW + 3);
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NH >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);  // f16 x f16 -> f32, M128 N192
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(256) fc_fill_kernel(float* __restrict__ CL, fl
 }
 
 struct FcArgs {
+    const __half* B1;  // fc1 of the right image, [P][384]
     const float* b2;
     const float* b3;
     const float* w4;
@@ -182,33 +185,33 @@ struct ItemCursor {
     }
 };
 
-// Barriers: ab_full[2] (TMA bytes of an A1 chunk + B1 staging chunk), sb_free[2] (4 arrivals: staging chunk consumed),
-// h_full[6] (4 arrivals: chunk kc of the A operand is in shared memory; used twice per tile: h1, h2), w_full[2] (TMA bytes),
-// w_free[2] (tcgen05.commit: the MMAs reading the stage are done), acc_full (commit; twice per tile), acc_free (4 arrivals:
-// the accumulator has been drained after fc3), l3_done (commit: fc3 no longer reads the h tile).
+// Barriers: a_full (TMA bytes of the six A1 chunks of a tile), h_full[6] (8 arrivals: chunk kc of the A operand is in shared
+// memory; completes twice per tile: h1, h2), w_full[5] (TMA bytes), w_free[5] (tcgen05.commit: the MMAs reading the stage are
+// done), acc_full (commit; twice per tile), acc_free (8 arrivals: the accumulator has been drained after fc3), l3_done
+// (commit: fc3 no longer reads the h tile).
 __global__ void __launch_bounds__(FC_THREADS, 1)
-fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmW3, const FcArgs a) {
+fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW2,
+               const __grid_constant__ CUtensorMap tmW3, const FcArgs a) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
-    uint64_t* ab_full = bars;        // [2]
-    uint64_t* sb_free = bars + 2;    // [2]
-    uint64_t* h_full = bars + 4;     // [6]
-    uint64_t* w_full = bars + 10;    // [2]
-    uint64_t* w_free = bars + 12;    // [2]
-    uint64_t* acc_full = bars + 14;
-    uint64_t* acc_free = bars + 15;
-    uint64_t* l3_done = bars + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* a_full = bars;
+    uint64_t* h_full = bars + 1;          // [6]
+    uint64_t* w_full = bars + 7;          // [NWS]
+    uint64_t* w_free = bars + 7 + NWS;    // [NWS]
+    uint64_t* acc_full = bars + 7 + 2 * NWS;
+    uint64_t* acc_free = acc_full + 1;
+    uint64_t* l3_done = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 3);
+    float* sbias = reinterpret_cast<float*>(sm + OFF_BIAS);  // [0] b2, [1] b3, [2] w4
+    float* zbuf = reinterpret_cast<float*>(sm + OFF_Z);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < 2; s++) {
-            mbar_init(ab_full + s, 1);
-            mbar_init(sb_free + s, NAW);
+        mbar_init(a_full, 1);
+        for (int s = 0; s < NWS; s++) {
             mbar_init(w_full + s, 1);
             mbar_init(w_free + s, 1);
         }
@@ -217,6 +220,11 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(acc_free, NAW);
         mbar_init(l3_done, 1);
         mbar_fence_init();
+    }
+    for (int i = tid; i < FC; i += FC_THREADS) {
+        sbias[i] = a.b2[i];
+        sbias[FC + i] = a.b3[i];
+        sbias[2 * FC + i] = a.w4[i];
     }
     if (warp == NAW + 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
@@ -229,39 +237,33 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == NAW) {
-        // ================================================================= TMA: A1 chunks into the h tile, B1 chunks into staging
+        // ================================================================= TMA: the six A1 chunks of a tile, straight into the h tile
         if (lane == 0) {
             ItemCursor it;
             it.start(a, blockIdx.x, gridDim.x);
-            uint32_t t = 0, c_ab = 0;
+            uint32_t t = 0;
             for (; it.valid(); it.next(a), t++) {
                 if (t > 0) mbar_wait(l3_done, (t - 1) & 1u);  // fc3 of the previous tile has read the h tile
                 const long long prow = (long long)it.y * a.W;
-                for (int kc = 0; kc < NKC; kc++, c_ab++) {
-                    const uint32_t st = c_ab & 1u;
-                    if (c_ab >= 2) mbar_wait(sb_free + st, ((c_ab - 2) >> 1) & 1u);
-                    mbar_expect_tx(ab_full + st, 2 * H_CHUNK);
-                    tma_load_2d(base + OFF_H + kc * H_CHUNK, &tmA, kc * KC, (int)(prow + it.x0), ab_full + st);
-                    tma_load_2d(base + OFF_SB + st * H_CHUNK, &tmB, kc * KC, (int)(prow + it.x0 - it.d), ab_full + st);
-                }
+                mbar_expect_tx(a_full, NKC * H_CHUNK);
+                for (int kc = 0; kc < NKC; kc++) tma_load_2d(base + OFF_H + kc * H_CHUNK, &tmA, kc * KC, (int)(prow + it.x0), a_full);
             }
         }
     } else if (warp == NAW + 1) {
-        // ================================================================= TMA: weight ring, W2 chunks 0..5 then W3 chunks 0..5 per tile
+        // ================================================================= TMA: weight ring; per tile W2 then W3, each as (kc, N half) blocks
         if (lane == 0) {
             ItemCursor it;
             it.start(a, blockIdx.x, gridDim.x);
             uint32_t g = 0;
             for (; it.valid(); it.next(a)) {
                 for (int layer = 0; layer < 2; layer++)
-                    for (int kc = 0; kc < NKC; kc++, g++) {
-                        const uint32_t st = g & 1u;
-                        if (g >= 2) mbar_wait(w_free + st, ((g - 2) >> 1) & 1u);
-                        mbar_expect_tx(w_full + st, W_STAGE);
-                        const CUtensorMap* tw = layer ? &tmW3 : &tmW2;
-                        tma_load_2d(base + OFF_W + st * W_STAGE, tw, kc * KC, 0, w_full + st);
-                        tma_load_2d(base + OFF_W + st * W_STAGE + W_HALF, tw, kc * KC, NH, w_full + st);
-                    }
+                    for (int kc = 0; kc < NKC; kc++)
+                        for (int nh = 0; nh < 2; nh++, g++) {
+                            const uint32_t st = g % NWS, use = g / NWS;
+                            if (use > 0) mbar_wait(w_free + st, (use - 1) & 1u);
+                            mbar_expect_tx(w_full + st, W_HALF);
+                            tma_load_2d(base + OFF_W + st * W_HALF, layer ? &tmW3 : &tmW2, kc * KC, nh * NH, w_full + st);
+                        }
             }
         }
     } else if (warp == NAW + 2) {
@@ -273,20 +275,18 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (; it.valid(); it.next(a), t++) {
                 if (t > 0) mbar_wait(acc_free, (t - 1) & 1u);  // the previous tile's accumulator has been drained
                 for (int layer = 0; layer < 2; layer++) {
-                    for (int kc = 0; kc < NKC; kc++, g++) {
-                        const uint32_t st = g & 1u;
+                    for (int kc = 0; kc < NKC; kc++) {
                         mbar_wait(h_full + kc, layer);  // first completion of the tile: h1, second: h2 (parity = 2t + layer)
-                        mbar_wait(w_full + st, (g >> 1) & 1u);
-                        tc_fence_after();
                         const uint64_t ad = sw128_desc(base + OFF_H + kc * H_CHUNK);
-                        const uint64_t bd0 = sw128_desc(base + OFF_W + st * W_STAGE);
-                        const uint64_t bd1 = sw128_desc(base + OFF_W + st * W_STAGE + W_HALF);
+                        for (int nh = 0; nh < 2; nh++, g++) {
+                            const uint32_t st = g % NWS, use = g / NWS;
+                            mbar_wait(w_full + st, use & 1u);
+                            tc_fence_after();
+                            const uint64_t bd = sw128_desc(base + OFF_W + st * W_HALF);
 #pragma unroll
-                        for (int k = 0; k < KC / 16; k++) {
-                            umma_f16(tmem_base, ad + 2 * k, bd0 + 2 * k, (kc | k) != 0 ? 1u : 0u);
-                            umma_f16(tmem_base + NH, ad + 2 * k, bd1 + 2 * k, (kc | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < KC / 16; k++) umma_f16(tmem_base + nh * NH, ad + 2 * k, bd + 2 * k, (kc | k) != 0 ? 1u : 0u);
+                            umma_commit(w_free + st);
                         }
-                        umma_commit(w_free + st);
                     }
                     umma_commit(acc_full);
                 }
@@ -294,92 +294,108 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ================================================================= activation / epilogue warps: thread = tile row
-        const int r = tid;  // 0..127 = TMEM lane
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+        // ================================================================= activation / epilogue warps
+        // thread = tile row r (TMEM lane) x column half: 16-byte units 4 half.. of every h1 chunk, accumulator columns 192 half..
+        const int q = warp & 3, half = warp >> 2;
+        const int r = 32 * q + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(NH * half);
         const uint32_t row_off = (uint32_t)r * 128u, rsw = (uint32_t)(r & 7);
+        const long long P = (long long)a.H * a.W;
         ItemCursor it;
         it.start(a, blockIdx.x, gridDim.x);
-        uint32_t t = 0, c_ab = 0;
-        for (; it.valid(); it.next(a), t++) {
-            // ---- h1 = relu(A1 + B1), in place in the swizzled tile (the swizzle is the same for both operands)
-            for (int kc = 0; kc < NKC; kc++, c_ab++) {
-                const uint32_t st = c_ab & 1u;
-                mbar_wait(ab_full + st, (c_ab >> 1) & 1u);
-                uint4* hp = reinterpret_cast<uint4*>(sm + OFF_H + kc * H_CHUNK + row_off);
-                const uint4* bp = reinterpret_cast<const uint4*>(sm + OFF_SB + st * H_CHUNK + row_off);
+        // the B1 rows of a tile are added from registers: this thread's 64 bytes of each of the six chunks, loaded one
+        // tile ahead (during the fc3 MMAs of the previous tile)
+        uint4 breg[NKC][4];
+        auto load_b1 = [&](const ItemCursor& c) {
+            const long long row = (long long)c.y * a.W + c.x0 - c.d + r;
+            const bool ok = row >= 0 && row < P;  // outside: the evaluation is invalid anyway
+            const uint4* src = reinterpret_cast<const uint4*>(a.B1 + (ok ? row : 0) * FC) + 4 * half;
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    uint4 x = hp[u];
-                    const uint4 y = bp[u];
+            for (int kc = 0; kc < NKC; kc++)
+#pragma unroll
+                for (int u = 0; u < 4; u++) breg[kc][u] = ok ? __ldg(src + kc * 8 + u) : make_uint4(0u, 0u, 0u, 0u);
+        };
+        if (it.valid()) load_b1(it);
+        uint32_t t = 0;
+        for (; it.valid(); t++) {
+            // ---- h1 = relu(A1 + B1), in place in the swizzled tile
+            mbar_wait(a_full, t & 1u);
+#pragma unroll
+            for (int kc = 0; kc < NKC; kc++) {
+                unsigned char* hrow = sm + OFF_H + kc * H_CHUNK + row_off;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    uint4* hp = reinterpret_cast<uint4*>(hrow + (((uint32_t)(4 * half + u) ^ rsw) << 4));
+                    uint4 x = *hp;
                     const __half2 z = __float2half2_rn(0.f);
                     __half2* xh = reinterpret_cast<__half2*>(&x);
-                    const __half2* yh = reinterpret_cast<const __half2*>(&y);
+                    const __half2* yh = reinterpret_cast<const __half2*>(&breg[kc][u]);
 #pragma unroll
-                    for (int q = 0; q < 4; q++) xh[q] = __hmax2(__hadd2(xh[q], yh[q]), z);
-                    hp[u] = x;
+                    for (int e = 0; e < 4; e++) xh[e] = __hmax2(__hadd2(xh[e], yh[e]), z);
+                    *hp = x;
                 }
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA (async proxy)
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(h_full + kc);
-                    mbar_arrive(sb_free + st);
-                }
+                if (lane == 0) mbar_arrive(h_full + kc);
             }
+            const int x = it.x0 + r, d = it.d;
+            const long long prow = (long long)it.y * a.W;
+            it.next(a);
             // ---- fc2 epilogue: h2 = relu(acc + b2) as fp16 into the same tile (fc2 has finished reading it)
             mbar_wait(acc_full, 0);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < FC / 16; c++) {
-                float v[16];
-                tmem_ld16(taddr + 16u * c, v);
+            for (int c = 0; c < NH / 16; c += 2) {
+                float v[2][16];
+                tmem_ld16(taddr + 16u * c, v[0]);
+                tmem_ld16(taddr + 16u * (c + 1), v[1]);
                 tmem_ld_wait();
-                __align__(16) __half2 hv[8];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.b2 + 16 * c) + q);
-                    hv[2 * q] = __floats2half2_rn(fmaxf(v[4 * q] + b.x, 0.f), fmaxf(v[4 * q + 1] + b.y, 0.f));
-                    hv[2 * q + 1] = __floats2half2_rn(fmaxf(v[4 * q + 2] + b.z, 0.f), fmaxf(v[4 * q + 3] + b.w, 0.f));
+                for (int p = 0; p < 2; p++) {
+                    const int col = NH * half + 16 * (c + p);
+                    __align__(16) __half2 hv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++)
+                        hv[e] = __floats2half2_rn(fmaxf(v[p][2 * e] + sbias[col + 2 * e], 0.f), fmaxf(v[p][2 * e + 1] + sbias[col + 2 * e + 1], 0.f));
+                    // columns col..col+15 = K chunk col / 64, 16-byte units (col % 64) / 8 and the next one of row r
+                    unsigned char* hrow = sm + OFF_H + (col >> 6) * H_CHUNK + row_off;
+                    const uint32_t u0 = (uint32_t)(col & 63) >> 3;
+                    *reinterpret_cast<uint4*>(hrow + ((u0 ^ rsw) << 4)) = *reinterpret_cast<const uint4*>(&hv[0]);
+                    *reinterpret_cast<uint4*>(hrow + (((u0 + 1) ^ rsw) << 4)) = *reinterpret_cast<const uint4*>(&hv[4]);
                 }
-                // columns 16c..16c+15 = K chunk c / 4, 16-byte units 2 (c & 3) and 2 (c & 3) + 1 of row r
-                unsigned char* hrow = sm + OFF_H + (c >> 2) * H_CHUNK + row_off;
-                const uint32_t u0 = 2u * (c & 3);
-                *reinterpret_cast<uint4*>(hrow + ((u0 ^ rsw) << 4)) = *reinterpret_cast<const uint4*>(&hv[0]);
-                *reinterpret_cast<uint4*>(hrow + (((u0 + 1) ^ rsw) << 4)) = *reinterpret_cast<const uint4*>(&hv[4]);
             }
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0)
                 for (int kc = 0; kc < NKC; kc++) mbar_arrive(h_full + kc);  // also: the accumulator may be overwritten
+            if (it.valid()) load_b1(it);  // in flight during the fc3 MMAs
             // ---- fc3 epilogue + fc4: z = w4 . relu(acc + b3) + b4, cost = -sigmoid(z)
             mbar_wait(acc_full, 1);
             tc_fence_after();
-            float z = a.b4;
+            float z = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < FC / 16; c++) {
-                float v[16];
-                tmem_ld16(taddr + 16u * c, v);
+            for (int c = 0; c < NH / 16; c += 2) {
+                float v[2][16];
+                tmem_ld16(taddr + 16u * c, v[0]);
+                tmem_ld16(taddr + 16u * (c + 1), v[1]);
                 tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.b3 + 16 * c) + q);
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(a.w4 + 16 * c) + q);
-                    z = fmaf(fmaxf(v[4 * q] + b.x, 0.f), w.x, z);
-                    z = fmaf(fmaxf(v[4 * q + 1] + b.y, 0.f), w.y, z);
-                    z = fmaf(fmaxf(v[4 * q + 2] + b.z, 0.f), w.z, z);
-                    z = fmaf(fmaxf(v[4 * q + 3] + b.w, 0.f), w.w, z);
+                for (int p = 0; p < 2; p++) {
+                    const int col = NH * half + 16 * (c + p);
+#pragma unroll
+                    for (int e = 0; e < 16; e++) z = fmaf(fmaxf(v[p][e] + sbias[FC + col + e], 0.f), sbias[2 * FC + col + e], z);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_free);
-            const int x = it.x0 + r;
-            if (x < a.W && x >= it.d) {
-                const float cost = -1.0f / (1.0f + expf(-z));
-                const long long prow = (long long)it.y * a.W;
-                a.CL[(prow + x) * a.Dp + it.d] = cost;
-                if (a.CR != nullptr) a.CR[(prow + x - it.d) * a.Dp + it.d] = cost;
+            if (half) zbuf[r] = z;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * NAW) : "memory");
+            if (!half && x < a.W && x >= d) {
+                const float cost = -1.0f / (1.0f + expf(-(z + zbuf[r] + a.b4)));
+                a.CL[(prow + x) * a.Dp + d] = cost;
+                if (a.CR != nullptr) a.CR[(prow + x - d) * a.Dp + d] = cost;
             }
         }
     }
@@ -463,12 +479,12 @@ extern "C" int mccnn_cost_volume_accurate(const float* fl, const float* fr, cons
     fc_fill_kernel<<<(unsigned)((P + 7) / 8), 256, 0, stream>>>(CL, CR, W, D, Dp, P, fill);
     MCCNN_LAUNCH_CHECK("fc_fill_kernel");
 
-    CUtensorMap tmA, tmB, tmW2, tmW3;
+    CUtensorMap tmA, tmW2, tmW3;
     if (int e = make_map(&tmA, A1, (size_t)P, TM)) return e;
-    if (int e = make_map(&tmB, B1, (size_t)P, TM)) return e;
     if (int e = make_map(&tmW2, w->w2t_f16, FC, NH)) return e;
     if (int e = make_map(&tmW3, w->w3t_f16, FC, NH)) return e;
     FcArgs a{};
+    a.B1 = B1;
     a.b2 = w->b2; a.b3 = w->b3; a.w4 = w->w4; a.b4 = w->b4;
     a.CL = CL; a.CR = CR;
     a.H = H; a.W = W; a.D = D; a.Dp = Dp;
@@ -477,7 +493,7 @@ extern "C" int mccnn_cost_volume_accurate(const float* fl, const float* fr, cons
     MCCNN_CUDA(cudaFuncSetAttribute(fc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
     long long grid = sm_count();
     if (grid > a.nitems) grid = a.nitems;
-    fc_head_kernel<<<(unsigned)grid, FC_THREADS, FC_SMEM, stream>>>(tmA, tmB, tmW2, tmW3, a);
+    fc_head_kernel<<<(unsigned)grid, FC_THREADS, FC_SMEM, stream>>>(tmA, tmW2, tmW3, a);
     MCCNN_LAUNCH_CHECK("fc_head_kernel");
     return 0;
 }
