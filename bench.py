@@ -37,13 +37,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c4", help="c1..c5 (SURVEY.md App. B); the metric is quoted on c4")
+    ap.add_argument("--config", default=None, help="c1..c5 (SURVEY.md App. B); the metric is quoted on c4 (default; c3 with --arch accurate)")
+    ap.add_argument("--arch", default="fast", choices=["fast", "accurate"], help="matching cost: MC-CNN-fast dot product (the reference's "
+                    "net, the headline) or the MC-CNN-accurate fully-connected decision head (BASELINE config 3; own oracle)")
     ap.add_argument("--batch", type=int, default=0, help="pairs per step per GPU (default 1; 32 for c5 = 256 pairs over 8 ranks), "
                     "kept in flight on --depth CUDA streams like match.py's streamed loop")
     ap.add_argument("--depth", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config is None:
+        a.config = "c3" if a.arch == "accurate" else "c4"
+    return a
 
 
 # ----------------------------------------------------------------------------------------- helpers
@@ -98,7 +103,7 @@ def make_pair(cfg: str, seed: int):
 
 
 # ----------------------------------------------------------------------------------------- CPU legs
-def cpu_hot_path_band(il, ir, weights, D, rows, threads):
+def cpu_hot_path_band(il, ir, weights, D, rows, threads, head=None):
     """The oracle (CPU restatement of the reference) on a horizontal band of `rows` rows of the pair:
     conv tower (torch CPU fp32, standing in for TensorFlow) + cost volume + SGM + WTA + L-R + median."""
     import torch
@@ -113,21 +118,29 @@ def cpu_hot_path_band(il, ir, weights, D, rows, threads):
     bl, br = np.ascontiguousarray(il[r0:r0 + rows]), np.ascontiguousarray(ir[r0:r0 + rows])
     t0 = time.perf_counter()
     fl, fr = ct.compute_feature(syn.standardise(bl), syn.standardise(br), 11, 11, 64, weights)
-    st.disparity_pipeline(bl, br, fl, fr, D)
+    if head is None:
+        st.disparity_pipeline(bl, br, fl, fr, D)
+    else:  # MC-CNN-accurate: the decision head (numpy fp32) as the matching cost, then the same post-processing chain
+        from oracle import fc_head as fh
+
+        cl, cr = fh.head_cost_volume(fl, fr, head, D)
+        sl, sr = st.sgm_all_paths(cl, cr, st.sgm_penalties(bl), st.sgm_penalties(br))
+        wl, wr = st.wta(sl), st.wta(sr)
+        st.median5(st.lrc_fill(wl, st.lr_flags(wl, wr)[0]), wl)
     return time.perf_counter() - t0
 
 
-def cpu_sample(il, ir, weights, D, target_s, threads):
+def cpu_sample(il, ir, weights, D, target_s, threads, head=None):
     """Pick a band height that costs about target_s seconds, run it, return (pairs/s equivalent, description)."""
     import numba
 
     numba.set_num_threads(threads)
     H, W = il.shape
-    cpu_hot_path_band(il[:, :64], ir[:, :64], weights, min(D, 16), 4, threads)  # JIT warm-up, not timed
+    cpu_hot_path_band(il[:, :64], ir[:, :64], weights, min(D, 16), 4, threads, head)  # JIT warm-up, not timed
     probe_rows = 4
-    t = cpu_hot_path_band(il, ir, weights, D, probe_rows, threads)
+    t = cpu_hot_path_band(il, ir, weights, D, probe_rows, threads, head)
     rows = int(max(probe_rows, min(H, probe_rows * target_s / max(t, 1e-3))))
-    t = cpu_hot_path_band(il, ir, weights, D, rows, threads)
+    t = cpu_hot_path_band(il, ir, weights, D, rows, threads, head)
     pairs_per_s = (rows / H) / t
     return pairs_per_s, t, f"{rows} of {H} rows x {W} px x {D} disparities of the same pair (whole hot path), {t:.1f} s"
 
@@ -146,27 +159,31 @@ def main():
     batch = a.batch if a.batch > 0 else (32 if a.config == "c5" else 1)
     shape_name = {"c1": "Middlebury-2006 third-size", "c2": "Middlebury-2005/2006 half-size", "c3": "Middlebury-2014 half-size",
                   "c4": "Middlebury-2014-shaped full-res", "c5": "KITTI-shaped"}[a.config]
-    config = {"workload": f"{a.config}: synthetic {shape_name} pair {W}x{H}, {D} disparities, MC-CNN-fast "
-                          "(5x 3x3 conv, 64 maps, random-init) + 8-path SGM + WTA + L-R check/fill + 5x5 median",
+    net = ("MC-CNN-fast (5x 3x3 conv, 64 maps, random-init)" if a.arch == "fast" else
+           "MC-CNN-accurate (5x 3x3 conv, 64 maps + fully-connected decision head 128-384-384-384-1, random-init; own oracle)")
+    config = {"workload": f"{a.config}: synthetic {shape_name} pair {W}x{H}, {D} disparities, {net} "
+                          "+ 8-path SGM + WTA + L-R check/fill + 5x5 median",
               "pairs_per_step_per_gpu": batch, "parallelism": f"pair-per-rank x{world}" + (f", {a.depth} pairs in flight per GPU" if batch > 1 else ""),
               "l2": f"per-step working set (4 fp32 volumes per pair in flight, {4 * evals * 4 / 1e9:.1f} GB each set) exceeds the 126 MB L2; no flush needed",
-              "arithmetic": "reference-exact (fp64 SGM state and cost accumulator, fp32 S rounded per path in reference order)"}
+              "arithmetic": "reference-exact (fp64 SGM state and cost accumulator, fp32 S rounded per path in reference order)" if a.arch == "fast" else
+                            "decision head: fp16 operands, fp32 accumulation on tcgen05 (own oracle, |d cost| <= 2e-3); SGM and post-processing reference-exact"}
 
     if a.impl == "reference":
         if rank != 0:
             return
         il, ir, _, _ = make_pair(a.config, 1000 + 4)
         weights = syn.glorot_weights()
+        head_w = syn.glorot_fc_weights() if a.arch == "accurate" else None
         import numba
 
         numba.set_num_threads(threads)
-        cpu_hot_path_band(il[:, :64], ir[:, :64], weights, min(D, 16), 4, threads)
-        t = cpu_hot_path_band(il, ir, weights, D, 4, threads)
+        cpu_hot_path_band(il[:, :64], ir[:, :64], weights, min(D, 16), 4, threads, head_w)
+        t = cpu_hot_path_band(il, ir, weights, D, 4, threads, head_w)
         per_step_s = max(2.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
         rows = int(max(4, min(H, 4 * per_step_s / max(t, 1e-3))))
         for _ in range(a.warmup):
-            cpu_hot_path_band(il, ir, weights, D, rows, threads)
-        ts = [cpu_hot_path_band(il, ir, weights, D, rows, threads) for _ in range(a.steps)]
+            cpu_hot_path_band(il, ir, weights, D, rows, threads, head_w)
+        ts = [cpu_hot_path_band(il, ir, weights, D, rows, threads, head_w) for _ in range(a.steps)]
         tot = float(np.sum(ts))
         v = (rows / H) * a.steps / tot
         sample = f"each step = {rows} of {H} rows x {W} px x {D} disparities (whole hot path), scaled to pairs"
@@ -195,8 +212,13 @@ def main():
     il, ir, _, _ = make_pair(a.config, 1000 + 4 + rank)
     weights = syn.glorot_weights()
     packed = eng.pack_weights(weights, 5)
+    head_w = syn.glorot_fc_weights() if a.arch == "accurate" else None
+    head = eng.FcHeadWeights(head_w) if head_w is not None else None
+    if head is not None and batch > 1:
+        raise SystemExit("--arch accurate runs one pair per step")
     d_il, d_ir = torch.from_numpy(il).cuda(), torch.from_numpy(ir).cuda()
-    ws = torch.empty(eng.match_workspace_bytes(H, W, D, 5), dtype=torch.uint8, device="cuda")
+    ws = torch.empty((eng.match_accurate_workspace_bytes if head is not None else eng.match_workspace_bytes)(H, W, D, 5),
+                     dtype=torch.uint8, device="cuda")
     out = (torch.empty((H, W), device="cuda"), torch.empty((H, W), device="cuda"))
     slots = []
     if batch > 1:  # pair-batch per rank: `depth` pairs in flight, each on its own stream with its own workspace
@@ -205,7 +227,7 @@ def main():
 
     def step():
         if batch == 1:
-            eng.match_pair(d_il, d_ir, packed, D, 5, out=out, workspace=ws)
+            eng.match_pair(d_il, d_ir, packed, D, 5, out=out, workspace=ws, head=head)
             return
         cur = torch.cuda.current_stream()
         for st, _, _ in slots:
@@ -257,7 +279,7 @@ def main():
                 streamed.submit(il, ir, i)
             streamed.drain()
             return
-        dl_, dr_ = eng.match_pair(h_il.cuda(non_blocking=True), h_ir.cuda(non_blocking=True), packed, D, 5, out=out, workspace=ws)
+        dl_, dr_ = eng.match_pair(h_il.cuda(non_blocking=True), h_ir.cuda(non_blocking=True), packed, D, 5, out=out, workspace=ws, head=head)
         h_dl.copy_(dl_, non_blocking=True)
         h_dr.copy_(dr_, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller holds the result on the host
@@ -284,7 +306,7 @@ def main():
     stage = np.zeros(7, np.float32)
     reps = max(3, a.steps)
     for _ in range(reps):
-        eng.match_pair(d_il, d_ir, packed, D, 5, stage_ms=stage, out=out, workspace=ws)
+        eng.match_pair(d_il, d_ir, packed, D, 5, stage_ms=stage, out=out, workspace=ws, head=head)
     stage /= reps
     sgm_launch_ms = float(stage[3]) / 7.0
     peak, peak_src = load_peaks()
@@ -296,8 +318,25 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "avg_launch_ms": sgm_launch_ms,
                 "stage_ms": {"features": float(stage[0]), "cost_volume": float(stage[1]), "sgm": float(stage[3]),
                              "lr_check_fill": float(stage[5]), "median": float(stage[6])}}
+    if head is not None:
+        # the decision head dominates: tensor-pipe bound; useful FLOP = evaluations with a match inside the other image x
+        # (fc2 + fc3 + fc4), fc1 is per pixel and not counted; peak = measured cuBLAS bf16 (MEASURED_PEAKS.json)
+        valid_evals = H * sum(min(D, x + 1) for x in range(W))
+        flop = valid_evals * (2.0 * 2 * 384 * 384 + 2 * 384)
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        tpeak = 1633.5
+        if os.path.exists(pk):
+            with open(pk) as f:
+                tpeak = float(json.load(f).get("bf16_tflops", tpeak))
+        ach = flop / (float(stage[1]) * 1e-3) / 1e12
+        roofline = {"kernel": "fc_head_kernel (tcgen05, fp16 operands / fp32 accumulation; 2 fc1 kernels + fill + 1 launch per pair)",
+                    "bound": "tensor", "achieved": ach, "peak": tpeak, "peak_source": "measured cuBLAS bf16 burst (MEASURED_PEAKS.json)",
+                    "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None, "algorithmic_flop_per_launch": flop,
+                    "avg_launch_ms": float(stage[1]),
+                    "stage_ms": {"features": float(stage[0]), "cost_volume": float(stage[1]), "sgm": float(stage[3]),
+                                 "lr_check_fill": float(stage[5]), "median": float(stage[6])}}
     tr = os.path.join(ROOT, "profiles", "sgm_traffic.json")
-    if os.path.exists(tr) and a.config == "c4":  # the ncu capture is of the c4 launch
+    if os.path.exists(tr) and a.config == "c4" and head is None:  # the ncu capture is of the c4 launch
         with open(tr) as f:
             t = json.load(f)
         roofline["traffic"] = t.get("dram_bytes_per_launch")
@@ -306,7 +345,7 @@ def main():
     # ---- N > 1: the same pair ALSO split by rows over all ranks (strong scaling of one pair): NVLink
     # peer-memory hand-off of the SGM path state inside the scan kernels, all_gather of the image / WTA bands
     sharded = None
-    if world > 1 and batch == 1:
+    if world > 1 and batch == 1 and head is None:
         try:
             from scenedepthestimation_b200 import sharded as sh
 
@@ -336,20 +375,20 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        v, t, desc = cpu_sample(il, ir, weights, D, a.cpu_seconds, threads)
+        v, t, desc = cpu_sample(il, ir, weights, D, a.cpu_seconds, threads, head_w)
         cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc}
 
     if rank == 0:
         print(json.dumps({
             "metric": "pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(3, a.warmup), "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "vs_baseline": None, "dtype": "f64" if head is None else "f16 x f16 -> f32 (head), f64 (SGM state)", "data": "synthetic", "config": config,
             "gdisp_evals_per_sec": value * evals / 1e9,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * H * W * batch,
                     "d2h_bytes_per_step": (2 * H * W * 4 if batch == 1 else H * W) * batch,
                     "api": "engine.match_pair (mccnn_match_pair) with pinned host u8 images in, host fp32 maps out" if batch == 1 else
                            "match.StreamedMatcher (match.py's loop): host u8 pairs in, host u8 disparity maps out"},
-            "gpu_launches": kernels_per_step(D) * a.steps * batch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": (kernels_per_step(D) + (3 if head is not None else 0) - (4 if head is not None and D >= 512 else 0)) * a.steps * batch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "single_pair_sharded": sharded}))
     if world > 1:
         dist.destroy_process_group()

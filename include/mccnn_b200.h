@@ -257,6 +257,13 @@ int mccnn_match_pair(const uint8_t* imageL, const uint8_t* imageR, const void* p
                      float* dispL_out, float* dispR_out, void* workspace, size_t workspace_bytes,
                      int H, int W, int D, int num_layers, const mccnn_sgm_params* params, int mode,
                      float* stage_ms_host, void* stream);
+/* The same path with the MC-CNN-accurate decision head as the matching cost (mccnn_cost_volume_accurate) in place of the
+ * dot product; everything after the cost volume is unchanged. stage_ms_host[1] then holds the head's time. */
+size_t mccnn_match_accurate_workspace_bytes(int H, int W, int D, int num_layers);
+int mccnn_match_pair_accurate(const uint8_t* imageL, const uint8_t* imageR, const void* packed_weights,
+                              const mccnn_fc_weights* head, float* dispL_out, float* dispR_out, void* workspace,
+                              size_t workspace_bytes, int H, int W, int D, int num_layers, const mccnn_sgm_params* params,
+                              int mode, float* stage_ms_host, void* stream);
 
 #ifdef __cplusplus
 }

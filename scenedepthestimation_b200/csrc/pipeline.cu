@@ -15,10 +15,10 @@ namespace {
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct PipeLayout {
-    size_t CL, CR, SL, SR, dl_wta, filled, flagL, armsL, armsR, sgm_ws, lrc_ws, end;
+    size_t CL, CR, SL, SR, dl_wta, filled, flagL, armsL, armsR, sgm_ws, lrc_ws, fc_ws, end;
 };
 
-PipeLayout pipe_layout(int H, int W, int D) {
+PipeLayout pipe_layout(int H, int W, int D, bool accurate = false) {
     PipeLayout l{};
     const size_t vol = align_up((size_t)H * W * disp_pitch(D) * sizeof(float));
     const size_t map = align_up((size_t)H * W * sizeof(float));
@@ -34,6 +34,7 @@ PipeLayout pipe_layout(int H, int W, int D) {
     l.armsR = o; o += align_up((size_t)H * W * 4);
     l.sgm_ws = o; o += align_up(mccnn_sgm_workspace_bytes(H, W, D));
     l.lrc_ws = o; o += align_up(mccnn_lrc_fill_workspace_bytes(H, W));
+    l.fc_ws = o; o += accurate ? align_up(mccnn_fc_head_workspace_bytes(H, W)) : 0;  // fc1 outputs of the MC-CNN-accurate head
     l.end = o;
     return l;
 }
@@ -42,7 +43,7 @@ struct MatchLayout {
     size_t padL, padR, featL, featR, conv_ws, scratch, pipe, end;
 };
 
-MatchLayout match_layout(int H, int W, int D, int nl) {
+MatchLayout match_layout(int H, int W, int D, int nl, bool accurate = false) {
     MatchLayout l{};
     const size_t pad = align_up((size_t)(H + 2 * nl) * (W + 2 * nl) * sizeof(float));
     const size_t feat = align_up((size_t)H * W * MCCNN_FEATURES * sizeof(float));
@@ -53,7 +54,7 @@ MatchLayout match_layout(int H, int W, int D, int nl) {
     l.featR = o; o += feat;
     l.conv_ws = o; o += align_up(mccnn_conv_workspace_bytes(H, W, nl));
     l.scratch = o; o += 256;
-    l.pipe = o; o += pipe_layout(H, W, D).end;
+    l.pipe = o; o += pipe_layout(H, W, D, accurate).end;
     l.end = o;
     return l;
 }
@@ -99,8 +100,8 @@ extern "C" size_t mccnn_match_workspace_bytes(int H, int W, int D, int num_layer
 
 static int run_pipeline(const uint8_t* imageL, const uint8_t* imageR, const float* fl, const float* fr, float* dispL_out,
                         float* dispR_out, char* ws, int H, int W, int D, const mccnn_sgm_params* params, int mode,
-                        StageTimer& tm, cudaStream_t stream) {
-    const PipeLayout l = pipe_layout(H, W, D);
+                        StageTimer& tm, cudaStream_t stream, const mccnn_fc_weights* head = nullptr) {
+    const PipeLayout l = pipe_layout(H, W, D, head != nullptr);
     float* CL = reinterpret_cast<float*>(ws + l.CL);
     float* CR = reinterpret_cast<float*>(ws + l.CR);
     float* SL = reinterpret_cast<float*>(ws + l.SL);
@@ -113,7 +114,10 @@ static int run_pipeline(const uint8_t* imageL, const uint8_t* imageR, const floa
     // the tensor-core variant, which wins once the disparity band is wide enough to fill its 128 x 32 tiles (measured on
     // B200: c4, D = 800: 56.3 vs 59.9 ms; c3, D = 400: 9.2 vs 8.6 ms). Its workspace borrows the S volumes, idle until SGM.
     const size_t tc_ws = mccnn_cost_volume_tc_workspace_bytes(H, W);
-    if (D >= 512 && tc_ws <= l.dl_wta - l.SL) {
+    if (head != nullptr) {
+        // MC-CNN-accurate: the matching cost is the fully-connected head on the two feature vectors (fc_head.cu)
+        if (int e = mccnn_cost_volume_accurate(fl, fr, head, CL, CR, ws + l.fc_ws, l.end - l.fc_ws, H, W, D, 1.0f, stream)) return e;
+    } else if (D >= 512 && tc_ws <= l.dl_wta - l.SL) {
         if (int e = mccnn_cost_volume_tc(fl, fr, CL, CR, ws + l.SL, l.dl_wta - l.SL, H, W, D, 1.0f, stream)) return e;
     } else {
         if (int e = mccnn_cost_volume(fl, fr, CL, CR, H, W, D, 1.0f, stream)) return e;
@@ -195,22 +199,20 @@ extern "C" int mccnn_disparity_pipeline(const uint8_t* imageL, const uint8_t* im
     return rc;
 }
 
-extern "C" int mccnn_match_pair(const uint8_t* imageL, const uint8_t* imageR, const void* packed_weights, float* dispL_out,
-                                float* dispR_out, void* workspace, size_t workspace_bytes, int H, int W, int D,
-                                int num_layers, const mccnn_sgm_params* params, int mode, float* stage_ms_host,
-                                void* stream_) {
+static int match_pair_impl(const uint8_t* imageL, const uint8_t* imageR, const void* packed_weights, const mccnn_fc_weights* head,
+                           float* dispL_out, float* dispR_out, void* workspace, size_t workspace_bytes, int H, int W, int D,
+                           int num_layers, const mccnn_sgm_params* params, int mode, float* stage_ms_host, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MCCNN_REQUIRE(imageL && imageR && packed_weights && dispL_out && dispR_out && workspace && params, MCCNN_EINVAL,
                   "mccnn_match_pair: null argument");
     MCCNN_REQUIRE(H >= 3 && W >= 3 && D >= 1 && D <= 1024 && num_layers >= 2 && num_layers <= 16, MCCNN_EINVAL,
                   "mccnn_match_pair: bad shape H=%d W=%d D=%d layers=%d", H, W, D, num_layers);
-    MCCNN_REQUIRE(workspace_bytes >= mccnn_match_workspace_bytes(H, W, D, num_layers), MCCNN_EWORKSPACE,
-                  "mccnn_match_pair: workspace too small (%zu < %zu)", workspace_bytes,
-                  mccnn_match_workspace_bytes(H, W, D, num_layers));
+    const size_t need = match_layout(H, W, D, num_layers, head != nullptr).end;
+    MCCNN_REQUIRE(workspace_bytes >= need, MCCNN_EWORKSPACE, "mccnn_match_pair: workspace too small (%zu < %zu)", workspace_bytes, need);
     MCCNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, MCCNN_EALIGN,
                   "mccnn_match_pair: workspace must be 256-byte aligned");
     char* ws = reinterpret_cast<char*>(workspace);
-    const MatchLayout l = match_layout(H, W, D, num_layers);
+    const MatchLayout l = match_layout(H, W, D, num_layers, head != nullptr);
     float* padL = reinterpret_cast<float*>(ws + l.padL);
     float* padR = reinterpret_cast<float*>(ws + l.padR);
     float* featL = reinterpret_cast<float*>(ws + l.featL);
@@ -227,7 +229,7 @@ extern "C" int mccnn_match_pair(const uint8_t* imageL, const uint8_t* imageR, co
         if ((rc = mccnn_conv_tower(padL, packed_weights, featL, ws + l.conv_ws, conv_ws, H, W, num_layers, stream))) break;
         if ((rc = mccnn_conv_tower(padR, packed_weights, featR, ws + l.conv_ws, conv_ws, H, W, num_layers, stream))) break;
         if ((rc = tm.mark())) break;  // [0] features
-        rc = run_pipeline(imageL, imageR, featL, featR, dispL_out, dispR_out, ws + l.pipe, H, W, D, params, mode, tm, stream);
+        rc = run_pipeline(imageL, imageR, featL, featR, dispL_out, dispR_out, ws + l.pipe, H, W, D, params, mode, tm, stream, head);
     } while (0);
     if (rc == 0 && stage_ms_host) {
         cudaError_t e = cudaEventSynchronize(tm.ev[tm.n - 1]);
@@ -246,4 +248,26 @@ extern "C" int mccnn_match_pair(const uint8_t* imageL, const uint8_t* imageR, co
     }
     tm.destroy();
     return rc;
+}
+
+extern "C" int mccnn_match_pair(const uint8_t* imageL, const uint8_t* imageR, const void* packed_weights, float* dispL_out,
+                                float* dispR_out, void* workspace, size_t workspace_bytes, int H, int W, int D,
+                                int num_layers, const mccnn_sgm_params* params, int mode, float* stage_ms_host,
+                                void* stream_) {
+    return match_pair_impl(imageL, imageR, packed_weights, nullptr, dispL_out, dispR_out, workspace, workspace_bytes, H, W, D,
+                           num_layers, params, mode, stage_ms_host, stream_);
+}
+
+extern "C" size_t mccnn_match_accurate_workspace_bytes(int H, int W, int D, int num_layers) {
+    if (H < 1 || W < 1 || D < 1 || num_layers < 2) return 0;
+    return match_layout(H, W, D, num_layers, true).end;
+}
+
+extern "C" int mccnn_match_pair_accurate(const uint8_t* imageL, const uint8_t* imageR, const void* packed_weights,
+                                         const mccnn_fc_weights* head, float* dispL_out, float* dispR_out, void* workspace,
+                                         size_t workspace_bytes, int H, int W, int D, int num_layers,
+                                         const mccnn_sgm_params* params, int mode, float* stage_ms_host, void* stream_) {
+    MCCNN_REQUIRE(head != nullptr, MCCNN_EINVAL, "mccnn_match_pair_accurate: null head weights");
+    return match_pair_impl(imageL, imageR, packed_weights, head, dispL_out, dispR_out, workspace, workspace_bytes, H, W, D,
+                           num_layers, params, mode, stage_ms_host, stream_);
 }

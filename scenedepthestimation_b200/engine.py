@@ -325,17 +325,27 @@ def match_workspace_bytes(H: int, W: int, D: int, num_layers: int = 5) -> int:
     return _lib.load().mccnn_match_workspace_bytes(H, W, D, num_layers)
 
 
+def match_accurate_workspace_bytes(H: int, W: int, D: int, num_layers: int = 5) -> int:
+    return _lib.load().mccnn_match_accurate_workspace_bytes(H, W, D, num_layers)
+
+
 def match_pair(imageL, imageR, packed, D: int, num_layers: int = 5, params=None, stage_ms: np.ndarray | None = None,
-               out=None, workspace: torch.Tensor | None = None):
-    """mccnn_match_pair on device u8 images -> (dispL filtered, dispR raw WTA)."""
+               out=None, workspace: torch.Tensor | None = None, head: "FcHeadWeights | None" = None):
+    """mccnn_match_pair on device u8 images -> (dispL filtered, dispR raw WTA); with `head` the matching cost is the
+    MC-CNN-accurate decision head (mccnn_match_pair_accurate)."""
     lib = _lib.load()
     H, W = imageL.shape
     params = params or _lib.default_sgm_params()
-    nws = lib.mccnn_match_workspace_bytes(H, W, D, num_layers)
+    nws = (lib.mccnn_match_accurate_workspace_bytes if head is not None else lib.mccnn_match_workspace_bytes)(H, W, D, num_layers)
     ws = workspace if workspace is not None else _ws.get(nws)
     dl, dr = out if out is not None else (torch.empty((H, W), dtype=torch.float32, device="cuda"),
                                           torch.empty((H, W), dtype=torch.float32, device="cuda"))
     sm = stage_ms.ctypes.data if stage_ms is not None else None
-    _lib.check(lib.mccnn_match_pair(_p(imageL), _p(imageR), _p(packed), _p(dl), _p(dr), _p(ws), ws.numel(), H, W, D,
-                                    num_layers, C.byref(params), EXACT, sm, _stream()), "mccnn_match_pair")
+    if head is not None:
+        _lib.check(lib.mccnn_match_pair_accurate(_p(imageL), _p(imageR), _p(packed), C.byref(head.c), _p(dl), _p(dr), _p(ws),
+                                                 ws.numel(), H, W, D, num_layers, C.byref(params), EXACT, sm, _stream()),
+                   "mccnn_match_pair_accurate")
+    else:
+        _lib.check(lib.mccnn_match_pair(_p(imageL), _p(imageR), _p(packed), _p(dl), _p(dr), _p(ws), ws.numel(), H, W, D,
+                                        num_layers, C.byref(params), EXACT, sm, _stream()), "mccnn_match_pair")
     return dl, dr

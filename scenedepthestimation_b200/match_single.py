@@ -23,13 +23,15 @@ parser.add_argument("--weights", type=str, default="./check_points_11_11/model_e
 parser.add_argument("--ndisp", type=int, default=128, help="disparity range (the reference hard-codes 128)")
 parser.add_argument("--image-dir", type=str, default="./eval/")
 parser.add_argument("--scale", type=int, default=1, help="multiply the uint8 map (match_single_ui.py uses 2)")
+parser.add_argument("--head-weights", type=str, default=None, help="MC-CNN-accurate: .npy dict with fc1..fc4 (fc() naming of "
+                    "mc_cnn_brunch.py:95-106), or 'random'; the matching cost is then the fully-connected decision head")
 
 
-def match_images(left_u8: np.ndarray, right_u8: np.ndarray, weights, ndisp: int = 128, scale: int = 1) -> np.ndarray:
+def match_images(left_u8: np.ndarray, right_u8: np.ndarray, weights, ndisp: int = 128, scale: int = 1, head=None) -> np.ndarray:
     """match_single.py:34-55 for in-memory images -> the uint8 map the reference would write."""
     from . import process_functional as pf
 
-    left_disparity, _ = pf.match_pair(left_u8, right_u8, weights, ndisp=ndisp)
+    left_disparity, _ = pf.match_pair(left_u8, right_u8, weights, ndisp=ndisp, head=head)
     return (left_disparity.astype('uint8') * scale).astype('uint8')
 
 
@@ -48,7 +50,8 @@ def main(argv=None):
     if left is None or right is None:
         raise FileNotFoundError(f"{left_image_path} / {right_image_path}")
     weights = synthetic.glorot_weights() if args.weights == 'random' else args.weights
-    out = match_images(left, right, weights, args.ndisp, args.scale)
+    head = synthetic.glorot_fc_weights() if args.head_weights == 'random' else args.head_weights
+    out = match_images(left, right, weights, args.ndisp, args.scale, head)
     out_dir = './result/{}'.format(args.file)
     os.makedirs(out_dir, exist_ok=True)
     cv2.imwrite(os.path.join(out_dir, 'ld{}.png'.format(args.id)), out)

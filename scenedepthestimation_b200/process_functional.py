@@ -117,15 +117,32 @@ def disparity_compute_by_gpu(imagel, imager, featuresl, featuresr, detail_time, 
     return dl.cpu().numpy(), dr.cpu().numpy(), detail_time
 
 
-def match_pair(left_u8, right_u8, checkpoint, ndisp=None, patch=11, detail_time=None, params=None):
-    """Fused match_single.py:34-55: u8 pair -> (left disparity f32, right raw WTA f32), one C call."""
+_head_cache = {}
+
+
+def _load_head(head):
+    """MC-CNN-accurate head weights: a dict / .npy path holding fc1..fc4 (the reference's fc() variable names,
+    mc_cnn_brunch.py:95-106) -> device copy in the kernel's layout, cached per object / path."""
+    if head is None or isinstance(head, _e.FcHeadWeights):
+        return head
+    key = head if isinstance(head, str) else id(head)
+    if key not in _head_cache:
+        w = np.load(head, encoding='bytes', allow_pickle=True).item() if isinstance(head, str) else head
+        w = {(k.decode() if isinstance(k, bytes) else k): v for k, v in w.items()}
+        _head_cache[key] = _e.FcHeadWeights(w)
+    return _head_cache[key]
+
+
+def match_pair(left_u8, right_u8, checkpoint, ndisp=None, patch=11, detail_time=None, params=None, head=None):
+    """Fused match_single.py:34-55: u8 pair -> (left disparity f32, right raw WTA f32), one C call. `head` (weights dict
+    or .npy path with fc1..fc4) switches the matching cost to the MC-CNN-accurate decision head."""
     _e._require_cuda()
     D = int(NDISP if ndisp is None else ndisp)
     nl = patch // 2
     packed = _load_weights(checkpoint, nl)
     il, ir = _e._dev(left_u8, torch.uint8), _e._dev(right_u8, torch.uint8)
     stage = np.zeros(7, np.float32) if detail_time is not None else None
-    dl, dr = _e.match_pair(il, ir, packed, D, nl, params=params, stage_ms=stage)
+    dl, dr = _e.match_pair(il, ir, packed, D, nl, params=params, stage_ms=stage, head=_load_head(head))
     if detail_time is not None:
         detail_time += (stage / 1000.0).astype(detail_time.dtype)
     return dl.cpu().numpy(), dr.cpu().numpy()

@@ -598,3 +598,27 @@ def test_accurate_head_vs_oracle(eng, H, W, D, gain):
         assert torch.isinf(CL[..., D:]).all() and torch.isinf(CR[..., D:]).all()
     only_left, none = eng.cost_volume_accurate(dev(fl), dev(fr), head, D, right=False)
     assert none is None and torch.equal(only_left, CL)
+
+
+def test_accurate_pipeline_end_to_end(eng):
+    """u8 pair -> disparity with the MC-CNN-accurate head in ONE C call (mccnn_match_pair_accurate): identical to the stages
+    called one by one, and everything after the head's cost volume is bit-exact against the oracle run on that volume."""
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import process_functional as pf
+    from scenedepthestimation_b200 import synthetic as syn
+
+    H, W, D = 24, 150, 40
+    il, ir, _ = syn.textured_pair(H, W, D, 21)
+    w, hw = syn.glorot_weights(), syn.glorot_fc_weights(gain=2.5)
+    dl, dr = pf.match_pair(il, ir, w, ndisp=D, head=hw)
+    packed, head = eng.pack_weights(w, 5), eng.FcHeadWeights(hw)
+    fl = eng.conv_tower(eng.standardize_pad(dev(il), 5), packed, 5)
+    fr = eng.conv_tower(eng.standardize_pad(dev(ir), 5), packed, 5)
+    CL, CR = eng.cost_volume_accurate(fl, fr, head, D)
+    cl, cr = unpitch(CL, D), unpitch(CR, D)
+    sl, sr = st.sgm_all_paths(cl, cr, st.sgm_penalties(il), st.sgm_penalties(ir))
+    wl, wr = st.wta(sl), st.wta(sr)
+    fll, _ = st.lr_flags(wl, wr)
+    exp = st.median5(st.lrc_fill(wl, fll), wl)
+    assert np.array_equal(dl, exp) and np.array_equal(dr, wr)
+    assert len(np.unique(dl)) > 4
