@@ -303,17 +303,22 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long P = (long long)a.H * a.W;
         ItemCursor it;
         it.start(a, blockIdx.x, gridDim.x);
-        // the B1 rows of a tile are added from registers: this thread's 64 bytes of each of the six chunks, loaded one
-        // tile ahead (during the fc3 MMAs of the previous tile)
+        // The B1 rows of a tile (one contiguous 96 KB block of global memory) are added from registers, loaded one tile ahead
+        // (during the fc3 MMAs of the previous tile). For this step a thread is not tied to its TMEM row: per K chunk it takes
+        // the 16-byte unit bu of rows br + 32 i, so that 8 lanes read one full 128-byte line (a row-per-thread mapping costs
+        // 32 lines per load instruction and 4.8k of the 26k cycles of a tile, measured).
+        const int bu = tid & 7, br = tid >> 3;
         uint4 breg[NKC][4];
         auto load_b1 = [&](const ItemCursor& c) {
-            const long long row = (long long)c.y * a.W + c.x0 - c.d + r;
-            const bool ok = row >= 0 && row < P;  // outside: the evaluation is invalid anyway
-            const uint4* src = reinterpret_cast<const uint4*>(a.B1 + (ok ? row : 0) * FC) + 4 * half;
+            const long long row0 = (long long)c.y * a.W + c.x0 - c.d + br;
 #pragma unroll
-            for (int kc = 0; kc < NKC; kc++)
+            for (int i = 0; i < 4; i++) {
+                const long long row = row0 + 32 * i;
+                const bool ok = row >= 0 && row < P;  // outside: the evaluation is invalid anyway
+                const uint4* src = reinterpret_cast<const uint4*>(a.B1 + (ok ? row : 0) * FC) + bu;
 #pragma unroll
-                for (int u = 0; u < 4; u++) breg[kc][u] = ok ? __ldg(src + kc * 8 + u) : make_uint4(0u, 0u, 0u, 0u);
+                for (int kc = 0; kc < NKC; kc++) breg[kc][i] = ok ? __ldg(src + kc * 8) : make_uint4(0u, 0u, 0u, 0u);
+            }
         };
         if (it.valid()) load_b1(it);
         uint32_t t = 0;
@@ -322,14 +327,14 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(a_full, t & 1u);
 #pragma unroll
             for (int kc = 0; kc < NKC; kc++) {
-                unsigned char* hrow = sm + OFF_H + kc * H_CHUNK + row_off;
+                unsigned char* hq = sm + OFF_H + kc * H_CHUNK + br * 128 + ((uint32_t)(bu ^ (br & 7)) << 4);  // + 32 i rows: same swizzle phase
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    uint4* hp = reinterpret_cast<uint4*>(hrow + (((uint32_t)(4 * half + u) ^ rsw) << 4));
+                for (int i = 0; i < 4; i++) {
+                    uint4* hp = reinterpret_cast<uint4*>(hq + i * 32 * 128);
                     uint4 x = *hp;
                     const __half2 z = __float2half2_rn(0.f);
                     __half2* xh = reinterpret_cast<__half2*>(&x);
-                    const __half2* yh = reinterpret_cast<const __half2*>(&breg[kc][u]);
+                    const __half2* yh = reinterpret_cast<const __half2*>(&breg[kc][i]);
 #pragma unroll
                     for (int e = 0; e < 4; e++) xh[e] = __hmax2(__hadd2(xh[e], yh[e]), z);
                     *hp = x;
