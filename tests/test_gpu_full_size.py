@@ -96,3 +96,51 @@ def test_full_size_properties(eng, cfg):
     for m in a:
         assert bool(((m >= 0) & (m <= D - 1)).all()) and bool(torch.isfinite(m).all())
     assert bool((a[1] == a[1].round()).all())  # raw WTA map holds integers; the left map holds fill means k/1..4 too
+
+
+@pytest.mark.parametrize("cfg", ["c2", "c3"])
+def test_accurate_head_full_size(eng, cfg):
+    """MC-CNN-accurate decision head at BASELINE config 3's full size (and c2): the right volume is the shear of the left one
+    bit for bit (one value is written to both), fills / pads as for the fast net, every valid cost in (-1, 0), two runs are
+    identical, and 4000 random evaluations recomputed one by one on the CPU (fp16-emulating oracle arithmetic,
+    oracle/fc_head.py) agree to 5e-4."""
+    from scenedepthestimation_b200 import synthetic as syn
+
+    W, H, D = syn.CONFIGS[cfg]
+    fl, fr = _unit_features(H, W, 21), _unit_features(H, W, 22)
+    w = syn.glorot_fc_weights(gain=2.5)
+    head = eng.FcHeadWeights(w)
+    CL, CR = eng.cost_volume_accurate(fl, fr, head, D)
+    CL2, _ = eng.cost_volume_accurate(fl, fr, head, D, right=False)
+    assert torch.equal(_bits(CL), _bits(CL2))
+    del CL2
+    Dp = CL.shape[-1]
+    d = torch.arange(D, device="cuda")
+    x = torch.arange(W, device="cuda")
+    rows = max(1, (1 << 28) // (W * Dp))
+    for y0 in range(0, H, rows):
+        cl, cr = CL[y0:y0 + rows, :, :D], CR[y0:y0 + rows, :, :D]
+        xs = x[:, None] + d[None, :]
+        ok = xs < W
+        gathered = cl[:, xs.clamp(max=W - 1), d[None, :].expand(W, D)]
+        exp = torch.where(ok[None], gathered, torch.ones((), device="cuda"))
+        assert torch.equal(_bits(cr), _bits(exp)), f"{cfg}: CR is not the shear of CL in rows {y0}.."
+        valid = (x[:, None] >= d[None, :])[None].expand_as(cl)
+        assert bool(((cl < 0) & (cl > -1))[valid].all()) and bool((cl[~valid] == 1.0).all())
+    if Dp > D:
+        assert bool(torch.isinf(CL[..., D:]).all())
+    rng = np.random.default_rng(7)
+    ys, ds = rng.integers(0, H, 4000), rng.integers(0, D, 4000)
+    xs_ = np.array([rng.integers(dd, W) for dd in ds])
+    f16 = lambda a: a.astype(np.float16)
+    W1 = w["fc1/weights:0"]
+    fln, frn = fl.cpu().numpy(), fr.cpu().numpy()
+    A1 = f16(fln[ys, xs_] @ W1[:64] + w["fc1/biases:0"])
+    B1 = f16(frn[ys, xs_ - ds] @ W1[64:])
+    h1 = np.maximum(A1 + B1, 0).astype(np.float32)
+    h2 = f16(np.maximum(h1 @ f16(w["fc2/weights:0"]).astype(np.float32) + w["fc2/biases:0"], 0)).astype(np.float32)
+    h3 = np.maximum(h2 @ f16(w["fc3/weights:0"]).astype(np.float32) + w["fc3/biases:0"], 0)
+    z = h3 @ w["fc4/weights:0"].reshape(-1) + w["fc4/biases:0"][0]
+    exp = -1.0 / (1.0 + np.exp(-z.astype(np.float64)))
+    got = CL[torch.from_numpy(ys).cuda(), torch.from_numpy(xs_).cuda(), torch.from_numpy(ds).cuda()].cpu().numpy()
+    assert np.abs(got - exp).max() <= 5e-4
