@@ -51,50 +51,60 @@ __global__ void __launch_bounds__(256) cross_arms_kernel(const uint8_t* __restri
                                           (unsigned char)len[3]);
 }
 
+// Both passes are bound by instruction issue (ncu: ~95 instructions per evaluation in the first version, 16 warps per SM
+// allowed by the fp64 rings), so the per-step work is kept lean: a flat thread index over (row, d) (no idle lanes, no
+// per-thread 64-bit index products), the arms of a pixel as two u16x2 words (one PRMT each from the uchar4) so that one
+// VIMNMX.U16x2 takes both minima of an intersection, ring slots addressed by a masked position, and in the column
+// pass the vertical arms of a row stored with that row's count prefix (no second pass over the arms).
+constexpr int CB_PF = 8;  // steps whose loads are in flight while the previous chunk runs through the prefix chain
+
+__device__ __forceinline__ unsigned arms_lr(unsigned w) { return __byte_perm(w, 0u, 0x4140); }  // left | right << 16
+__device__ __forceinline__ unsigned arms_ud(unsigned w) { return __byte_perm(w, 0u, 0x4342); }  // up | down << 16
+
 // Row pass: H[y][x][d] = sum of vol[y][xx][d] over the column window of (y, x, d).
-template <int RING>
+// Ring: slot p % RING holds the fp64 prefix of elements < p, as [RING][CB_THREADS] doubles.
+template <int RING, int DIR>
 __global__ void __launch_bounds__(CB_THREADS) cbca_row_kernel(const float* __restrict__ vol, float* __restrict__ Hs,
-                                                             const uchar4* __restrict__ armsA,
-                                                             const uchar4* __restrict__ armsB, int W, int D, int Dp,
-                                                             int dir, int L1) {
-    extern __shared__ double ring_d[];  // [RING][CB_THREADS]
-    const int y = blockIdx.y;
-    const int d = blockIdx.x * CB_THREADS + threadIdx.x;
-    if (d >= Dp) return;
+                                                             const unsigned* __restrict__ armsA,
+                                                             const unsigned* __restrict__ armsB, int H, int W, int D, int Dp,
+                                                             int L1) {
+    extern __shared__ double ring_d[];
+    const long long gid = (long long)blockIdx.x * CB_THREADS + threadIdx.x;
+    if (gid >= (long long)H * Dp) return;
+    const int y = (int)(gid / Dp), d = (int)(gid - (long long)y * Dp);
     double* ring = ring_d + threadIdx.x;
     const float* vrow = vol + (size_t)y * W * Dp + d;
     float* hrow = Hs + (size_t)y * W * Dp + d;
-    const uchar4* aA = armsA + (size_t)y * W;
-    const uchar4* aB = armsB + (size_t)y * W;
     if (d >= D) {  // pad entries stay +INF
         for (int x = 0; x < W; x++) hrow[(size_t)x * Dp] = kInf;
         return;
     }
-    double run = 0.0;
-    ring[0] = 0.0;  // prefix before element 0 sits in slot 0; prefix including element x in slot (x + 1) % RING
+    const unsigned* aA = armsA + (size_t)y * W;
+    const unsigned* aB = armsB + (size_t)y * W + DIR * d;  // B pixel of x: aB[x], valid for 0 <= x + DIR * d < W
+    const int xo_lo = DIR < 0 ? d : 0, xo_hi = DIR < 0 ? W : W - d;  // x range with a B pixel
     const int la = L1 - 1;  // an arm reaches at most x + L1 - 1
-    // software pipeline: the loads of chunk k+1 (8 cost rows, the arms of the 8 pixels it emits) are in flight
-    // while chunk k runs through the dependent prefix / ring updates
-    float v[8], vn[8];
-    uchar4 ea[8], eb[8], ean[8], ebn[8];
-    auto fetch = [&](int s0, float (&vv)[8], uchar4 (&aa)[8], uchar4 (&bb)[8]) {
+    double run = 0.0;
+    ring[0] = 0.0;
+    float v[CB_PF], vn[CB_PF];
+    unsigned ea[CB_PF], ean[CB_PF], eb[CB_PF], ebn[CB_PF];
+    auto fetch = [&](int s0, float (&vv)[CB_PF], unsigned (&aa)[CB_PF], unsigned (&bb)[CB_PF]) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < CB_PF; u++) {
             const int s = s0 + u;
             vv[u] = (s < W) ? __ldg(vrow + (size_t)s * Dp) : 0.0f;
-            const int x = min(max(s - la, 0), W - 1);
-            const int xo = min(max(x + dir * d, 0), W - 1);
-            aa[u] = aA[x];
-            bb[u] = aB[xo];
+            const int x = s - la;
+            const bool has_b = x >= xo_lo && x < xo_hi;
+            aa[u] = has_b ? __ldg(aA + x) : 0u;
+            bb[u] = has_b ? __ldg(aB + x) : 0u;
         }
     };
     fetch(0, vn, ean, ebn);
-    for (int s0 = 0; s0 < W + la; s0 += 8) {
+    for (int s0 = 0; s0 < W + la; s0 += CB_PF) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) { v[u] = vn[u]; ea[u] = ean[u]; eb[u] = ebn[u]; }
-        if (s0 + 8 < W + la) fetch(s0 + 8, vn, ean, ebn);
+        for (int u = 0; u < CB_PF; u++) { v[u] = vn[u]; ea[u] = ean[u]; eb[u] = ebn[u]; }
+        if (s0 + CB_PF < W + la) fetch(s0 + CB_PF, vn, ean, ebn);
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < CB_PF; u++) {
             const int s = s0 + u;
             if (s < W) {
                 run += (double)v[u];
@@ -102,12 +112,12 @@ __global__ void __launch_bounds__(CB_THREADS) cbca_row_kernel(const float* __res
             }
             const int x = s - la;
             if (x >= 0 && x < W) {
-                const int xo = x + dir * d;
-                float out = 0.0f;  // no B-pixel: never used, the column pass passes the original entry through
-                if (xo >= 0 && xo < W) {
-                    const int lo = x - min((int)ea[u].x, (int)eb[u].x);      // exclusive
-                    const int hi = x + min((int)ea[u].y, (int)eb[u].y) - 1;  // inclusive
-                    out = (float)(ring[((hi + 1) & (RING - 1)) * CB_THREADS] - ring[((lo + 1) & (RING - 1)) * CB_THREADS]);
+                float out = 0.0f;  // no B pixel: never used, the column pass passes the original entry through
+                if (x >= xo_lo && x < xo_hi) {
+                    const unsigned m = __vminu2(arms_lr(ea[u]), arms_lr(eb[u]));
+                    const int lo1 = x + 1 - (int)(m & 0xffffu);  // first summed element
+                    const int hi1 = x + (int)(m >> 16);         // one past the last
+                    out = (float)(ring[(hi1 & (RING - 1)) * CB_THREADS] - ring[(lo1 & (RING - 1)) * CB_THREADS]);
                 }
                 hrow[(size_t)x * Dp] = out;
             }
@@ -116,77 +126,96 @@ __global__ void __launch_bounds__(CB_THREADS) cbca_row_kernel(const float* __res
 }
 
 // Column pass: out[y][x][d] = sum of H[yy][x][d] over the row window / number of summed entries.
-template <int RING>
+// Rings: [RING][CB_THREADS] fp64 prefix sums; [RING][CB_THREADS] words = prefix of the row counts << 10 (22 bits: H * 63 < 2^22)
+// | (up - 1) << 5 | (down - 1) of the row the prefix ends with.
+template <int RING, int DIR>
 __global__ void __launch_bounds__(CB_THREADS) cbca_col_kernel(const float* __restrict__ Hs, const float* __restrict__ vol,
-                                                             float* __restrict__ out, const uchar4* __restrict__ armsA,
-                                                             const uchar4* __restrict__ armsB, int H, int W, int D, int Dp,
-                                                             int dir, int L1) {
-    extern __shared__ double ring_d[];  // [RING][CB_THREADS] sums, then [RING][CB_THREADS] counts (int)
-    const int x = blockIdx.y;
-    const int d = blockIdx.x * CB_THREADS + threadIdx.x;
-    if (d >= Dp) return;
+                                                             float* __restrict__ out, const unsigned* __restrict__ armsA,
+                                                             const unsigned* __restrict__ armsB, int H, int W, int D, int Dp,
+                                                             int L1) {
+    extern __shared__ double ring_d[];
+    const long long gid = (long long)blockIdx.x * CB_THREADS + threadIdx.x;
+    if (gid >= (long long)W * Dp) return;
+    const int x = (int)(gid / Dp), d = (int)(gid - (long long)x * Dp);
     double* ring = ring_d + threadIdx.x;
-    int* ringn = reinterpret_cast<int*>(ring_d + RING * CB_THREADS) + threadIdx.x;
+    unsigned* ringw = reinterpret_cast<unsigned*>(ring_d + RING * CB_THREADS) + threadIdx.x;
     const size_t rstride = (size_t)W * Dp;
     const float* hcol = Hs + (size_t)x * Dp + d;
     const float* vcol = vol + (size_t)x * Dp + d;
     float* ocol = out + (size_t)x * Dp + d;
     if (d >= D) {
-        for (int y = 0; y < H; y++) ocol[(size_t)y * rstride] = kInf;
+        for (int yy = 0; yy < H; yy++) ocol[(size_t)yy * rstride] = kInf;
         return;
     }
-    const int xo = x + dir * d;
+    const int xo = x + DIR * d;
     if (xo < 0 || xo >= W) {  // no B-pixel: pass through
-        for (int y = 0; y < H; y++) ocol[(size_t)y * rstride] = __ldg(vcol + (size_t)y * rstride);
+        for (int yy = 0; yy < H; yy++) ocol[(size_t)yy * rstride] = __ldg(vcol + (size_t)yy * rstride);
         return;
     }
-    const uchar4* aA = armsA + x;
-    const uchar4* aB = armsB + xo;
+    const unsigned* aA = armsA + x;
+    const unsigned* aB = armsB + xo;
     double run = 0.0;
-    int runn = 0;
+    unsigned runn = 0;
     ring[0] = 0.0;
-    ringn[0] = 0;
+    ringw[0] = 0u;
     const int la = L1 - 1;
-    float v[8], vn[8];
-    uchar4 a[8], b[8], an[8], bn[8], ea[8], eb[8], ean[8], ebn[8];
-    auto fetch = [&](int s0, float (&vv)[8], uchar4 (&aa)[8], uchar4 (&bb)[8], uchar4 (&eaa)[8], uchar4 (&ebb)[8]) {
+    float v[CB_PF], vn[CB_PF];
+    unsigned a[CB_PF], an[CB_PF], b[CB_PF], bn[CB_PF];
+    auto fetch = [&](int s0, float (&vv)[CB_PF], unsigned (&aa)[CB_PF], unsigned (&bb)[CB_PF]) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < CB_PF; u++) {
             const int s = s0 + u;
-            const int sc = min(s, H - 1);
-            vv[u] = (s < H) ? __ldg(hcol + (size_t)s * rstride) : 0.0f;
-            aa[u] = aA[(size_t)sc * W];
-            bb[u] = aB[(size_t)sc * W];
-            const int y = min(max(s - la, 0), H - 1);
-            eaa[u] = aA[(size_t)y * W];
-            ebb[u] = aB[(size_t)y * W];
+            const bool in = s < H;
+            vv[u] = in ? __ldg(hcol + (size_t)s * rstride) : 0.0f;
+            aa[u] = in ? __ldg(aA + (size_t)s * W) : 0x01010101u;
+            bb[u] = in ? __ldg(aB + (size_t)s * W) : 0x01010101u;
         }
     };
-    fetch(0, vn, an, bn, ean, ebn);
-    for (int s0 = 0; s0 < H + la; s0 += 8) {
+    fetch(0, vn, an, bn);
+    for (int s0 = 0; s0 < H + la; s0 += CB_PF) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) { v[u] = vn[u]; a[u] = an[u]; b[u] = bn[u]; ea[u] = ean[u]; eb[u] = ebn[u]; }
-        if (s0 + 8 < H + la) fetch(s0 + 8, vn, an, bn, ean, ebn);
+        for (int u = 0; u < CB_PF; u++) { v[u] = vn[u]; a[u] = an[u]; b[u] = bn[u]; }
+        if (s0 + CB_PF < H + la) fetch(s0 + CB_PF, vn, an, bn);
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < CB_PF; u++) {
             const int s = s0 + u;
             if (s < H) {
                 run += (double)v[u];
-                runn += min((int)a[u].x, (int)b[u].x) + min((int)a[u].y, (int)b[u].y) - 1;
-                ring[((s + 1) & (RING - 1)) * CB_THREADS] = run;
-                ringn[((s + 1) & (RING - 1)) * CB_THREADS] = runn;
+                const unsigned lr = __vminu2(arms_lr(a[u]), arms_lr(b[u]));
+                const unsigned ud = __vminu2(arms_ud(a[u]), arms_ud(b[u]));
+                runn += (lr & 0xffffu) + (lr >> 16) - 1u;  // entries of the row window of (s, x, d)
+                const int sl = ((s + 1) & (RING - 1)) * CB_THREADS;
+                ring[sl] = run;
+                ringw[sl] = (runn << 10) | (((ud & 0xffffu) - 1u) << 5) | ((ud >> 16) - 1u);  // the arms of row s travel with its prefix
             }
             const int y = s - la;
             if (y >= 0 && y < H) {
-                const int lo = y - min((int)ea[u].z, (int)eb[u].z);      // exclusive
-                const int hi = y + min((int)ea[u].w, (int)eb[u].w) - 1;  // inclusive
-                const int ih = ((hi + 1) & (RING - 1)) * CB_THREADS, il = ((lo + 1) & (RING - 1)) * CB_THREADS;
+                const unsigned e = ringw[((y + 1) & (RING - 1)) * CB_THREADS];
+                const int up = (int)((e >> 5) & 31u) + 1, dn = (int)(e & 31u) + 1;
+                const int ih = ((y + dn) & (RING - 1)) * CB_THREADS, il = ((y - up + 1) & (RING - 1)) * CB_THREADS;
                 const double sum = ring[ih] - ring[il];
-                const int cnt = ringn[ih] - ringn[il];
-                ocol[(size_t)y * rstride] = (float)(sum / (double)cnt);
+                const unsigned cnt = (ringw[ih] >> 10) - (ringw[il] >> 10);
+                ocol[(size_t)y * rstride] = (float)sum / (float)cnt;
             }
         }
     }
+}
+
+template <int RING, int DIR>
+int launch_cbca(const float* vol_in, float* vol_out, float* tmp, const unsigned* aA, const unsigned* aB, int H, int W, int D,
+                int Dp, int L1, cudaStream_t stream) {
+    const size_t smr = (size_t)RING * CB_THREADS * sizeof(double);
+    const size_t smc = smr + (size_t)RING * CB_THREADS * sizeof(unsigned);
+    MCCNN_CUDA(cudaFuncSetAttribute(cbca_row_kernel<RING, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+    MCCNN_CUDA(cudaFuncSetAttribute(cbca_col_kernel<RING, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+    const long long nrow = (long long)H * Dp, ncol = (long long)W * Dp;
+    cbca_row_kernel<RING, DIR><<<(unsigned)((nrow + CB_THREADS - 1) / CB_THREADS), CB_THREADS, smr, stream>>>(vol_in, tmp, aA, aB, H, W, D,
+                                                                                                         Dp, L1);
+    MCCNN_LAUNCH_CHECK("cbca_row_kernel");
+    cbca_col_kernel<RING, DIR><<<(unsigned)((ncol + CB_THREADS - 1) / CB_THREADS), CB_THREADS, smc, stream>>>(tmp, vol_in, vol_out, aA, aB,
+                                                                                                         H, W, D, Dp, L1);
+    MCCNN_LAUNCH_CHECK("cbca_col_kernel");
+    return 0;
 }
 
 }  // namespace
@@ -215,24 +244,12 @@ extern "C" int mccnn_cbca(const float* vol_in, float* vol_out, float* tmp, const
     MCCNN_REQUIRE(direction == -1 || direction == 1, MCCNN_EINVAL, "mccnn_cbca: direction must be -1 (left volume) or +1 (right)");
     MCCNN_REQUIRE(L1 >= 1 && L1 <= 32, MCCNN_EINVAL, "mccnn_cbca: L1=%d outside 1..32", L1);
     const int Dp = disp_pitch(D);
-    const uchar4* aA = reinterpret_cast<const uchar4*>(arms_self);
-    const uchar4* aB = reinterpret_cast<const uchar4*>(arms_other);
-    const int nd = ceil_div(Dp, CB_THREADS);
-    if (L1 <= 16) {
-        const size_t smr = (size_t)32 * CB_THREADS * sizeof(double), smc = smr + (size_t)32 * CB_THREADS * sizeof(int);
-        MCCNN_CUDA(cudaFuncSetAttribute(cbca_col_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
-        cbca_row_kernel<32><<<dim3(nd, H), CB_THREADS, smr, stream>>>(vol_in, tmp, aA, aB, W, D, Dp, direction, L1);
-        MCCNN_LAUNCH_CHECK("cbca_row_kernel");
-        cbca_col_kernel<32><<<dim3(nd, W), CB_THREADS, smc, stream>>>(tmp, vol_in, vol_out, aA, aB, H, W, D, Dp, direction, L1);
-        MCCNN_LAUNCH_CHECK("cbca_col_kernel");
-    } else {
-        const size_t smr = (size_t)64 * CB_THREADS * sizeof(double), smc = smr + (size_t)64 * CB_THREADS * sizeof(int);
-        MCCNN_CUDA(cudaFuncSetAttribute(cbca_row_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-        MCCNN_CUDA(cudaFuncSetAttribute(cbca_col_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
-        cbca_row_kernel<64><<<dim3(nd, H), CB_THREADS, smr, stream>>>(vol_in, tmp, aA, aB, W, D, Dp, direction, L1);
-        MCCNN_LAUNCH_CHECK("cbca_row_kernel");
-        cbca_col_kernel<64><<<dim3(nd, W), CB_THREADS, smc, stream>>>(tmp, vol_in, vol_out, aA, aB, H, W, D, Dp, direction, L1);
-        MCCNN_LAUNCH_CHECK("cbca_col_kernel");
-    }
-    return 0;
+    const unsigned* aA = reinterpret_cast<const unsigned*>(arms_self);  // uchar4 {left, right, up, down} as one word
+    const unsigned* aB = reinterpret_cast<const unsigned*>(arms_other);
+    // ring slots: a window reaches L1 - 1 elements ahead of and L1 behind the emission position
+    if (L1 <= 16)
+        return direction < 0 ? launch_cbca<32, -1>(vol_in, vol_out, tmp, aA, aB, H, W, D, Dp, L1, stream)
+                             : launch_cbca<32, 1>(vol_in, vol_out, tmp, aA, aB, H, W, D, Dp, L1, stream);
+    return direction < 0 ? launch_cbca<64, -1>(vol_in, vol_out, tmp, aA, aB, H, W, D, Dp, L1, stream)
+                         : launch_cbca<64, 1>(vol_in, vol_out, tmp, aA, aB, H, W, D, Dp, L1, stream);
 }
