@@ -85,41 +85,69 @@ __global__ void __launch_bounds__(CB_THREADS) cbca_row_kernel(const float* __res
     const int la = L1 - 1;  // an arm reaches at most x + L1 - 1
     double run = 0.0;
     ring[0] = 0.0;
+    // Addresses: one pointer per stream, advanced once per chunk of CB_PF steps; inside a chunk the offsets u * Dp are loop
+    // invariants (a 64-bit index product per access was a third of all instructions). Chunks that lie entirely inside
+    // [la, W) take a path without range tests on s and x.
     float v[CB_PF], vn[CB_PF];
     unsigned ea[CB_PF], ean[CB_PF], eb[CB_PF], ebn[CB_PF];
-    auto fetch = [&](int s0, float (&vv)[CB_PF], unsigned (&aa)[CB_PF], unsigned (&bb)[CB_PF]) {
+    const unsigned nb = (unsigned)(xo_hi - xo_lo);  // x has a B pixel iff (unsigned)(x - xo_lo) < nb
+    auto fetch = [&](int s0, const float* vp, float (&vv)[CB_PF], unsigned (&aa)[CB_PF], unsigned (&bb)[CB_PF]) {
+        if (s0 >= la && s0 + CB_PF <= W) {
 #pragma unroll
-        for (int u = 0; u < CB_PF; u++) {
-            const int s = s0 + u;
-            vv[u] = (s < W) ? __ldg(vrow + (size_t)s * Dp) : 0.0f;
-            const int x = s - la;
-            const bool has_b = x >= xo_lo && x < xo_hi;
-            aa[u] = has_b ? __ldg(aA + x) : 0u;
-            bb[u] = has_b ? __ldg(aB + x) : 0u;
+            for (int u = 0; u < CB_PF; u++) {
+                vv[u] = __ldg(vp + u * Dp);
+                const int x = s0 - la + u;
+                const bool has_b = (unsigned)(x - xo_lo) < nb;
+                aa[u] = has_b ? __ldg(aA + x) : 0u;
+                bb[u] = has_b ? __ldg(aB + x) : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < CB_PF; u++) {
+                const int s = s0 + u;
+                vv[u] = (s < W) ? __ldg(vp + u * Dp) : 0.0f;
+                const int x = s - la;
+                const bool has_b = x >= 0 && x < W && (unsigned)(x - xo_lo) < nb;
+                aa[u] = has_b ? __ldg(aA + x) : 0u;
+                bb[u] = has_b ? __ldg(aB + x) : 0u;
+            }
         }
     };
-    fetch(0, vn, ean, ebn);
-    for (int s0 = 0; s0 < W + la; s0 += CB_PF) {
+    const float* vp = vrow;          // element s0 of the row
+    float* hp = hrow - (size_t)la * Dp;  // element s0 - la (not dereferenced before s0 - la + u >= 0)
+    const size_t chunk = (size_t)CB_PF * Dp;
+    fetch(0, vp, vn, ean, ebn);
+    for (int s0 = 0; s0 < W + la; s0 += CB_PF, vp += chunk, hp += chunk) {
 #pragma unroll
         for (int u = 0; u < CB_PF; u++) { v[u] = vn[u]; ea[u] = ean[u]; eb[u] = ebn[u]; }
-        if (s0 + CB_PF < W + la) fetch(s0 + CB_PF, vn, ean, ebn);
-#pragma unroll
-        for (int u = 0; u < CB_PF; u++) {
-            const int s = s0 + u;
-            if (s < W) {
-                run += (double)v[u];
-                ring[((s + 1) & (RING - 1)) * CB_THREADS] = run;
+        if (s0 + CB_PF < W + la) fetch(s0 + CB_PF, vp + chunk, vn, ean, ebn);
+        auto emit = [&](int u, int x) {
+            float out = 0.0f;  // no B pixel: never used, the column pass passes the original entry through
+            if ((unsigned)(x - xo_lo) < nb) {
+                const unsigned m = __vminu2(arms_lr(ea[u]), arms_lr(eb[u]));
+                const int lo1 = x + 1 - (int)(m & 0xffffu);  // first summed element
+                const int hi1 = x + (int)(m >> 16);         // one past the last
+                out = (float)(ring[(hi1 & (RING - 1)) * CB_THREADS] - ring[(lo1 & (RING - 1)) * CB_THREADS]);
             }
-            const int x = s - la;
-            if (x >= 0 && x < W) {
-                float out = 0.0f;  // no B pixel: never used, the column pass passes the original entry through
-                if (x >= xo_lo && x < xo_hi) {
-                    const unsigned m = __vminu2(arms_lr(ea[u]), arms_lr(eb[u]));
-                    const int lo1 = x + 1 - (int)(m & 0xffffu);  // first summed element
-                    const int hi1 = x + (int)(m >> 16);         // one past the last
-                    out = (float)(ring[(hi1 & (RING - 1)) * CB_THREADS] - ring[(lo1 & (RING - 1)) * CB_THREADS]);
+            hp[u * Dp] = out;
+        };
+        if (s0 >= la && s0 + CB_PF <= W) {
+#pragma unroll
+            for (int u = 0; u < CB_PF; u++) {
+                run += (double)v[u];
+                ring[((s0 + u + 1) & (RING - 1)) * CB_THREADS] = run;
+                emit(u, s0 - la + u);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < CB_PF; u++) {
+                const int s = s0 + u;
+                if (s < W) {
+                    run += (double)v[u];
+                    ring[((s + 1) & (RING - 1)) * CB_THREADS] = run;
                 }
-                hrow[(size_t)x * Dp] = out;
+                const int x = s - la;
+                if (x >= 0 && x < W) emit(u, x);
             }
         }
     }
@@ -161,41 +189,67 @@ __global__ void __launch_bounds__(CB_THREADS) cbca_col_kernel(const float* __res
     const int la = L1 - 1;
     float v[CB_PF], vn[CB_PF];
     unsigned a[CB_PF], an[CB_PF], b[CB_PF], bn[CB_PF];
-    auto fetch = [&](int s0, float (&vv)[CB_PF], unsigned (&aa)[CB_PF], unsigned (&bb)[CB_PF]) {
+    auto fetch = [&](int s0, const float* hq, const unsigned* pa, const unsigned* pb, float (&vv)[CB_PF], unsigned (&aa)[CB_PF],
+                     unsigned (&bb)[CB_PF]) {
+        if (s0 + CB_PF <= H) {
 #pragma unroll
-        for (int u = 0; u < CB_PF; u++) {
-            const int s = s0 + u;
-            const bool in = s < H;
-            vv[u] = in ? __ldg(hcol + (size_t)s * rstride) : 0.0f;
-            aa[u] = in ? __ldg(aA + (size_t)s * W) : 0x01010101u;
-            bb[u] = in ? __ldg(aB + (size_t)s * W) : 0x01010101u;
+            for (int u = 0; u < CB_PF; u++) {
+                vv[u] = __ldg(hq + (size_t)u * rstride);
+                aa[u] = __ldg(pa + u * W);
+                bb[u] = __ldg(pb + u * W);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < CB_PF; u++) {
+                const bool in = s0 + u < H;
+                vv[u] = in ? __ldg(hq + (size_t)u * rstride) : 0.0f;
+                aa[u] = in ? __ldg(pa + u * W) : 0x01010101u;
+                bb[u] = in ? __ldg(pb + u * W) : 0x01010101u;
+            }
         }
     };
-    fetch(0, vn, an, bn);
-    for (int s0 = 0; s0 < H + la; s0 += CB_PF) {
+    // one pointer per stream, advanced once per chunk (see the row pass)
+    const float* hq = hcol;                       // row s0
+    const unsigned *pa = aA, *pb = aB;            // row s0
+    float* oq = ocol - (size_t)la * rstride;      // row s0 - la (not dereferenced before that row exists)
+    const size_t chunk = (size_t)CB_PF * rstride, achunk = (size_t)CB_PF * W;
+    fetch(0, hq, pa, pb, vn, an, bn);
+    for (int s0 = 0; s0 < H + la; s0 += CB_PF, hq += chunk, pa += achunk, pb += achunk, oq += chunk) {
 #pragma unroll
         for (int u = 0; u < CB_PF; u++) { v[u] = vn[u]; a[u] = an[u]; b[u] = bn[u]; }
-        if (s0 + CB_PF < H + la) fetch(s0 + CB_PF, vn, an, bn);
+        if (s0 + CB_PF < H + la) fetch(s0 + CB_PF, hq + chunk, pa + achunk, pb + achunk, vn, an, bn);
+        auto accumulate = [&](int u, int s) {
+            run += (double)v[u];
+            const unsigned lr = __vminu2(arms_lr(a[u]), arms_lr(b[u]));
+            const unsigned ud = __vminu2(arms_ud(a[u]), arms_ud(b[u]));
+            runn += (lr & 0xffffu) + (lr >> 16) - 1u;  // entries of the row window of (s, x, d)
+            const int sl = ((s + 1) & (RING - 1)) * CB_THREADS;
+            ring[sl] = run;
+            // the arms of row s travel with its prefix: (up - 1) << 5 | (down - 1), both fields from one subtraction
+            const unsigned udm = ud - 0x00010001u;
+            ringw[sl] = (runn << 10) | ((udm & 0xffffu) << 5) | (udm >> 16);
+        };
+        auto emit = [&](int u, int y) {
+            const unsigned e = ringw[((y + 1) & (RING - 1)) * CB_THREADS];
+            const int up = (int)((e >> 5) & 31u), dn = (int)(e & 31u);  // lengths - 1
+            const int ih = ((y + dn + 1) & (RING - 1)) * CB_THREADS, il = ((y - up) & (RING - 1)) * CB_THREADS;
+            const double sum = ring[ih] - ring[il];
+            const unsigned cnt = (ringw[ih] >> 10) - (ringw[il] >> 10);
+            oq[(size_t)u * rstride] = (float)sum / (float)cnt;
+        };
+        if (s0 >= la && s0 + CB_PF <= H) {
 #pragma unroll
-        for (int u = 0; u < CB_PF; u++) {
-            const int s = s0 + u;
-            if (s < H) {
-                run += (double)v[u];
-                const unsigned lr = __vminu2(arms_lr(a[u]), arms_lr(b[u]));
-                const unsigned ud = __vminu2(arms_ud(a[u]), arms_ud(b[u]));
-                runn += (lr & 0xffffu) + (lr >> 16) - 1u;  // entries of the row window of (s, x, d)
-                const int sl = ((s + 1) & (RING - 1)) * CB_THREADS;
-                ring[sl] = run;
-                ringw[sl] = (runn << 10) | (((ud & 0xffffu) - 1u) << 5) | ((ud >> 16) - 1u);  // the arms of row s travel with its prefix
+            for (int u = 0; u < CB_PF; u++) {
+                accumulate(u, s0 + u);
+                emit(u, s0 - la + u);
             }
-            const int y = s - la;
-            if (y >= 0 && y < H) {
-                const unsigned e = ringw[((y + 1) & (RING - 1)) * CB_THREADS];
-                const int up = (int)((e >> 5) & 31u) + 1, dn = (int)(e & 31u) + 1;
-                const int ih = ((y + dn) & (RING - 1)) * CB_THREADS, il = ((y - up + 1) & (RING - 1)) * CB_THREADS;
-                const double sum = ring[ih] - ring[il];
-                const unsigned cnt = (ringw[ih] >> 10) - (ringw[il] >> 10);
-                ocol[(size_t)y * rstride] = (float)sum / (float)cnt;
+        } else {
+#pragma unroll
+            for (int u = 0; u < CB_PF; u++) {
+                const int s = s0 + u;
+                if (s < H) accumulate(u, s);
+                const int y = s - la;
+                if (y >= 0 && y < H) emit(u, y);
             }
         }
     }
