@@ -114,3 +114,35 @@ def test_cbca_oracle_self_consistency():
     gl, gr = st.cbca(cl, cr, il, ir, 2, L1, tau)
     for d in range(D):
         np.testing.assert_allclose(gr[:, :W - d, d], gl[:, d:, d], rtol=1e-6, atol=1e-7)
+
+
+def test_accurate_head_oracle_self_consistency():
+    """oracle/fc_head.py (MC-CNN-accurate decision head; the reference only has fc(), mc_cnn_brunch.py:95-106: parity
+    unpinned): the per-image split of fc1 equals the network evaluated literally on the concatenated vector, the right
+    volume is the shear of the left one, fills where the match leaves the image, and rounding to fp16 where the CUDA
+    kernel does moves a cost by less than 2e-3."""
+    from oracle import fc_head as fh
+    from scenedepthestimation_b200 import synthetic as syn
+
+    H, W, D = 3, 37, 20
+    fl, fr = syn.unit_features(H, W, 64, 3)
+    w = syn.glorot_fc_weights(gain=2.5)
+    cl, cr = fh.head_cost_volume(fl, fr, w, D, dtype=np.float64)
+    relu = lambda v: np.maximum(v, 0)
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        y, d = rng.integers(0, H), rng.integers(0, D)
+        x = rng.integers(d, W)
+        v = np.concatenate([fl[y, x], fr[y, x - d]]).astype(np.float64)
+        h = relu(v @ w["fc1/weights:0"] + w["fc1/biases:0"])
+        h = relu(h @ w["fc2/weights:0"] + w["fc2/biases:0"])
+        h = relu(h @ w["fc3/weights:0"] + w["fc3/biases:0"])
+        z = h @ w["fc4/weights:0"].reshape(-1) + w["fc4/biases:0"][0]
+        assert abs(-1.0 / (1.0 + np.exp(-z)) - cl[y, x, d]) < 1e-6
+        assert cr[y, x - d, d] == cl[y, x, d]
+    x, d = np.arange(W)[:, None], np.arange(D)[None, :]
+    assert (cl[:, x < d] == 1.0).all() and (cr[:, x + d >= W] == 1.0).all()
+    assert ((cl[:, x >= d] < 0) & (cl[:, x >= d] > -1)).all()
+    c16, _ = fh.head_cost_volume(fl, fr, w, D, emulate_fp16=True)
+    c32, _ = fh.head_cost_volume(fl, fr, w, D)
+    assert np.abs(c16 - c32).max() < 2e-3 and np.abs(c32 - cl).max() < 1e-5
