@@ -38,9 +38,12 @@ constexpr int NKC = FC / KC;                   // 6
 constexpr int NH = FC / 2;                     // 192: N of one MMA
 constexpr int H_CHUNK = TM * 128;              // 16384 bytes: [128 rows][64 fp16]
 constexpr int W_HALF = NH * 128;               // 24576 bytes: [192 n][64 fp16], one stage of the weight ring
-constexpr int NWS = 5;                         // weight ring stages (120 KB in flight: the kernel is bound by this stream)
-constexpr int OFF_H = 0;                       // 6 chunks: h1, then h2
-constexpr int OFF_W = OFF_H + NKC * H_CHUNK;   // 98304
+constexpr int NWS = 4;                         // weight ring stages (96 KB in flight; 3 stages make the weight stream the bound, measured)
+constexpr int NH1 = 1;                         // h1 chunks 0..2 have their own buffer (built for the NEXT tile while fc3 of this one runs);
+                                               // chunks 3..5 borrow the first three chunks of the h2 tile, idle between fc3 and the fc2 epilogue
+constexpr int OFF_H1 = 0;                      // h1 chunks 0..2
+constexpr int OFF_H2 = OFF_H1 + NH1 * H_CHUNK; // 49152: the whole h2 tile (6 chunks)
+constexpr int OFF_W = OFF_H2 + NKC * H_CHUNK;  // 147456
 constexpr int OFF_BIAS = OFF_W + NWS * W_HALF; // 221184: b2, b3, w4 (3 x 384 floats)
 constexpr int OFF_Z = OFF_BIAS + 3 * FC * 4;   // 225792: partial fc4 sums of the upper column half (128 floats)
 constexpr int OFF_BAR = OFF_Z + TM * 4;        // 226304
@@ -185,10 +188,14 @@ struct ItemCursor {
     }
 };
 
-// Barriers: a_full (TMA bytes of the six A1 chunks of a tile), h_full[6] (8 arrivals: chunk kc of the A operand is in shared
-// memory; completes twice per tile: h1, h2), w_full[5] (TMA bytes), w_free[5] (tcgen05.commit: the MMAs reading the stage are
-// done), acc_full (commit; twice per tile), acc_free (8 arrivals: the accumulator has been drained after fc3), l3_done
-// (commit: fc3 no longer reads the h tile).
+// Barriers (one completion per tile unless noted): a_full[6] (TMA bytes of A1 chunk kc), h_full[6] (8 arrivals: chunk kc holds
+// relu(A1 + B1)), h1_free[3] (tcgen05.commit: the fc2 MMAs reading h1 chunk kc < 3 are done), l3_done (commit: fc3 no longer
+// reads the h2 tile), h2_full (8 arrivals: the fc2 epilogue has written the h2 tile and drained the accumulator), w_full[3]
+// (TMA bytes) / w_free[3] (commit), per use of a ring stage; acc_full (commit; twice per tile: fc2, fc3), acc_free (8 arrivals:
+// the accumulator has been drained after fc3).
+// Timeline of tile t on the activation warps: [h1 chunks 3..5 of t in place in the idle h2 tile, under the first fc2 MMAs] ->
+// wait fc2 -> fc2 epilogue (h2 tile) -> [B1 loads and h1 chunks 0..2 of t + 1, under the fc3 MMAs] -> wait fc3 -> fc3 epilogue +
+// fc4 -> store. The A1 chunks 3..5 of t + 1 land in the h2 tile as soon as fc3 of t has finished, i.e. under the fc3 epilogue.
 __global__ void __launch_bounds__(FC_THREADS, 1)
 fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW2,
                const __grid_constant__ CUtensorMap tmW3, const FcArgs a) {
@@ -197,28 +204,34 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* sm = smem_raw + (base - raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
-    uint64_t* a_full = bars;
-    uint64_t* h_full = bars + 1;          // [6]
-    uint64_t* w_full = bars + 7;          // [NWS]
-    uint64_t* w_free = bars + 7 + NWS;    // [NWS]
-    uint64_t* acc_full = bars + 7 + 2 * NWS;
-    uint64_t* acc_free = acc_full + 1;
-    uint64_t* l3_done = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 3);
+    uint64_t* a_full = bars;                  // [NKC]
+    uint64_t* h_full = bars + NKC;            // [NKC]
+    uint64_t* h1_free = bars + 2 * NKC;       // [NH1]
+    uint64_t* w_full = h1_free + NH1;         // [NWS]
+    uint64_t* w_free = w_full + NWS;          // [NWS]
+    uint64_t* h2_full = w_free + NWS;
+    uint64_t* acc_full = h2_full + 1;
+    uint64_t* acc_free = h2_full + 2;
+    uint64_t* l3_done = h2_full + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h2_full + 4);
     float* sbias = reinterpret_cast<float*>(sm + OFF_BIAS);  // [0] b2, [1] b3, [2] w4
     float* zbuf = reinterpret_cast<float*>(sm + OFF_Z);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        mbar_init(a_full, 1);
+        for (int k = 0; k < NKC; k++) {
+            mbar_init(a_full + k, 1);
+            mbar_init(h_full + k, NAW);
+        }
+        for (int k = 0; k < NH1; k++) mbar_init(h1_free + k, 1);
+        mbar_init(l3_done, 1);
         for (int s = 0; s < NWS; s++) {
             mbar_init(w_full + s, 1);
             mbar_init(w_free + s, 1);
         }
-        for (int k = 0; k < NKC; k++) mbar_init(h_full + k, NAW);
+        mbar_init(h2_full, NAW);
         mbar_init(acc_full, 1);
         mbar_init(acc_free, NAW);
-        mbar_init(l3_done, 1);
         mbar_fence_init();
     }
     for (int i = tid; i < FC; i += FC_THREADS) {
@@ -237,16 +250,21 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == NAW) {
-        // ================================================================= TMA: the six A1 chunks of a tile, straight into the h tile
+        // ================================================================= TMA: A1 chunks 0..2 into the h1 buffer (free once fc2 of the previous
+        // tile has consumed them), chunks 3..5 into the h2 tile (free once fc3 of the previous tile has finished)
         if (lane == 0) {
             ItemCursor it;
             it.start(a, blockIdx.x, gridDim.x);
             uint32_t t = 0;
             for (; it.valid(); it.next(a), t++) {
-                if (t > 0) mbar_wait(l3_done, (t - 1) & 1u);  // fc3 of the previous tile has read the h tile
                 const long long prow = (long long)it.y * a.W;
-                mbar_expect_tx(a_full, NKC * H_CHUNK);
-                for (int kc = 0; kc < NKC; kc++) tma_load_2d(base + OFF_H + kc * H_CHUNK, &tmA, kc * KC, (int)(prow + it.x0), a_full);
+                for (int kc = 0; kc < NKC; kc++) {
+                    if (t > 0 && kc < NH1) mbar_wait(h1_free + kc, (t - 1) & 1u);
+                    if (t > 0 && kc == NH1) mbar_wait(l3_done, (t - 1) & 1u);
+                    mbar_expect_tx(a_full + kc, H_CHUNK);
+                    const uint32_t dst = kc < NH1 ? OFF_H1 + kc * H_CHUNK : OFF_H2 + (kc - NH1) * H_CHUNK;
+                    tma_load_2d(base + dst, &tmA, kc * KC, (int)(prow + it.x0), a_full + kc);
+                }
             }
         }
     } else if (warp == NAW + 1) {
@@ -275,9 +293,16 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (; it.valid(); it.next(a), t++) {
                 if (t > 0) mbar_wait(acc_free, (t - 1) & 1u);  // the previous tile's accumulator has been drained
                 for (int layer = 0; layer < 2; layer++) {
+                    if (layer) mbar_wait(h2_full, t & 1u);
                     for (int kc = 0; kc < NKC; kc++) {
-                        mbar_wait(h_full + kc, layer);  // first completion of the tile: h1, second: h2 (parity = 2t + layer)
-                        const uint64_t ad = sw128_desc(base + OFF_H + kc * H_CHUNK);
+                        uint32_t a_addr;
+                        if (layer == 0) {
+                            mbar_wait(h_full + kc, t & 1u);
+                            a_addr = base + (kc < NH1 ? OFF_H1 + kc * H_CHUNK : OFF_H2 + (kc - NH1) * H_CHUNK);
+                        } else {
+                            a_addr = base + OFF_H2 + kc * H_CHUNK;
+                        }
+                        const uint64_t ad = sw128_desc(a_addr);
                         for (int nh = 0; nh < 2; nh++, g++) {
                             const uint32_t st = g % NWS, use = g / NWS;
                             mbar_wait(w_full + st, use & 1u);
@@ -287,6 +312,7 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int k = 0; k < KC / 16; k++) umma_f16(tmem_base + nh * NH, ad + 2 * k, bd + 2 * k, (kc | k) != 0 ? 1u : 0u);
                             umma_commit(w_free + st);
                         }
+                        if (layer == 0 && kc < NH1) umma_commit(h1_free + kc);
                     }
                     umma_commit(acc_full);
                 }
@@ -295,18 +321,16 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ================================================================= activation / epilogue warps
-        // thread = tile row r (TMEM lane) x column half: 16-byte units 4 half.. of every h1 chunk, accumulator columns 192 half..
+        // epilogues: thread = tile row r (TMEM lane) x column half (accumulator columns 192 half..)
         const int q = warp & 3, half = warp >> 2;
         const int r = 32 * q + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(NH * half);
         const uint32_t row_off = (uint32_t)r * 128u, rsw = (uint32_t)(r & 7);
         const long long P = (long long)a.H * a.W;
-        ItemCursor it;
-        it.start(a, blockIdx.x, gridDim.x);
-        // The B1 rows of a tile (one contiguous 96 KB block of global memory) are added from registers, loaded one tile ahead
-        // (during the fc3 MMAs of the previous tile). For this step a thread is not tied to its TMEM row: per K chunk it takes
-        // the 16-byte unit bu of rows br + 32 i, so that 8 lanes read one full 128-byte line (a row-per-thread mapping costs
-        // 32 lines per load instruction and 4.8k of the 26k cycles of a tile, measured).
+        // The B1 rows of a tile (one contiguous 96 KB block of global memory) are added from registers, loaded one tile ahead.
+        // For this step a thread is not tied to its TMEM row: per K chunk it takes the 16-byte unit bu of rows br + 32 i, so that
+        // 8 lanes read one full 128-byte line (a row-per-thread mapping costs 32 lines per load instruction and 4.8k of the
+        // 26k cycles of a tile, measured).
         const int bu = tid & 7, br = tid >> 3;
         uint4 breg[NKC][4];
         auto load_b1 = [&](const ItemCursor& c) {
@@ -320,33 +344,42 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kc = 0; kc < NKC; kc++) breg[kc][i] = ok ? __ldg(src + kc * 8) : make_uint4(0u, 0u, 0u, 0u);
             }
         };
-        if (it.valid()) load_b1(it);
+        // h1 chunk kc of tile number tt = relu(A1 + B1), in place where the TMA put the A1 chunk
+        auto build_h1 = [&](int kc, uint32_t tt) {
+            mbar_wait(a_full + kc, tt & 1u);
+            unsigned char* hq = sm + (kc < NH1 ? OFF_H1 + kc * H_CHUNK : OFF_H2 + (kc - NH1) * H_CHUNK) + br * 128 +
+                                ((uint32_t)(bu ^ (br & 7)) << 4);  // + 32 i rows: same swizzle phase
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint4* hp = reinterpret_cast<uint4*>(hq + i * 32 * 128);
+                uint4 x = *hp;
+                const __half2 z = __float2half2_rn(0.f);
+                __half2* xh = reinterpret_cast<__half2*>(&x);
+                const __half2* yh = reinterpret_cast<const __half2*>(&breg[kc][i]);
+#pragma unroll
+                for (int e = 0; e < 4; e++) xh[e] = __hmax2(__hadd2(xh[e], yh[e]), z);
+                *hp = x;
+            }
+            fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h_full + kc);
+        };
+        ItemCursor it;
+        it.start(a, blockIdx.x, gridDim.x);
+        if (it.valid()) {
+            load_b1(it);
+#pragma unroll
+            for (int kc = 0; kc < NH1; kc++) build_h1(kc, 0u);
+        }
         uint32_t t = 0;
         for (; it.valid(); t++) {
-            // ---- h1 = relu(A1 + B1), in place in the swizzled tile
-            mbar_wait(a_full, t & 1u);
+            // ---- h1 chunks 3..5 of this tile, in the idle h2 tile (their A1 rows arrived under the previous fc3 epilogue)
 #pragma unroll
-            for (int kc = 0; kc < NKC; kc++) {
-                unsigned char* hq = sm + OFF_H + kc * H_CHUNK + br * 128 + ((uint32_t)(bu ^ (br & 7)) << 4);  // + 32 i rows: same swizzle phase
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    uint4* hp = reinterpret_cast<uint4*>(hq + i * 32 * 128);
-                    uint4 x = *hp;
-                    const __half2 z = __float2half2_rn(0.f);
-                    __half2* xh = reinterpret_cast<__half2*>(&x);
-                    const __half2* yh = reinterpret_cast<const __half2*>(&breg[kc][i]);
-#pragma unroll
-                    for (int e = 0; e < 4; e++) xh[e] = __hmax2(__hadd2(xh[e], yh[e]), z);
-                    *hp = x;
-                }
-                fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(h_full + kc);
-            }
+            for (int kc = NH1; kc < NKC; kc++) build_h1(kc, t);
             const int x = it.x0 + r, d = it.d;
             const long long prow = (long long)it.y * a.W;
             it.next(a);
-            // ---- fc2 epilogue: h2 = relu(acc + b2) as fp16 into the same tile (fc2 has finished reading it)
+            // ---- fc2 epilogue: h2 = relu(acc + b2) as fp16 into the h2 tile (fc3 of the previous tile has long finished)
             mbar_wait(acc_full, 0);
             tc_fence_after();
 #pragma unroll 1
@@ -363,7 +396,7 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int e = 0; e < 8; e++)
                         hv[e] = __floats2half2_rn(fmaxf(v[p][2 * e] + sbias[col + 2 * e], 0.f), fmaxf(v[p][2 * e + 1] + sbias[col + 2 * e + 1], 0.f));
                     // columns col..col+15 = K chunk col / 64, 16-byte units (col % 64) / 8 and the next one of row r
-                    unsigned char* hrow = sm + OFF_H + (col >> 6) * H_CHUNK + row_off;
+                    unsigned char* hrow = sm + OFF_H2 + (col >> 6) * H_CHUNK + row_off;
                     const uint32_t u0 = (uint32_t)(col & 63) >> 3;
                     *reinterpret_cast<uint4*>(hrow + ((u0 ^ rsw) << 4)) = *reinterpret_cast<const uint4*>(&hv[0]);
                     *reinterpret_cast<uint4*>(hrow + (((u0 + 1) ^ rsw) << 4)) = *reinterpret_cast<const uint4*>(&hv[4]);
@@ -372,9 +405,13 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0)
-                for (int kc = 0; kc < NKC; kc++) mbar_arrive(h_full + kc);  // also: the accumulator may be overwritten
-            if (it.valid()) load_b1(it);  // in flight during the fc3 MMAs
+            if (lane == 0) mbar_arrive(h2_full);  // also: the accumulator may be overwritten by fc3
+            // ---- under the fc3 MMAs: the B1 rows and the first h1 chunks of the next tile
+            if (it.valid()) {
+                load_b1(it);
+#pragma unroll
+                for (int kc = 0; kc < NH1; kc++) build_h1(kc, t + 1);
+            }
             // ---- fc3 epilogue + fc4: z = w4 . relu(acc + b3) + b4, cost = -sigmoid(z)
             mbar_wait(acc_full, 1);
             tc_fence_after();
