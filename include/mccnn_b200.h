@@ -126,7 +126,8 @@ int mccnn_cost_volume_tc(const float* fl, const float* fr, float* CL, float* CR,
  * fc2 / fc3 run on tcgen05 with fp16 operands and fp32 accumulation (csrc/fc_head.cu); |error| of a cost is a few 1e-4.
  * All pointers are device pointers:
  *   w1_left / w1_right: fp32 [64][384], rows 0..63 / 64..127 of fc1/weights (the layer is split per image)
- *   w2t_f16 / w3t_f16 : fp16 [384 out][384 in], the TRANSPOSE of fc2/weights, fc3/weights (K-major for the MMA)
+ *   w2_blocks_f16 / w3_blocks_f16: fc2/weights, fc3/weights ([384 in][384 out]) packed by mccnn_pack_fc_matrix_host into the
+ *                       12 pre-swizzled [192 out][64 in] fp16 blocks the kernel streams (mccnn_fc_matrix_blocks_bytes() bytes)
  *   b1, b2, b3, w4    : fp32 [384]; b4: the scalar fc4 bias
  * workspace: mccnn_fc_head_workspace_bytes(H, W) bytes, 256-byte aligned. */
 #define MCCNN_FC_UNITS 384
@@ -134,13 +135,15 @@ typedef struct {
     const float* w1_left;
     const float* w1_right;
     const float* b1;
-    const void* w2t_f16;
+    const void* w2_blocks_f16;
     const float* b2;
-    const void* w3t_f16;
+    const void* w3_blocks_f16;
     const float* b3;
     const float* w4;
     float b4;
 } mccnn_fc_weights;
+size_t mccnn_fc_matrix_blocks_bytes(void);
+int mccnn_pack_fc_matrix_host(const float* w_in_out_host, void* blocks_f16_host);
 size_t mccnn_fc_head_workspace_bytes(int H, int W);
 int mccnn_cost_volume_accurate(const float* fl, const float* fr, const mccnn_fc_weights* weights, float* CL, float* CR,
                                void* workspace, size_t workspace_bytes, int H, int W, int D, float fill, void* stream);

@@ -25,8 +25,8 @@ class Shard(C.Structure):
 
 class FcWeights(C.Structure):
     """mccnn_fc_weights: device pointers of the MC-CNN-accurate head (include/mccnn_b200.h)."""
-    _fields_ = [("w1_left", C.c_void_p), ("w1_right", C.c_void_p), ("b1", C.c_void_p), ("w2t_f16", C.c_void_p),
-                ("b2", C.c_void_p), ("w3t_f16", C.c_void_p), ("b3", C.c_void_p), ("w4", C.c_void_p), ("b4", C.c_float)]
+    _fields_ = [("w1_left", C.c_void_p), ("w1_right", C.c_void_p), ("b1", C.c_void_p), ("w2_blocks_f16", C.c_void_p),
+                ("b2", C.c_void_p), ("w3_blocks_f16", C.c_void_p), ("b3", C.c_void_p), ("w4", C.c_void_p), ("b4", C.c_float)]
 
 
 _vp, _sz, _i, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_float
@@ -49,6 +49,8 @@ SIGNATURES = {
     "mccnn_cost_volume": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "mccnn_cost_volume_tc_workspace_bytes": (_sz, [_i, _i]),
     "mccnn_cost_volume_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp]),
+    "mccnn_fc_matrix_blocks_bytes": (_sz, []),
+    "mccnn_pack_fc_matrix_host": (_i, [_vp, _vp]),
     "mccnn_fc_head_workspace_bytes": (_sz, [_i, _i]),
     "mccnn_cost_volume_accurate": (_i, [_vp, _vp, C.POINTER(FcWeights), _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp]),
     "mccnn_volume_to_dhw": (_i, [_vp, _vp, _i, _i, _i, _vp]),

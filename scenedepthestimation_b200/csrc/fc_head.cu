@@ -17,7 +17,7 @@
 //     image row at one disparity: the A1 and B1 rows of the tile are two contiguous [128][384] blocks. A1 comes by TMA
 //     in six K chunks of 64 straight into the 128-byte-swizzled K-major layout; the activation warps add the B1 rows
 //     (held in registers, loaded one tile ahead) + ReLU in place. W2 / W3 stream through a five-stage ring of
-//     [192 n][64 k] blocks (24 KB each, TMA from L2), four K = 16 MMAs of N = 192 per block. The 128 x 384 fp32 accumulator
+//     [192 n][64 k] blocks (24 KB each, pre-swizzled on the host, one bulk copy from L2 per block), four K = 16 MMAs of N = 192 per block. The 128 x 384 fp32 accumulator
 //     (384 TMEM columns) is drained by the activation warps: bias + ReLU + fp16 back into the same shared-memory tile as
 //     the A operand of fc3; after fc3: bias + ReLU, dot with w4, sigmoid, store.
 //   * Warp roles: 8 activation / epilogue warps (TMEM lane quarter x column half), 1 TMA warp for the A1 chunks, 1 TMA
@@ -151,6 +151,8 @@ __global__ void __launch_bounds__(256) fc_fill_kernel(float* __restrict__ CL, fl
 
 struct FcArgs {
     const __half* B1;  // fc1 of the right image, [P][384]
+    const unsigned char* w2b;  // fc2 / fc3 weights as 12 pre-swizzled [192 n][64 k] fp16 blocks each (mccnn_pack_fc_matrix_host)
+    const unsigned char* w3b;
     const float* b2;
     const float* b3;
     const float* w4;
@@ -197,8 +199,7 @@ struct ItemCursor {
 // wait fc2 -> fc2 epilogue (h2 tile) -> [B1 loads and h1 chunks 0..2 of t + 1, under the fc3 MMAs] -> wait fc3 -> fc3 epilogue +
 // fc4 -> store. The A1 chunks 3..5 of t + 1 land in the h2 tile as soon as fc3 of t has finished, i.e. under the fc3 epilogue.
 __global__ void __launch_bounds__(FC_THREADS, 1)
-fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW2,
-               const __grid_constant__ CUtensorMap tmW3, const FcArgs a) {
+fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const FcArgs a) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -280,7 +281,8 @@ fc_head_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const uint32_t st = g % NWS, use = g / NWS;
                             if (use > 0) mbar_wait(w_free + st, (use - 1) & 1u);
                             mbar_expect_tx(w_full + st, W_HALF);
-                            tma_load_2d(base + OFF_W + st * W_HALF, layer ? &tmW3 : &tmW2, kc * KC, nh * NH, w_full + st);
+                            // one contiguous 24 KB block, already in the 128-byte-swizzled layout the MMA reads
+                            bulk_g2s(sm + OFF_W + st * W_HALF, (layer ? a.w3b : a.w2b) + (size_t)(kc * 2 + nh) * W_HALF, W_HALF, w_full + st);
                         }
             }
         }
@@ -488,6 +490,27 @@ inline size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 using namespace mccnn;
 
+extern "C" size_t mccnn_fc_matrix_blocks_bytes(void) { return (size_t)FC * FC * sizeof(__half); }
+
+// fc2 / fc3 weights [384 in][384 out] fp32 (the reference's fc() layout, mc_cnn_brunch.py:97) -> the 12 blocks the kernel
+// streams: block (kc, nh) = outputs 192 nh.., inputs 64 kc.., as [192 n][64 k] fp16 K-major rows of 128 bytes whose 16-byte
+// units sit at position u ^ (n & 7) (the 128-byte swizzle tcgen05 reads), blocks in (kc, nh) order.
+extern "C" int mccnn_pack_fc_matrix_host(const float* w_in_out_host, void* blocks_f16_host) {
+    MCCNN_REQUIRE(w_in_out_host && blocks_f16_host, MCCNN_EINVAL, "mccnn_pack_fc_matrix_host: null argument");
+    __half* out = reinterpret_cast<__half*>(blocks_f16_host);
+    for (int kc = 0; kc < NKC; kc++)
+        for (int nh = 0; nh < 2; nh++) {
+            __half* blk = out + (size_t)(kc * 2 + nh) * (W_HALF / sizeof(__half));
+            for (int n = 0; n < NH; n++)
+                for (int u = 0; u < 8; u++)
+                    for (int e = 0; e < 8; e++) {
+                        const int k = kc * KC + 8 * u + e, o = nh * NH + n;
+                        blk[(size_t)n * 64 + ((u ^ (n & 7)) << 3) + e] = __float2half_rn(w_in_out_host[(size_t)k * FC + o]);
+                    }
+        }
+    return 0;
+}
+
 extern "C" size_t mccnn_fc_head_workspace_bytes(int H, int W) {
     if (H < 1 || W < 1) return 0;
     return 2 * a256((size_t)H * W * FC * sizeof(__half));
@@ -498,11 +521,11 @@ extern "C" int mccnn_cost_volume_accurate(const float* fl, const float* fr, cons
                                           void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MCCNN_REQUIRE(fl && fr && w && CL && workspace, MCCNN_EINVAL, "mccnn_cost_volume_accurate: null argument");
-    MCCNN_REQUIRE(w->w1_left && w->w1_right && w->b1 && w->w2t_f16 && w->b2 && w->w3t_f16 && w->b3 && w->w4, MCCNN_EINVAL,
+    MCCNN_REQUIRE(w->w1_left && w->w1_right && w->b1 && w->w2_blocks_f16 && w->b2 && w->w3_blocks_f16 && w->b3 && w->w4, MCCNN_EINVAL,
                   "mccnn_cost_volume_accurate: null weight pointer");
     MCCNN_REQUIRE(H >= 1 && W >= 1 && D >= 1 && D <= 4096, MCCNN_EINVAL, "mccnn_cost_volume_accurate: bad shape H=%d W=%d D=%d", H, W, D);
     MCCNN_REQUIRE((long long)H * W + TM < 0x7fffffffLL, MCCNN_EINVAL, "mccnn_cost_volume_accurate: image too large for 32-bit tile rows");
-    MCCNN_REQUIRE(aligned16(fl) && aligned16(fr) && aligned16(w->w2t_f16) && aligned16(w->w3t_f16) && aligned16(w->b2) &&
+    MCCNN_REQUIRE(aligned16(fl) && aligned16(fr) && aligned16(w->w2_blocks_f16) && aligned16(w->w3_blocks_f16) && aligned16(w->b2) &&
                       aligned16(w->b3) && aligned16(w->w4) && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
                   MCCNN_EALIGN, "mccnn_cost_volume_accurate: features / weights must be 16-byte, the workspace 256-byte aligned");
     MCCNN_REQUIRE(workspace_bytes >= mccnn_fc_head_workspace_bytes(H, W), MCCNN_EWORKSPACE,
@@ -521,12 +544,12 @@ extern "C" int mccnn_cost_volume_accurate(const float* fl, const float* fr, cons
     fc_fill_kernel<<<(unsigned)((P + 7) / 8), 256, 0, stream>>>(CL, CR, W, D, Dp, P, fill);
     MCCNN_LAUNCH_CHECK("fc_fill_kernel");
 
-    CUtensorMap tmA, tmW2, tmW3;
+    CUtensorMap tmA;
     if (int e = make_map(&tmA, A1, (size_t)P, TM)) return e;
-    if (int e = make_map(&tmW2, w->w2t_f16, FC, NH)) return e;
-    if (int e = make_map(&tmW3, w->w3t_f16, FC, NH)) return e;
     FcArgs a{};
     a.B1 = B1;
+    a.w2b = reinterpret_cast<const unsigned char*>(w->w2_blocks_f16);
+    a.w3b = reinterpret_cast<const unsigned char*>(w->w3_blocks_f16);
     a.b2 = w->b2; a.b3 = w->b3; a.w4 = w->w4; a.b4 = w->b4;
     a.CL = CL; a.CR = CR;
     a.H = H; a.W = W; a.D = D; a.Dp = Dp;
@@ -535,7 +558,7 @@ extern "C" int mccnn_cost_volume_accurate(const float* fl, const float* fr, cons
     MCCNN_CUDA(cudaFuncSetAttribute(fc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
     long long grid = sm_count();
     if (grid > a.nitems) grid = a.nitems;
-    fc_head_kernel<<<(unsigned)grid, FC_THREADS, FC_SMEM, stream>>>(tmA, tmW2, tmW3, a);
+    fc_head_kernel<<<(unsigned)grid, FC_THREADS, FC_SMEM, stream>>>(tmA, a);
     MCCNN_LAUNCH_CHECK("fc_head_kernel");
     return 0;
 }

@@ -135,7 +135,8 @@ def cost_volume_tc(fl: torch.Tensor, fr: torch.Tensor, D: int, fill: float = 1.0
 
 class FcHeadWeights:
     """Device copy of the MC-CNN-accurate head's weights in the layout mccnn_cost_volume_accurate wants
-    (fc1 split per image, fc2 / fc3 transposed to fp16 [out][in]); keeps the tensors alive for the ctypes struct."""
+    (fc1 split per image, fc2 / fc3 as the pre-swizzled fp16 blocks of mccnn_pack_fc_matrix_host); keeps the tensors alive
+    for the ctypes struct."""
 
     def __init__(self, weights: dict):
         _require_cuda()
@@ -151,12 +152,20 @@ class FcHeadWeights:
                 or w4.reshape(-1).shape != (FC_UNITS,):
             raise ValueError(f"head must be fc1 [{2 * FEATURES},{FC_UNITS}], fc2/fc3 [{FC_UNITS},{FC_UNITS}], fc4 [{FC_UNITS},1]")
         dev = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt).contiguous()
+        lib = _lib.load()
+
+        def blocks(w):  # [384 in][384 out] fp32 -> the kernel's pre-swizzled fp16 blocks (one definition of the layout: the C side)
+            src = np.ascontiguousarray(w, dtype=np.float32)
+            out = np.empty(lib.mccnn_fc_matrix_blocks_bytes(), np.uint8)
+            _lib.check(lib.mccnn_pack_fc_matrix_host(src.ctypes.data, out.ctypes.data), "mccnn_pack_fc_matrix_host")
+            return torch.from_numpy(out).cuda()
+
         self.t = dict(w1_left=dev(w1[:FEATURES]), w1_right=dev(w1[FEATURES:]), b1=dev(get("fc1/biases")),
-                      w2t=dev(w2.T, torch.float16), b2=dev(get("fc2/biases")), w3t=dev(w3.T, torch.float16),
+                      w2b=blocks(w2), b2=dev(get("fc2/biases")), w3b=blocks(w3),
                       b3=dev(get("fc3/biases")), w4=dev(w4.reshape(-1)))
         t = self.t
-        self.c = _lib.FcWeights(t["w1_left"].data_ptr(), t["w1_right"].data_ptr(), t["b1"].data_ptr(), t["w2t"].data_ptr(),
-                                t["b2"].data_ptr(), t["w3t"].data_ptr(), t["b3"].data_ptr(), t["w4"].data_ptr(),
+        self.c = _lib.FcWeights(t["w1_left"].data_ptr(), t["w1_right"].data_ptr(), t["b1"].data_ptr(), t["w2b"].data_ptr(),
+                                t["b2"].data_ptr(), t["w3b"].data_ptr(), t["b3"].data_ptr(), t["w4"].data_ptr(),
                                 float(get("fc4/biases").reshape(-1)[0]))
 
 
