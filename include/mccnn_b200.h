@@ -268,6 +268,22 @@ int mccnn_match_pair_accurate(const uint8_t* imageL, const uint8_t* imageR, cons
                               size_t workspace_bytes, int H, int W, int D, int num_layers, const mccnn_sgm_params* params,
                               int mode, float* stage_ms_host, void* stream);
 
+/* ---- training step of the siamese tower ------------------------------------------------------------
+ * Replaces the graph train.py builds (train.py:71-99) and runs once per batch: three weight-sharing branches
+ * Net(num_of_conv_layers = L, 64 maps) on [B][p][p] patches with p = 2 L + 1 (mc_cnn_brunch.py:31-48), cosine similarities of
+ * the left feature with the positive / negative right feature, loss = mean(max(0, margin - cos_pos + cos_neg)) (:83-89),
+ * tf.train.MomentumOptimizer: accum = momentum * accum + grad; var -= lr * accum (:97-99). TensorFlow's arithmetic is not
+ * pinned: results are held to a tolerance against oracle/train_step.py (fp64 autograd).
+ *  params / velocity / grads_out: flat fp32 vectors of mccnn_train_param_count(L) floats, per layer i the HWIO weights
+ *      [3][3][cin][64] (conv{i}/weights) followed by the 64 biases (conv{i}/biases); cin = 1 for the first layer
+ *  left / right_pos / right_neg: fp32 [B][p][p] device patches; loss_out: one device float
+ *  grads_out may be NULL; apply_update = 0 computes loss and gradients only (params, velocity untouched). */
+size_t mccnn_train_param_count(int num_layers);
+size_t mccnn_train_workspace_bytes(int batch, int patch, int num_layers);
+int mccnn_train_step(const float* left, const float* right_pos, const float* right_neg, float* params, float* velocity,
+                     float* grads_out, float* loss_out, void* workspace, size_t workspace_bytes, int batch, int patch,
+                     int num_layers, float margin, float lr, float momentum, int apply_update, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

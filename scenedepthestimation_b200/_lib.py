@@ -76,6 +76,9 @@ SIGNATURES = {
     "mccnn_disparity_pipeline": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _PP, _i, _vp, _vp]),
     "mccnn_match_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mccnn_match_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _PP, _i, _vp, _vp]),
+    "mccnn_train_param_count": (_sz, [_i]),
+    "mccnn_train_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mccnn_train_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _f, _f, _i, _vp]),
     "mccnn_match_accurate_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mccnn_match_pair_accurate": (_i, [_vp, _vp, _vp, C.POINTER(FcWeights), _vp, _vp, _vp, _sz, _i, _i, _i, _i, _PP, _i, _vp, _vp]),
 }

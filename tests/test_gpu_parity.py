@@ -622,3 +622,37 @@ def test_accurate_pipeline_end_to_end(eng):
     exp = st.median5(st.lrc_fill(wl, fll), wl)
     assert np.array_equal(dl, exp) and np.array_equal(dr, wr)
     assert len(np.unique(dl)) > 4
+
+
+@pytest.mark.parametrize("B,L", [(16, 5), (128, 5), (7, 2)])
+def test_train_step_vs_autograd_oracle(eng, B, L):
+    """One training step of the siamese tower (train.py:71-99) through mccnn_train_step against oracle/train_step.py (fp64 torch
+    autograd; TensorFlow's own arithmetic is not pinned): loss to 1e-6, every gradient to 1e-4 in relative Frobenius norm (1e-3 of the layer's largest entry per element),
+    and the momentum update of weights and accumulators over two steps."""
+    from oracle import train_step as ot
+    from scenedepthestimation_b200 import synthetic as syn
+    from scenedepthestimation_b200 import train as tr
+
+    w = syn.glorot_weights(L)
+    left, pos, neg = tr.synthetic_patches(B, 2 * L + 1, seed=3 + B)
+    t = tr.Trainer(w, L, margin=0.3, learning_rate=0.01, beta=0.9)
+    loss = t.step(left, pos, neg, update=False)
+    eloss, eg = ot.loss_and_grads(w, left, pos, neg, 0.3, L)
+    assert 0.0 < eloss and abs(loss - eloss) <= 1e-6 + 1e-5 * eloss
+    g = t.grads_dict()
+    for k in eg:
+        scale = np.abs(eg[k]).max()
+        # fp32 kernels against fp64 autograd: rounding of the sums (up to 31k terms) plus, rarely, one activation whose
+        # pre-activation is within 1e-7 of zero and takes the other side of the ReLU (measured: 1e-6 absolute once in 2M)
+        assert scale > 0 and np.abs(g[k] - eg[k]).max() <= 1e-3 * scale, k
+        assert np.linalg.norm((g[k] - eg[k]).ravel()) <= 1e-4 * np.linalg.norm(eg[k].ravel()), k
+    assert all(np.array_equal(a, np.asarray(w[k], np.float32)) for k, a in t.weights_dict().items())  # update=False leaves them
+    # two real steps: weights follow tf.train.MomentumOptimizer
+    ew, ev = {k: np.asarray(v, np.float64) for k, v in w.items()}, {k: np.zeros_like(v, dtype=np.float64) for k, v in w.items()}
+    for s in range(2):
+        l2, p2, n2 = tr.synthetic_patches(B, 2 * L + 1, seed=50 + s)
+        t.step(l2, p2, n2)
+        _, eg2 = ot.loss_and_grads(ew, l2, p2, n2, 0.3, L)
+        ew, ev = ot.momentum_update(ew, ev, eg2, 0.01, 0.9)
+    for k, a in t.weights_dict().items():
+        assert np.abs(a - ew[k]).max() <= 1e-6 + 1e-5 * np.abs(ew[k]).max(), k

@@ -146,3 +146,30 @@ def test_accurate_head_oracle_self_consistency():
     c16, _ = fh.head_cost_volume(fl, fr, w, D, emulate_fp16=True)
     c32, _ = fh.head_cost_volume(fl, fr, w, D)
     assert np.abs(c16 - c32).max() < 2e-3 and np.abs(c32 - cl).max() < 1e-5
+
+
+def test_train_step_oracle_gradients_by_finite_differences():
+    """oracle/train_step.py (the training graph of train.py:71-99 in fp64 autograd): gradients agree with central finite
+    differences of its own loss, and the momentum rule is tf.train.MomentumOptimizer's (accum = beta * accum + grad)."""
+    from oracle import train_step as ot
+    from scenedepthestimation_b200 import synthetic as syn
+
+    rng = np.random.default_rng(0)
+    L = 2
+    w = {k: np.asarray(v, np.float64) for k, v in syn.glorot_weights(L).items()}
+    left = rng.standard_normal((6, 5, 5))
+    pos = left + 0.2 * rng.standard_normal(left.shape)
+    neg = rng.standard_normal(left.shape)
+    loss, g = ot.loss_and_grads(w, left, pos, neg, 0.3, L)
+    assert loss > 0
+    for k, idx in (("conv1/weights:0", (0, 1, 0, 5)), ("conv2/weights:0", (2, 1, 7, 3)), ("conv2/biases:0", (11,)), ("conv1/biases:0", (40,))):
+        eps = 1e-6
+        wp, wm = {a: b.copy() for a, b in w.items()}, {a: b.copy() for a, b in w.items()}
+        wp[k][idx] += eps
+        wm[k][idx] -= eps
+        fd = (ot.loss_and_grads(wp, left, pos, neg, 0.3, L)[0] - ot.loss_and_grads(wm, left, pos, neg, 0.3, L)[0]) / (2 * eps)
+        assert abs(fd - g[k][idx]) <= 1e-6 + 1e-4 * abs(fd), (k, fd, g[k][idx])
+    v0 = {k: np.ones_like(b) for k, b in w.items()}
+    nw, nv = ot.momentum_update(w, v0, g, 0.1, 0.9)
+    k = "conv2/weights:0"
+    assert np.allclose(nv[k], 0.9 + g[k]) and np.allclose(nw[k], w[k] - 0.1 * (0.9 + g[k]))
