@@ -146,8 +146,27 @@ def cpu_sample(il, ir, weights, D, target_s, threads, head=None):
 
 
 # ----------------------------------------------------------------------------------------- main
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line: libraries write banners to fd 1 (NCCL prints its version there whatever
+    NCCL_DEBUG_FILE says), so fd 1 is pointed at stderr for the whole run and the line goes to a duplicate of the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: str):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
     a = parse()
+    claim_stdout()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -187,7 +206,7 @@ def main():
         tot = float(np.sum(ts))
         v = (rows / H) * a.steps / tot
         sample = f"each step = {rows} of {H} rows x {W} px x {D} disparities (whole hot path), scaled to pairs"
-        print(json.dumps({
+        emit(json.dumps({
             "impl": "reference", "metric": "pairs_per_sec", "value": v, "unit": "pairs/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -405,7 +424,7 @@ def main():
         cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc}
 
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(3, a.warmup), "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if head is None else "f16 x f16 -> f32 (head), f64 (SGM state)", "data": "synthetic", "config": config,
