@@ -656,3 +656,43 @@ def test_train_step_vs_autograd_oracle(eng, B, L):
         ew, ev = ot.momentum_update(ew, ev, eg2, 0.01, 0.9)
     for k, a in t.weights_dict().items():
         assert np.abs(a - ew[k]).max() <= 1e-6 + 1e-5 * np.abs(ew[k]).max(), k
+
+
+@pytest.mark.parametrize("H,W,D", [(1, 5, 1), (1, 1, 3), (2, 129, 200), (3, 7, 7)])
+def test_accurate_head_edge_shapes(eng, H, W, D):
+    """Degenerate shapes of the decision head: one pixel, one disparity, D > W (most disparities have no match), a row that
+    ends one pixel into a second 128-pixel tile."""
+    from oracle import fc_head as fh
+    from scenedepthestimation_b200 import synthetic as syn
+
+    fl, fr = syn.unit_features(H, W, 64, 77 + W)
+    w = syn.glorot_fc_weights(seed=2, gain=2.5)
+    CL, CR = eng.cost_volume_accurate(dev(fl), dev(fr), eng.FcHeadWeights(w), D)
+    el, er = fh.head_cost_volume(fl, fr, w, D, emulate_fp16=True)
+    assert np.abs(unpitch(CL, D) - el).max() <= 5e-4 and np.abs(unpitch(CR, D) - er).max() <= 5e-4
+
+
+def test_entry_points_reject_bad_arguments(eng):
+    """The new entry points fail loudly (negative status + message), never silently: wrong head shapes, a patch size that does
+    not reduce to one pixel, a workspace that is too small."""
+    import ctypes as C
+
+    from scenedepthestimation_b200 import _lib, synthetic as syn
+    from scenedepthestimation_b200 import train as tr
+
+    lib = _lib.load()
+    bad = syn.glorot_fc_weights()
+    bad["fc2/weights:0"] = bad["fc2/weights:0"][:, :100]
+    with pytest.raises(ValueError):
+        eng.FcHeadWeights(bad)
+    fl = torch.zeros((2, 8, 64), device="cuda")
+    head = eng.FcHeadWeights(syn.glorot_fc_weights())
+    CL = torch.empty((2, 8, 4), device="cuda")
+    ws = torch.empty(256, dtype=torch.uint8, device="cuda")
+    rc = lib.mccnn_cost_volume_accurate(fl.data_ptr(), fl.data_ptr(), C.byref(head.c), CL.data_ptr(), None, ws.data_ptr(), 256, 2, 8, 4, 1.0, None)
+    assert rc == -3 and b"workspace" in lib.mccnn_last_error()
+    assert lib.mccnn_train_workspace_bytes(8, 12, 5) == 0  # patch must be 2 * layers + 1
+    t = tr.Trainer(None, 2)
+    with pytest.raises(ValueError):
+        t.step(np.zeros((4, 5, 5)), np.zeros((3, 5, 5)), np.zeros((4, 5, 5)))
+    assert t.step(*tr.synthetic_patches(1, 5, 0)) >= 0.0  # a batch of one
