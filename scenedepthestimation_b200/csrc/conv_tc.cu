@@ -18,12 +18,13 @@
 //
 // Precision: the reference runs fp32 convolutions. Every operand is split into two fp16 numbers,
 // x = hi + lo / 2048 (22-bit significand, lo scaled so that it cannot underflow), and each k-step
-// issues three MMAs: hi*hi into one fp32 TMEM accumulator, hi*lo and lo*hi into a second one; the
-// epilogue forms main + corr / 2048. The dropped lo*lo term is 2^-22 relative. Activations travel
+// issues three MMAs: hi*hi, hi*lo and lo*hi into three fp32 TMEM accumulators; the
+// epilogue forms main + (corr1 + corr2) / 2048. The dropped lo*lo term is 2^-22 relative. Activations travel
 // between layers as two fp16 NHWC tensors (same bytes as fp32).
 //
-// Warp roles (192 threads, one CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM
-// allocator, warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/split or l2-normalise -> global).
+// Warp roles (320 threads, one CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM
+// allocator, warps 2..9 = epilogue (TMEM lane quarter x channel half: TMEM -> registers -> bias/ReLU/split or
+// l2-normalise -> global; with four epilogue warps the epilogue, not the MMAs, set the pace of a tile).
 // Two smem stages for A, two TMEM accumulator sets so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include <cuda.h>
@@ -43,10 +44,13 @@ constexpr int TC_STAGES = 2;
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES;  // hi + lo
 constexpr int SMEM_A_OFF = W_TC_BYTES;         // 147456, a multiple of 1024
 constexpr int SMEM_BAR_OFF = SMEM_A_OFF + TC_STAGES * STAGE_BYTES;
-constexpr int TC_SMEM_BYTES = SMEM_BAR_OFF + 128 + 1024;  // + barriers + alignment slack
-constexpr int TC_THREADS = 192;
-constexpr uint32_t TMEM_COLS = 256;
+constexpr int SMEM_SS_OFF = SMEM_BAR_OFF + 128;       // l2-normalise: partial sums of squares of the two channel halves, [2 parities][2][128]
+constexpr int TC_SMEM_BYTES = SMEM_SS_OFF + 2 * 2 * TILE_M * 4 + 1024;  // + alignment slack
+constexpr int TC_EPI_WARPS = 8;             // epilogue warps: TMEM lane quarter x channel half (the epilogue, not the MMAs, bounded the tile: ncu)
+constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);
+constexpr uint32_t TMEM_COLS = 512;  // 2 accumulator sets x 3 accumulators x 64 columns = 384, rounded up to a power of two
 constexpr uint32_t IDESC_F16_M128_N64 = (1u << 4) | ((uint32_t)(NF >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | ((uint32_t)(2 * NF >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -71,18 +75,28 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr, uint32_t base
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)(base_offset & 7u) << 49) | ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+// Issued from WARP-CONVERGENT code: every lane runs the instruction stream, elect.sync picks the one lane that issues.
+// (Inside an `if (lane == 0)` region the compiler wraps every uniform-datapath instruction in an ELECT / BRA.U.ANY loop:
+// ~75 cycles per MMA, twice the 37 cycles an M128 N64 K16 MMA takes: the issue, not the pipe, set the pace.)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
+        ".reg .pred p, q;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(IDESC_F16_M128_N64), "r"(accumulate)
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
@@ -166,7 +180,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
         mbar_init(wbar, 1);
         mbar_fence_init();
     }
@@ -185,7 +199,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         // ===== TMA producer
         if (lane == 0) {
             mbar_expect_tx(wbar, W_TC_BYTES);
-            for (int i = 0; i < W_TC_BYTES / 16384; i++) bulk_g2s_addr(base + i * 16384, a.w_tc + (size_t)i * 16384, 16384, wbar);
+            // per tap the hi tile and the lo tile side by side: [64 cout hi][64 cout lo] is ONE N = 128 B operand
+            for (int tap = 0; tap < 9; tap++) {
+                bulk_g2s_addr(base + tap * 2 * B_TILE_BYTES, a.w_tc + (size_t)tap * B_TILE_BYTES, B_TILE_BYTES, wbar);
+                bulk_g2s_addr(base + tap * 2 * B_TILE_BYTES + B_TILE_BYTES, a.w_tc + (size_t)(9 + tap) * B_TILE_BYTES, B_TILE_BYTES, wbar);
+            }
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 const int y = tile / a.tiles_per_row, x0 = (tile % a.tiles_per_row) * TILE_M;
@@ -201,15 +219,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread)
-        if (lane == 0) {
+        // ===== MMA issuer: the whole warp runs the loop (convergent), one elected lane issues
+        {
             mbar_wait(wbar, 0);
             uint32_t it = 0, tc = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tc++) {
                 const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
                 mbar_wait(&tempty[acc], aph ^ 1u);
                 tc_fence_after();
-                const uint32_t d_main = tmem_base + acc * 128u, d_corr = d_main + 64u;
+                // three accumulators per tile (hi*hi, hi*lo, lo*hi): consecutive MMAs never target the same TMEM columns, so the
+                // tensor pipe does not wait for an accumulate to land (with hi*lo and lo*hi in ONE accumulator the pipe was busy
+                // 49 % of the time although neither loads nor the epilogue held the MMA warp back: ncu)
+                const uint32_t d_main = tmem_base + acc * 192u, d_c2 = d_main + 128u;
                 for (int ky = 0; ky < 3; ky++, it++) {
                     const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
                     mbar_wait(&full[s], ph);
@@ -221,14 +242,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                         // same window, start shifted by kx pixels (= kx 128-byte rows)
                         const uint64_t a_hi = sw128_desc(a_addr + kx * 128);
                         const uint64_t a_lo = sw128_desc(a_addr + A_TILE_BYTES + kx * 128);
-                        const uint64_t b_hi = sw128_desc(base + tap * B_TILE_BYTES);
-                        const uint64_t b_lo = sw128_desc(base + 9 * B_TILE_BYTES + tap * B_TILE_BYTES);
+                        const uint64_t b_hilo = sw128_desc(base + tap * 2 * B_TILE_BYTES);  // rows 0..63 hi, 64..127 lo
 #pragma unroll
                         for (int k = 0; k < 4; k++) {  // UMMA_K = 16 fp16 = 32 bytes = 2 descriptor units
                             const uint32_t first = (tap | k) != 0 ? 1u : 0u;
-                            umma_f16(d_main, a_hi + 2 * k, b_hi + 2 * k, first);
-                            umma_f16(d_corr, a_hi + 2 * k, b_lo + 2 * k, first);
-                            umma_f16(d_corr, a_lo + 2 * k, b_hi + 2 * k, 1u);
+                            // a_hi x [b_hi | b_lo] -> columns 0..63 = hi*hi (main), 64..127 = hi*lo; a_lo x b_hi -> third accumulator
+                            umma_f16(d_main, a_hi + 2 * k, b_hilo + 2 * k, first, IDESC_F16_M128_N128);
+                            umma_f16(d_c2, a_lo + 2 * k, b_hilo + 2 * k, first, IDESC_F16_M128_N64);
                         }
                     }
                     umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
@@ -237,52 +257,66 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             }
         }
     } else {
-        // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
-        const int q = warp & 3;
+        // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; two warps per lane quarter, 32 output channels each
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const int m = q * 32 + lane;
+        constexpr int CH = NF / 2;
+        float bias[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) bias[j] = __ldg(&a.bias[CH * half + j]);
+        float* ssbuf = reinterpret_cast<float*>(sm + SMEM_SS_OFF);
         uint32_t tc = 0;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tc++) {
             const uint32_t acc = tc & 1u, aph = (tc >> 1) & 1u;
             const int y = tile / a.tiles_per_row, x0 = (tile % a.tiles_per_row) * TILE_M;
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128u;
-            float v[NF];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 192u + CH * half;
+            float v[CH];
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                float mn[16], cr[16];
+            for (int c = 0; c < CH / 16; c++) {
+                float mn[16], c1[16], c2[16];
                 tmem_ld16(taddr + c * 16, mn);
-                tmem_ld16(taddr + 64 + c * 16, cr);
+                tmem_ld16(taddr + 64 + c * 16, c1);
+                tmem_ld16(taddr + 128 + c * 16, c2);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; j++) v[c * 16 + j] = fmaf(cr[j], 1.0f / 2048.0f, mn[j]);
+                for (int j = 0; j < 16; j++) v[c * 16 + j] = fmaf(c1[j] + c2[j], 1.0f / 2048.0f, mn[j]);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
 
             const int x = x0 + m;
-            if (x < Wout) {
-                const size_t o = ((size_t)y * Wout + x) * NF;
-                if (!LAST) {
+            const size_t o = ((size_t)y * Wout + min(x, Wout - 1)) * NF + CH * half;
+            if (!LAST) {
+                if (x < Wout) {
 #pragma unroll
-                    for (int c8 = 0; c8 < NF / 8; c8++) {
+                    for (int c8 = 0; c8 < CH / 8; c8++) {
                         __align__(16) __half hi[8], lo[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) split_store(fmaxf(v[c8 * 8 + j] + __ldg(&a.bias[c8 * 8 + j]), 0.f), hi[j], lo[j]);
+                        for (int j = 0; j < 8; j++) split_store(fmaxf(v[c8 * 8 + j] + bias[c8 * 8 + j], 0.f), hi[j], lo[j]);
                         *reinterpret_cast<uint4*>(&a.out_hi[o + c8 * 8]) = *reinterpret_cast<const uint4*>(hi);
                         *reinterpret_cast<uint4*>(&a.out_lo[o + c8 * 8]) = *reinterpret_cast<const uint4*>(lo);
                     }
-                } else {
-                    float ss = 0.f;
+                }
+            } else {
+                // l2-normalise over all 64 channels: the two halves exchange their sums of squares (double-buffered by
+                // tile parity: a warp is at most one barrier ahead of the slowest one)
+                float ss = 0.f;
 #pragma unroll
-                    for (int j = 0; j < NF; j++) {
-                        v[j] += __ldg(&a.bias[j]);
-                        ss = fmaf(v[j], v[j], ss);
-                    }
-                    const float s = 1.0f / sqrtf(fmaxf(ss, 1e-12f));
+                for (int j = 0; j < CH; j++) {
+                    v[j] += bias[j];
+                    ss = fmaf(v[j], v[j], ss);
+                }
+                float* sb = ssbuf + (tc & 1u) * 2 * TILE_M;
+                sb[half * TILE_M + m] = ss;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+                const float tot = sb[m] + sb[TILE_M + m];  // same order in both halves: identical scale
+                const float s = 1.0f / sqrtf(fmaxf(tot, 1e-12f));
+                if (x < Wout) {
 #pragma unroll
-                    for (int c4 = 0; c4 < NF / 4; c4++)
+                    for (int c4 = 0; c4 < CH / 4; c4++)
                         *reinterpret_cast<float4*>(&a.out_f32[o + c4 * 4]) =
                             make_float4(v[c4 * 4] * s, v[c4 * 4 + 1] * s, v[c4 * 4 + 2] * s, v[c4 * 4 + 3] * s);
                 }
