@@ -69,6 +69,29 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// The same two operations issued from WARP-CONVERGENT code: every lane executes the instruction, elect.sync picks the lane that
+// issues it. Inside an `if (lane == 0)` region the compiler wraps each uniform-datapath instruction (UBLKCP, UTCHMMA, ...) in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop, about ten dependent instructions per copy on the issuing warp's critical path.
+__device__ __forceinline__ void mbar_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(bytes)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_elect(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
+        "}" ::"r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
 // 1-D bulk copy shared -> global.
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),

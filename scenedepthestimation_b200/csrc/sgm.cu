@@ -252,9 +252,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             const size_t off = ((size_t)(lrow - a.row0) * a.W + lcol) * pix_stride;
             const int st = g % STAGES;
             float* dst = inbuf + (size_t)st * IN_BUFS * ROW;
-            mbar_expect_tx(&bars[st], copy_bytes * IN_BUFS);
-            bulk_g2s(dst, Cv + off, copy_bytes, &bars[st]);
-            if constexpr (kReadS) bulk_g2s(dst + ROW, Sv + off, copy_bytes, &bars[st]);
+            // called by the whole warp (convergent); one elected lane issues (see common.cuh)
+            mbar_expect_tx_elect(&bars[st], copy_bytes * IN_BUFS);
+            bulk_g2s_elect(dst, Cv + off, copy_bytes, &bars[st]);
+            if constexpr (kReadS) bulk_g2s_elect(dst + ROW, Sv + off, copy_bytes, &bars[st]);
         };
         auto image_at = [&](int t) -> int {
             int row, col;
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
         {
             const int pre = min(STAGES, t_end - t_begin);
             for (int k = 0; k < pre; k++) {
-                if (lane == 0) issue_load(gstep + k);
+                issue_load(gstep + k);
                 scan_advance(a, lrow, lcol);
             }
         }
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             // every lane's results (which depend on all of its cf/sf loads) are stored or reduced: refill the stage
             __syncwarp();
             if (t + STAGES < t_end) {
-                if (lane == 0) issue_load(gstep + STAGES);
+                issue_load(gstep + STAGES);
                 scan_advance(a, lrow, lcol);
             }
             gstep++;
