@@ -92,6 +92,27 @@ __device__ __forceinline__ void bulk_g2s_elect(void* smem_dst, const void* gmem_
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void bulk_s2g_commit_elect(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\t"
+        "@q cp.async.bulk.commit_group;\n\t"
+        "}" ::"l"(gmem_dst),
+        "r"(smem_u32(smem_src)), "r"(bytes)
+        : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read_elect() {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.wait_group.read %0;\n\t"
+        "}" ::"n"(N)
+        : "memory");
+}
 // 1-D bulk copy shared -> global.
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),

@@ -380,15 +380,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
                 }
             } else if constexpr (STORE) {
                 float* ob = outbuf + (OUTB > 1 ? (ostep % OUTB) * ROW : 0);
-                if (lane == 0) bulk_wait_read<OUTB - 1>();  // the store issued OUTB steps ago has left its staging row
+                // bulk-group bookkeeping is per thread: elect.sync names the same lane every time (full mask), and the warp stays
+                // convergent, so the copy is not wrapped in an ELECT / BRA.U.ANY loop (common.cuh)
+                bulk_wait_read_elect<OUTB - 1>();  // the store issued OUTB steps ago has left its staging row
                 __syncwarp();
                 store_chunk<NPL>(ob, lane, so);
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
-                    bulk_s2g(Sv + ((size_t)(row - a.row0) * a.W + col) * pix_stride, ob, copy_bytes);
-                    bulk_commit();
-                }
+                bulk_s2g_commit_elect(Sv + ((size_t)(row - a.row0) * a.W + col) * pix_stride, ob, copy_bytes);
                 ostep++;
             }
 
@@ -457,7 +456,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             if (lane == 0) st_release_sys(a.flag_out + slot, a.epoch);
         }
     }
-    if (lane == 0) bulk_wait_all<0>();
+    // drained by the lane elect.sync names (the one that committed the groups)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.wait_group 0;\n\t"
+        "}" ::: "memory");
 }
 
 template <int NPL, int STAGES, int MODE, int OUTB>
