@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCCNN_ABI_VERSION 3
+#define MCCNN_ABI_VERSION 4
 #define MCCNN_FEATURES 64 /* num_of_feature_maps: hard-coded 64 in the reference (process_functional.py:128) */
 
 enum {
@@ -196,12 +196,23 @@ typedef struct {
     void* xchg_prev;
     void* xchg_next;
     unsigned epoch;
+    /* Robustness (a rank that dies, fails its argument check or never launches must not wedge the other GPUs):
+     *  go_flag   : NULL, or a device int every rank agrees on before its launch (e.g. an all-reduced MIN of "my arguments are
+     *              fine and I will launch"); the scan kernels return at once when it is 0;
+     *  timeout_ms: a scanline waits at most this long for its neighbour's hand-over (0 = 2000 ms), then the launch gives
+     *              up everywhere on this rank and mccnn_sgm_shard_status reports it. */
+    const int* go_flag;
+    unsigned timeout_ms;
 } mccnn_shard;
 size_t mccnn_sgm_shard_exchange_bytes(int W);
 int mccnn_sgm_sharded(const float* CLb, const float* CRb, const uint8_t* imageL, const uint8_t* imageR,
                       float* SLb, float* SRb, float* dispLb, float* dispRb, void* workspace, size_t workspace_bytes,
                       int W, int D, const mccnn_sgm_params* params, int mode, int keep_volumes,
                       const mccnn_shard* shard, int pass_mask, void* stream);
+
+/* After mccnn_sgm_sharded: synchronises the stream and returns the launch's status word in *status_host
+ * (0 = every scanline got its hand-over; 1 = a wait hit the deadline, the outputs are invalid). */
+int mccnn_sgm_shard_status(const void* workspace, int* status_host, void* stream);
 
 /* One path kernel on one volume, S += path (launch-for-launch twin of :1166-1202; for tests).
  * path: 0..7 in the reference's launch order. */
@@ -238,6 +249,10 @@ int mccnn_wta_subpixel(const float* S, float* disp, int H, int W, int D, void* s
  * gt_half is the ground truth already resized and halved (fp32 [H][W]). */
 int mccnn_bad_pixels(const uint8_t* disp_u8, const float* gt_half, unsigned long long* counts2,
                      int H, int W, void* stream);
+/* The same count for the 16-bit maps written when the disparity range exceeds what the reference's uint8 PNG holds
+ * (match_single.py:55 wraps there). */
+int mccnn_bad_pixels_u16(const uint16_t* disp_u16, const float* gt_half, unsigned long long* counts2,
+                         int H, int W, void* stream);
 
 /* ---- whole path ----------------------------------------------------------------------------
  * disparity_compute_by_gpu (:1093-1267) from device-resident inputs: cost volume -> SGM -> WTA ->

@@ -20,7 +20,8 @@ class SgmParams(C.Structure):
 
 class Shard(C.Structure):
     _fields_ = [("rank", C.c_int), ("world", C.c_int), ("H_full", C.c_int), ("row0", C.c_int), ("rows", C.c_int),
-                ("xchg_local", C.c_void_p), ("xchg_prev", C.c_void_p), ("xchg_next", C.c_void_p), ("epoch", C.c_uint)]
+                ("xchg_local", C.c_void_p), ("xchg_prev", C.c_void_p), ("xchg_next", C.c_void_p), ("epoch", C.c_uint),
+                ("go_flag", C.c_void_p), ("timeout_ms", C.c_uint)]
 
 
 class FcWeights(C.Structure):
@@ -60,6 +61,7 @@ SIGNATURES = {
     "mccnn_sgm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _PP, _i, _i, _vp]),
     "mccnn_sgm_shard_exchange_bytes": (_sz, [_i]),
     "mccnn_sgm_sharded": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _PP, _i, _i, C.POINTER(Shard), _i, _vp]),
+    "mccnn_sgm_shard_status": (_i, [_vp, C.POINTER(_i), _vp]),
     "mccnn_sgm_single_path": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _PP, _i, _vp]),
     "mccnn_wta": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mccnn_wta_dhw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
@@ -72,6 +74,7 @@ SIGNATURES = {
     "mccnn_encode_u16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mccnn_wta_subpixel": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mccnn_bad_pixels": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "mccnn_bad_pixels_u16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "mccnn_pipeline_workspace_bytes": (_sz, [_i, _i, _i]),
     "mccnn_disparity_pipeline": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _PP, _i, _vp, _vp]),
     "mccnn_match_workspace_bytes": (_sz, [_i, _i, _i, _i]),

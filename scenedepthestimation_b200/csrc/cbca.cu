@@ -260,8 +260,8 @@ int launch_cbca(const float* vol_in, float* vol_out, float* tmp, const unsigned*
                 int Dp, int L1, cudaStream_t stream) {
     const size_t smr = (size_t)RING * CB_THREADS * sizeof(double);
     const size_t smc = smr + (size_t)RING * CB_THREADS * sizeof(unsigned);
-    MCCNN_CUDA(cudaFuncSetAttribute(cbca_row_kernel<RING, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-    MCCNN_CUDA(cudaFuncSetAttribute(cbca_col_kernel<RING, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+    if (int e = kernel_setup<cbca_row_kernel<RING, DIR>>(CB_THREADS, smr, nullptr)) return e;
+    if (int e = kernel_setup<cbca_col_kernel<RING, DIR>>(CB_THREADS, smc, nullptr)) return e;
     const long long nrow = (long long)H * Dp, ncol = (long long)W * Dp;
     cbca_row_kernel<RING, DIR><<<(unsigned)((nrow + CB_THREADS - 1) / CB_THREADS), CB_THREADS, smr, stream>>>(vol_in, tmp, aA, aB, H, W, D,
                                                                                                          Dp, L1);

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <mutex>
 #include "../../include/mccnn_b200.h"
 
 namespace mccnn {
@@ -35,6 +36,28 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline int disp_pitch(int D) { return (D + 3) & ~3; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 int sm_count();
+int current_device();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the occupancy query cost several microseconds each: done once per
+// (kernel instantiation, device, shared-memory size) instead of on every launch. Kern is a template ARGUMENT so that every
+// kernel owns its cache (kernels of one signature share a function-pointer type).
+template <auto Kern>
+inline int kernel_setup(int threads, size_t smem, int* blocks_per_sm) {
+    struct Slot { size_t smem; int per_sm; bool set; };
+    static Slot slots[64] = {};
+    static std::mutex mu;
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    Slot& s = slots[dev & 63];
+    if (!s.set || s.smem != smem) {
+        MCCNN_CUDA(cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        MCCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, Kern, threads, smem));
+        s.smem = smem; s.per_sm = per_sm; s.set = true;
+    }
+    if (blocks_per_sm) *blocks_per_sm = s.per_sm;
+    return 0;
+}
 
 // ------------------------------------------------------------------ PTX: mbarrier + bulk async copy
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

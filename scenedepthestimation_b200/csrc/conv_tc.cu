@@ -401,8 +401,8 @@ int conv_tower_tc(const float* padded, const float* w_fp32, const size_t* layer_
         MCCNN_LAUNCH_CHECK("conv1_split_kernel");
         Hin -= 2; Win -= 2;
     }
-    MCCNN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    MCCNN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    if (int e = kernel_setup<conv_tc_kernel<false>>(TC_THREADS, TC_SMEM_BYTES, nullptr)) return e;
+    if (int e = kernel_setup<conv_tc_kernel<true>>(TC_THREADS, TC_SMEM_BYTES, nullptr)) return e;
     int cur = 0;
     for (int l = 1; l < num_layers; l++) {
         const bool last = (l == num_layers - 1);

@@ -240,8 +240,8 @@ extern "C" int mccnn_conv_tower_fp32(const float* padded, const void* packed_wei
         Hin -= 2; Win -= 2;
     }
     const size_t smem = sizeof(ConvSmem);
-    MCCNN_CUDA(cudaFuncSetAttribute(conv64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MCCNN_CUDA(cudaFuncSetAttribute(conv64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int e = kernel_setup<conv64_kernel<false>>(256, smem, nullptr)) return e;
+    if (int e = kernel_setup<conv64_kernel<true>>(256, smem, nullptr)) return e;
     int cur = 0;
     for (int l = 1; l < num_layers; l++) {
         const float* w = wts + layer_offset_floats(l);

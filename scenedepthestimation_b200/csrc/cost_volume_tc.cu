@@ -657,7 +657,7 @@ extern "C" int mccnn_cost_volume_tc(const float* fl, const float* fr, float* CL,
     a.queue = queue;
     a.queue_count = queue_count;
     a.queue_cap = (unsigned)(queue_cap > 0xffffffffu ? 0xffffffffu : queue_cap);
-    MCCNN_CUDA(cudaFuncSetAttribute(cost_volume_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    if (int e = kernel_setup<cost_volume_tc_kernel>(CVT_THREADS, TC_SMEM, nullptr)) return e;
     int grid = sm_count();
     if (grid > a.nitems) grid = a.nitems;
     cost_volume_tc_kernel<<<grid, CVT_THREADS, TC_SMEM, stream>>>(tmSL, tmSR, tmFL, tmFR, a);

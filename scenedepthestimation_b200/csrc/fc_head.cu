@@ -555,7 +555,7 @@ extern "C" int mccnn_cost_volume_accurate(const float* fl, const float* fr, cons
     a.H = H; a.W = W; a.D = D; a.Dp = Dp;
     a.tiles_x = ceil_div(W, TM);
     a.nitems = (long long)H * a.tiles_x * D;
-    MCCNN_CUDA(cudaFuncSetAttribute(fc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
+    if (int e = kernel_setup<fc_head_kernel>(FC_THREADS, FC_SMEM, nullptr)) return e;
     long long grid = sm_count();
     if (grid > a.nitems) grid = a.nitems;
     fc_head_kernel<<<(unsigned)grid, FC_THREADS, FC_SMEM, stream>>>(tmA, a);

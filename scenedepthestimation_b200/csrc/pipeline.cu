@@ -59,16 +59,33 @@ MatchLayout match_layout(int H, int W, int D, int nl, bool accurate = false) {
     return l;
 }
 
+// Stage timing events: created once per host thread and device and kept (9 events; cudaEventCreate / Destroy on every timed
+// call cost more than a small-D SGM pass, and a failure half-way used to leak the ones already created).
 struct StageTimer {
-    cudaEvent_t ev[9];
+    cudaEvent_t* ev = nullptr;
     int n = 0;
     bool on = false;
     cudaStream_t s{};
     int begin(cudaStream_t stream, bool enable) {
         on = enable;
         s = stream;
+        n = 0;
         if (!on) return 0;
-        for (int i = 0; i < 9; i++) MCCNN_CUDA(cudaEventCreate(&ev[i]));
+        struct PerDevice { cudaEvent_t ev[9]; bool made; };
+        static thread_local PerDevice cache[64] = {};
+        PerDevice& c = cache[current_device() & 63];
+        if (!c.made) {
+            int made = 0;
+            cudaError_t err = cudaSuccess;
+            for (; made < 9 && err == cudaSuccess; made++) err = cudaEventCreate(&c.ev[made]);
+            if (err != cudaSuccess) {
+                for (int i = 0; i < made - 1; i++) cudaEventDestroy(c.ev[i]);
+                on = false;
+                return cuda_fail(err, "cudaEventCreate");
+            }
+            c.made = true;
+        }
+        ev = c.ev;
         return mark();
     }
     int mark() {
@@ -76,11 +93,7 @@ struct StageTimer {
         MCCNN_CUDA(cudaEventRecord(ev[n++], s));
         return 0;
     }
-    void destroy() {
-        if (on)
-            for (int i = 0; i < 9; i++) cudaEventDestroy(ev[i]);
-        on = false;
-    }
+    void destroy() { on = false; }   // the events stay cached for the next timed call of this thread
 };
 
 }  // namespace

@@ -253,7 +253,8 @@ __global__ void encode_u16_kernel(const float* __restrict__ disp, unsigned short
     out[i] = (unsigned short)(v <= 0.f ? 0.f : (v >= 65535.f ? 65535.f : v));
 }
 
-__global__ void bad_pixels_kernel(const unsigned char* __restrict__ disp, const float* __restrict__ gt,
+template <typename T>
+__global__ void bad_pixels_kernel(const T* __restrict__ disp, const float* __restrict__ gt,
                                   unsigned long long* __restrict__ counts, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int bad = 0, valid = 0;
@@ -382,7 +383,18 @@ extern "C" int mccnn_bad_pixels(const uint8_t* disp_u8, const float* gt_half, un
     if (int e = check_hw("mccnn_bad_pixels", H, W)) return e;
     MCCNN_CUDA(cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
     const size_t n = (size_t)H * W;
-    bad_pixels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(disp_u8, gt_half, counts2, n);
+    bad_pixels_kernel<unsigned char><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(disp_u8, gt_half, counts2, n);
+    MCCNN_LAUNCH_CHECK("bad_pixels_kernel");
+    return 0;
+}
+
+extern "C" int mccnn_bad_pixels_u16(const uint16_t* disp_u16, const float* gt_half, unsigned long long* counts2, int H, int W,
+                                    void* stream) {
+    MCCNN_REQUIRE(disp_u16 && gt_half && counts2, MCCNN_EINVAL, "mccnn_bad_pixels_u16: null argument");
+    if (int e = check_hw("mccnn_bad_pixels_u16", H, W)) return e;
+    MCCNN_CUDA(cudaMemsetAsync(counts2, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
+    const size_t n = (size_t)H * W;
+    bad_pixels_kernel<unsigned short><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(disp_u16, gt_half, counts2, n);
     MCCNN_LAUNCH_CHECK("bad_pixels_kernel");
     return 0;
 }

@@ -58,7 +58,16 @@ struct SgmArgs {
     double* hand_out;
     unsigned* flag_out;
     unsigned epoch;
+    // sharded runs only: `go` (may be null) is a device word every rank agrees on before the launch (an all-reduced
+    // "all ranks validated their arguments and will launch"); 0 = return at once. A scanline waits for its hand-over at
+    // most `timeout_ns`; a warp that gives up sets *status (the workspace word the host reads back) and every warp that
+    // sees it set leaves too, so a rank that died or never launched cannot wedge the other GPUs.
+    const int* go;
+    unsigned* status;
+    unsigned long long timeout_ns;
 };
+
+constexpr int STATUS_WORD = 32;  // index of the status word inside the 64-word SGM workspace (counters use 0..13)
 
 constexpr int HAND_STRIDE = 1024 + 8;  // doubles per (side, scanline) slot: state of up to 1024 disparities + min
 
@@ -133,6 +142,11 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ double warp_min_f64(double v) {
     long long k = dkey(v);
@@ -193,6 +207,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
     constexpr int OUT_BUFS = OUTB > 0 ? OUTB : 0;  // 0: S is not staged; n: ring of n staging rows (a bulk store takes ~1 us to drain)
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
+    if (a.go != nullptr && *reinterpret_cast<const volatile int*>(a.go) == 0) return;  // some rank will not launch: nobody waits
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int PER_WARP_FLOATS = ROW * (STAGES * IN_BUFS + OUT_BUFS);
     float* wbase = reinterpret_cast<float*>(smem_raw) + (size_t)warp * PER_WARP_FLOATS;
@@ -263,12 +278,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
             return (int)img[(size_t)row * a.W + col];
         };
 
-        {
-            const int pre = min(STAGES, t_end - t_begin);
-            for (int k = 0; k < pre; k++) {
-                issue_load(gstep + k);
-                scan_advance(a, lrow, lcol);
-            }
+        const int pre = min(STAGES, t_end - t_begin);
+        for (int k = 0; k < pre; k++) {
+            issue_load(gstep + k);
+            scan_advance(a, lrow, lcol);
         }
         // image values: lane l of blk_cur holds I[pixel tb + 1 + l]
         int i_cur = image_at(t_begin);
@@ -284,9 +297,28 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) sgm_scan_kernel(const SgmA
         if (t_begin > 0 && t_begin < a.nsteps_dp) {
             // resume a scanline started on another rank: wait for its state (fp64 L[], min over d)
             const size_t slot = (size_t)side * a.nlines + line;
-            if (lane == 0)
-                while (ld_acquire_sys(a.flag_in + slot) != a.epoch) __nanosleep(64);
-            __syncwarp();
+            int gave_up = 0;
+            if (lane == 0) {
+                const unsigned long long t0 = global_timer_ns();
+                unsigned spins = 0;
+                while (ld_acquire_sys(a.flag_in + slot) != a.epoch) {
+                    __nanosleep(64);
+                    if ((++spins & 63u) == 0) {  // every ~4 us: has another warp given up, or is the deadline over?
+                        if (*reinterpret_cast<volatile unsigned*>(a.status) != 0u) { gave_up = 1; break; }
+                        if (global_timer_ns() - t0 > a.timeout_ns) {
+                            atomicExch(a.status, 1u);
+                            gave_up = 1;
+                            break;
+                        }
+                    }
+                }
+            }
+            gave_up = __shfl_sync(0xffffffffu, gave_up, 0);
+            if (gave_up) {
+                // the prefetched rows are already on their way into this warp's ring: let them land, then leave the kernel
+                for (int k = 0; k < pre; k++) mbar_wait(&bars[(gstep + k) % STAGES], ((gstep + k) / STAGES) & 1u);
+                break;
+            }
             const double* src = a.hand_in + slot * HAND_STRIDE;
 #pragma unroll
             for (int j = 0; j < NPL; j++) L[j] = __ldcv(src + lane * NPL + j);
@@ -471,9 +503,8 @@ int launch_scan(const SgmArgs& a, cudaStream_t stream) {
     const size_t smem = (size_t)WARPS_PER_CTA * (32 * NPL * (STAGES * IN_BUFS + (OUTB > 0 ? OUTB : 0))) * sizeof(float) +
                         (size_t)WARPS_PER_CTA * STAGES * sizeof(uint64_t);
     auto kern = sgm_scan_kernel<NPL, STAGES, MODE, OUTB>;
-    MCCNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    MCCNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS_PER_CTA * 32, smem));
+    if (int e = kernel_setup<sgm_scan_kernel<NPL, STAGES, MODE, OUTB>>(WARPS_PER_CTA * 32, smem, &per_sm)) return e;
     MCCNN_REQUIRE(per_sm >= 1, MCCNN_EINVAL, "sgm_scan_kernel<%d>: does not fit on an SM (smem %zu)", NPL, smem);
     const int total_lines = a.nsides * a.nlines;
     int grid = sm_count() * per_sm;
@@ -574,6 +605,9 @@ static int run_sgm(const float* CL, const float* CR, const uint8_t* imageL, cons
     a.row0 = sh ? sh->row0 : 0;
     a.Hb = sh ? sh->rows : H;
     a.epoch = sh ? sh->epoch : 0;
+    a.go = sh ? sh->go_flag : nullptr;
+    a.status = counters + STATUS_WORD;
+    a.timeout_ns = (unsigned long long)((sh && sh->timeout_ms) ? sh->timeout_ms : 2000u) * 1000000ull;
 
     // pass -> reference path: pass 0 = down (+ the up path's raw-cost add), 1..5 = right, left, down-right, up-right,
     // down-left, 6 = up-left + winner-takes-all (also visits row 0, which the path skips)
@@ -694,6 +728,17 @@ extern "C" int mccnn_sgm_sharded(const float* CLb, const float* CRb, const uint8
                    pass_mask & 0x7f, stream);
 }
 
+extern "C" int mccnn_sgm_shard_status(const void* workspace, int* status_host, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MCCNN_REQUIRE(workspace && status_host, MCCNN_EINVAL, "mccnn_sgm_shard_status: null argument");
+    unsigned v = 0;
+    MCCNN_CUDA(cudaMemcpyAsync(&v, reinterpret_cast<const unsigned*>(workspace) + STATUS_WORD, sizeof(v), cudaMemcpyDeviceToHost, stream));
+    MCCNN_CUDA(cudaStreamSynchronize(stream));
+    *status_host = (int)v;
+    if (v != 0) set_error("mccnn_sgm_sharded: a scanline waited longer than the hand-over deadline for its neighbour rank (status %u)", v);
+    return 0;
+}
+
 extern "C" int mccnn_sgm_single_path(const float* C, const uint8_t* image, float* S, void* workspace,
                                      size_t workspace_bytes, int H, int W, int D, const mccnn_sgm_params* params,
                                      int path, void* stream_) {
@@ -701,7 +746,7 @@ extern "C" int mccnn_sgm_single_path(const float* C, const uint8_t* image, float
     if (int e = check_common(C, H, W, D)) return e;
     MCCNN_REQUIRE(S && image && params && workspace, MCCNN_EINVAL, "mccnn_sgm_single_path: null argument");
     MCCNN_REQUIRE(path >= 0 && path < 8, MCCNN_EINVAL, "mccnn_sgm_single_path: path %d outside 0..7", path);
-    MCCNN_REQUIRE(workspace_bytes >= 4, MCCNN_EWORKSPACE, "mccnn_sgm_single_path: workspace too small");
+    MCCNN_REQUIRE(workspace_bytes >= 8, MCCNN_EWORKSPACE, "mccnn_sgm_single_path: workspace too small");
     MCCNN_REQUIRE(aligned16(C) && aligned16(S), MCCNN_EALIGN, "mccnn_sgm_single_path: volumes must be 16-byte aligned");
     unsigned* counter = reinterpret_cast<unsigned*>(workspace);
     MCCNN_CUDA(cudaMemsetAsync(counter, 0, 4, stream));
@@ -712,6 +757,7 @@ extern "C" int mccnn_sgm_single_path(const float* C, const uint8_t* image, float
     a.nsides = 1;
     a.side0 = 0;
     a.store_s = 1;
+    a.status = counter + 1;   // unused without sharding
     set_params(a, params);
     if (path == 1) {  // penalty channels 0/1 are never written by the reference: P1 = P2 = 0
         a.P1 = a.P2 = a.P1r = a.P2r = 0.0;

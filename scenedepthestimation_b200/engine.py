@@ -42,16 +42,27 @@ def _dev(x, dtype) -> torch.Tensor:
 
 
 class Workspace:
-    """Caller-owned scratch memory, cached by size (the C ABI never allocates)."""
+    """Caller-owned scratch memory (the C ABI never allocates), cached per (device, CUDA stream): two streams, or two host
+    threads on their own streams, never share the volumes of a call in flight. A buffer that has to grow is handed back to
+    torch's caching allocator, which keeps it alive for the work already queued on its stream (the tensor was allocated
+    and only ever used on that stream)."""
 
     def __init__(self):
-        self._buf = None
+        self._bufs = {}
 
     def get(self, nbytes: int) -> torch.Tensor:
-        if self._buf is None or self._buf.numel() < nbytes:
-            self._buf = None
-            self._buf = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
-        return self._buf
+        key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            self._bufs.pop(key, None)
+            buf = None
+            with torch.cuda.stream(torch.cuda.current_stream()):
+                buf = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
+            self._bufs[key] = buf
+        return buf
+
+    def clear(self):
+        self._bufs.clear()
 
 
 _ws = Workspace()
@@ -305,10 +316,12 @@ def encode_u8(disp, scale: int = 1):
     return out
 
 
-def bad_pixels(disp_u8, gt_half):
-    H, W = disp_u8.shape
+def bad_pixels(disp_int, gt_half):
+    """disp_int: u8 map, or a 16-bit map (torch.int16 / uint16 storage, read as unsigned)."""
+    H, W = disp_int.shape
     counts = torch.empty(2, dtype=torch.int64, device="cuda")
-    _lib.check(_lib.load().mccnn_bad_pixels(_p(disp_u8), _p(gt_half), _p(counts), H, W, _stream()), "mccnn_bad_pixels")
+    fn = _lib.load().mccnn_bad_pixels if disp_int.element_size() == 1 else _lib.load().mccnn_bad_pixels_u16
+    _lib.check(fn(_p(disp_int), _p(gt_half), _p(counts), H, W, _stream()), "mccnn_bad_pixels")
     bad, valid = counts.tolist()
     return bad, valid
 

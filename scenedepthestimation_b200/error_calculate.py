@@ -48,16 +48,21 @@ def save_pfm(fname, image, scale=1.0):
 
 
 def error_rate(disp_u8, true_disp):
-    """error_calculate.py:63-83 for one image; true_disp is the full-resolution ground truth."""
+    """error_calculate.py:63-83 for one image; true_disp is the full-resolution ground truth. The map may be the reference's
+    uint8 or the uint16 written for disparity ranges uint8 cannot hold (match_single.output_dtype)."""
     import cv2
 
     _e._require_cuda()
+    disp_u8 = np.asarray(disp_u8)
+    if disp_u8.dtype not in (np.uint8, np.uint16):
+        raise TypeError(f"disparity map must be uint8 or uint16, got {disp_u8.dtype}")
     height, width = disp_u8.shape[0:2]
     gt = np.asarray(true_disp, dtype=np.float32)
     if gt.ndim == 3:
         gt = gt[:, :, 0]
     gt = cv2.resize(gt, (width, height)) / 2
-    bad, _ = _e.bad_pixels(_e._dev(disp_u8, torch.uint8), _e._dev(gt.astype(np.float32), torch.float32))
+    dev = _e._dev(disp_u8, torch.uint8) if disp_u8.dtype == np.uint8 else _e._dev(disp_u8.view(np.int16), torch.int16)
+    bad, _ = _e.bad_pixels(dev, _e._dev(gt.astype(np.float32), torch.float32))
     return bad / (height * width)
 
 
@@ -66,7 +71,7 @@ def evaluate(result_paths, true_paths):
 
     total = 0.0
     for i, (r, t) in enumerate(zip(result_paths, true_paths)):
-        disp = cv2.imread(r, cv2.IMREAD_GRAYSCALE)
+        disp = cv2.imread(r, cv2.IMREAD_GRAYSCALE | cv2.IMREAD_ANYDEPTH)   # keeps 16-bit maps 16-bit
         true_disp, _ = load_pfm(t)
         rate = error_rate(disp, true_disp)
         total += rate

@@ -33,13 +33,15 @@ def shard(ids, rank: int, world: int):
 
 
 def match_batch(pairs, weights, ndisp=128, scale=2, detail_time=None):
-    """pairs: iterable of (left_u8, right_u8) -> list of uint8 maps (match.py:90 writes uint8*2)."""
+    """pairs: iterable of (left_u8, right_u8) -> list of integer maps (match.py:90 writes uint8*2; uint16 where that would
+    wrap, match_single.output_dtype)."""
     from . import process_functional as pf
+    from .match_single import encode_disparity
 
     out = []
     for left, right in pairs:
         dl, _ = pf.match_pair(left, right, weights, ndisp=ndisp, detail_time=detail_time)
-        out.append((dl.astype('uint8') * scale).astype('uint8'))
+        out.append(encode_disparity(dl, ndisp, scale))
     return out
 
 
@@ -53,10 +55,13 @@ class StreamedMatcher:
 
         from . import engine as eng
         from . import process_functional as pf
+        from .match_single import output_dtype
 
         eng._require_cuda()
         self.torch, self.eng = torch, eng
         self.H, self.W, self.D, self.scale, self.nl = H, W, int(ndisp), int(scale), num_layers
+        self.wide = output_dtype(ndisp, scale) is np.uint16   # 16-bit maps where the reference's uint8 would wrap
+        odt = torch.int16 if self.wide else torch.uint8       # int16 storage, reinterpreted as uint16 on the host
         self.packed = pf._load_weights(weights, num_layers)
         nws = eng.match_workspace_bytes(H, W, self.D, num_layers)
         self.slots = []
@@ -64,9 +69,9 @@ class StreamedMatcher:
             self.slots.append(dict(
                 stream=torch.cuda.Stream(), done=torch.cuda.Event(), busy=False, tag=None,
                 h_in=torch.empty((2, H, W), dtype=torch.uint8).pin_memory(),
-                h_out=torch.empty((H, W), dtype=torch.uint8).pin_memory(),
+                h_out=torch.empty((H, W), dtype=odt).pin_memory(),
                 d_in=torch.empty((2, H, W), dtype=torch.uint8, device="cuda"),
-                d_out=torch.empty((H, W), dtype=torch.uint8, device="cuda"),
+                d_out=torch.empty((H, W), dtype=odt, device="cuda"),
                 disp=(torch.empty((H, W), dtype=torch.float32, device="cuda"), torch.empty((H, W), dtype=torch.float32, device="cuda")),
                 ws=torch.empty(nws, dtype=torch.uint8, device="cuda")))
         self.next = 0
@@ -74,10 +79,11 @@ class StreamedMatcher:
     def _collect(self, slot):
         slot["done"].synchronize()
         slot["busy"] = False
-        return slot["tag"], slot["h_out"].numpy().copy()
+        img = slot["h_out"].numpy().copy()
+        return slot["tag"], (img.view(np.uint16) if self.wide else img)
 
     def submit(self, left_u8, right_u8, tag=None):
-        """Enqueue one pair; returns the (tag, uint8 map) of the pair that previously used the slot, or None."""
+        """Enqueue one pair; returns the (tag, integer map) of the pair that previously used the slot, or None."""
         torch, eng = self.torch, self.eng
         slot = self.slots[self.next]
         self.next = (self.next + 1) % len(self.slots)
@@ -88,8 +94,14 @@ class StreamedMatcher:
             slot["d_in"].copy_(slot["h_in"], non_blocking=True)
             eng.match_pair(slot["d_in"][0], slot["d_in"][1], self.packed, self.D, self.nl, out=slot["disp"], workspace=slot["ws"])
             lib = eng._lib.load()
-            eng._lib.check(lib.mccnn_encode_u8(slot["disp"][0].data_ptr(), slot["d_out"].data_ptr(), self.H, self.W, self.scale,
-                                               slot["stream"].cuda_stream), "mccnn_encode_u8")
+            if self.wide:   # trunc(d) * scale in 16 bits: mccnn_encode_u16 takes the scale as a power of two or the map is scaled after
+                eng._lib.check(lib.mccnn_encode_u16(slot["disp"][0].data_ptr(), slot["d_out"].data_ptr(), self.H, self.W, 0,
+                                                    slot["stream"].cuda_stream), "mccnn_encode_u16")
+                if self.scale != 1:
+                    slot["d_out"].mul_(self.scale)
+            else:
+                eng._lib.check(lib.mccnn_encode_u8(slot["disp"][0].data_ptr(), slot["d_out"].data_ptr(), self.H, self.W, self.scale,
+                                                   slot["stream"].cuda_stream), "mccnn_encode_u8")
             slot["h_out"].copy_(slot["d_out"], non_blocking=True)
             slot["done"].record(slot["stream"])
         slot["busy"], slot["tag"] = True, tag

@@ -23,16 +23,31 @@ parser.add_argument("--weights", type=str, default="./check_points_11_11/model_e
 parser.add_argument("--ndisp", type=int, default=128, help="disparity range (the reference hard-codes 128)")
 parser.add_argument("--image-dir", type=str, default="./eval/")
 parser.add_argument("--scale", type=int, default=1, help="multiply the uint8 map (match_single_ui.py uses 2)")
+parser.add_argument("--pfm", action="store_true", help="also write the fp32 map as ./result/{file}/ld{id}.pfm")
 parser.add_argument("--head-weights", type=str, default=None, help="MC-CNN-accurate: .npy dict with fc1..fc4 (fc() naming of "
                     "mc_cnn_brunch.py:95-106), or 'random'; the matching cost is then the fully-connected decision head")
 
 
+def output_dtype(ndisp: int, scale: int = 1):
+    """The reference writes `astype('uint8')` (match_single.py:55; `* 2` in match.py:90 / match_single_ui.py:55), which wraps as
+    soon as a scaled disparity exceeds 255; its range is hard-coded to 128 disparities, so it never does there. With ndisp a
+    parameter the map is written as a 16-bit PNG whenever (ndisp - 1) * scale > 255: same integer values (truncation toward
+    zero, then the scale), no wrap. error_calculate reads either depth."""
+    return np.uint8 if (int(ndisp) - 1) * int(scale) <= 255 else np.uint16
+
+
+def encode_disparity(disparity_f32: np.ndarray, ndisp: int, scale: int = 1) -> np.ndarray:
+    dt = output_dtype(ndisp, scale)
+    return (disparity_f32.astype(dt) * dt(scale)).astype(dt)
+
+
 def match_images(left_u8: np.ndarray, right_u8: np.ndarray, weights, ndisp: int = 128, scale: int = 1, head=None) -> np.ndarray:
-    """match_single.py:34-55 for in-memory images -> the uint8 map the reference would write."""
+    """match_single.py:34-55 for in-memory images -> the integer map the reference would write (uint8; uint16 for ranges
+    the reference's uint8 cannot hold, see output_dtype)."""
     from . import process_functional as pf
 
     left_disparity, _ = pf.match_pair(left_u8, right_u8, weights, ndisp=ndisp, head=head)
-    return (left_disparity.astype('uint8') * scale).astype('uint8')
+    return encode_disparity(left_disparity, ndisp, scale)
 
 
 def main(argv=None):
@@ -51,10 +66,17 @@ def main(argv=None):
         raise FileNotFoundError(f"{left_image_path} / {right_image_path}")
     weights = synthetic.glorot_weights() if args.weights == 'random' else args.weights
     head = synthetic.glorot_fc_weights() if args.head_weights == 'random' else args.head_weights
-    out = match_images(left, right, weights, args.ndisp, args.scale, head)
+    from . import process_functional as pf
+
+    left_disparity, _ = pf.match_pair(left, right, weights, ndisp=args.ndisp, head=head)
     out_dir = './result/{}'.format(args.file)
     os.makedirs(out_dir, exist_ok=True)
-    cv2.imwrite(os.path.join(out_dir, 'ld{}.png'.format(args.id)), out)
+    # 8-bit PNG as in the reference; 16-bit where uint8 would wrap (output_dtype)
+    cv2.imwrite(os.path.join(out_dir, 'ld{}.png'.format(args.id)), encode_disparity(left_disparity, args.ndisp, args.scale))
+    if args.pfm:
+        from .error_calculate import save_pfm
+
+        save_pfm(os.path.join(out_dir, 'ld{}.pfm'.format(args.id)), left_disparity)
 
 
 if __name__ == "__main__":

@@ -37,13 +37,37 @@ def sgm_params(**overrides):
         setattr(p, k, v)
     return p
 
-_weights_cache: dict = {}
+_weights_cache: dict = {}   # key -> packed device blob; keyed by CONTENT for dicts (never by id(): addresses are reused)
+_CACHE_SLOTS = 4
+
+
+def _content_key(arrays) -> str:
+    """Digest of the values, shapes and dtypes of a sequence of (name, array): ~1 ms for the tower's 0.6 MB."""
+    import hashlib
+
+    h = hashlib.blake2b(digest_size=16)
+    for name, a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(f"{name}|{a.dtype.str}|{a.shape}|".encode())
+        h.update(a.view(np.uint8).reshape(-1).data)
+    return h.hexdigest()
+
+
+def _cache_put(cache: dict, key, value):
+    while len(cache) >= _CACHE_SLOTS:
+        cache.pop(next(iter(cache)))   # oldest entry (dicts keep insertion order)
+    cache[key] = value
+    return value
 
 
 def _load_weights(checkpoint, num_layers):
     if isinstance(checkpoint, dict):
         weights = checkpoint
-        key = ("dict", id(checkpoint), num_layers)
+        names = [f"conv{i}/{k}:0" for i in range(1, num_layers + 1) for k in ("weights", "biases")]
+        missing = [n for n in names if n not in weights]
+        if missing:
+            raise KeyError(f"weights dict lacks {missing[:4]} ...")
+        key = ("dict", _content_key((n, weights[n]) for n in names), num_layers)
     else:
         path = os.fspath(checkpoint)
         if not path.endswith(".npy"):
@@ -56,8 +80,7 @@ def _load_weights(checkpoint, num_layers):
         if weights is None:
             weights = np.load(checkpoint, encoding="bytes", allow_pickle=True).item()
             weights = {(k.decode() if isinstance(k, bytes) else k): v for k, v in weights.items()}
-        _weights_cache.clear()
-        _weights_cache[key] = _e.pack_weights(weights, num_layers)
+        _cache_put(_weights_cache, key, _e.pack_weights(weights, num_layers))
     return _weights_cache[key]
 
 
@@ -125,17 +148,25 @@ def _load_head(head):
     mc_cnn_brunch.py:95-106) -> device copy in the kernel's layout, cached per object / path."""
     if head is None or isinstance(head, _e.FcHeadWeights):
         return head
-    key = head if isinstance(head, str) else id(head)
+    if isinstance(head, (str, os.PathLike)):
+        path = os.fspath(head)
+        key = ("file", path, os.path.getmtime(path))
+        w = None
+    else:
+        w = {(k.decode() if isinstance(k, bytes) else k): v for k, v in head.items()}
+        key = ("dict", _content_key(sorted((k, np.asarray(v)) for k, v in w.items() if k.startswith("fc"))))
     if key not in _head_cache:
-        w = np.load(head, encoding='bytes', allow_pickle=True).item() if isinstance(head, str) else head
-        w = {(k.decode() if isinstance(k, bytes) else k): v for k, v in w.items()}
-        _head_cache[key] = _e.FcHeadWeights(w)
+        if w is None:
+            w = np.load(head, encoding='bytes', allow_pickle=True).item()
+            w = {(k.decode() if isinstance(k, bytes) else k): v for k, v in w.items()}
+        _cache_put(_head_cache, key, _e.FcHeadWeights(w))
     return _head_cache[key]
 
 
 def match_pair(left_u8, right_u8, checkpoint, ndisp=None, patch=11, detail_time=None, params=None, head=None):
     """Fused match_single.py:34-55: u8 pair -> (left disparity f32, right raw WTA f32), one C call. `head` (weights dict
-    or .npy path with fc1..fc4) switches the matching cost to the MC-CNN-accurate decision head."""
+    or .npy path with fc1..fc4) switches the matching cost to the MC-CNN-accurate decision head.
+    Weight dicts are recognised by content (a digest of the arrays), so a new or an updated dict is always repacked."""
     _e._require_cuda()
     D = int(NDISP if ndisp is None else ndisp)
     nl = patch // 2

@@ -37,12 +37,13 @@ def band_rows(H: int, world: int):
     return out
 
 
-def _shard(rank, world, H, row0, rows, local, prev, nxt, epoch) -> _lib.Shard:
-    return _lib.Shard(rank, world, H, row0, rows, local, prev, nxt, epoch)
+def _shard(rank, world, H, row0, rows, local, prev, nxt, epoch, go_flag=None, timeout_ms=0) -> _lib.Shard:
+    return _lib.Shard(rank, world, H, row0, rows, local, prev, nxt, epoch, go_flag, timeout_ms)
 
 
-def sgm_band(CLb, CRb, il_full, ir_full, D, shard: _lib.Shard, pass_mask=0x7F, keep_volumes=True, out=None, params=None):
-    """mccnn_sgm_sharded on this rank's band -> (SLb, SRb, dispLb, dispRb)."""
+def sgm_band(CLb, CRb, il_full, ir_full, D, shard: _lib.Shard, pass_mask=0x7F, keep_volumes=True, out=None, params=None, ws=None):
+    """mccnn_sgm_sharded on this rank's band -> (SLb, SRb, dispLb, dispRb). `ws`: the 256-byte SGM workspace (holds the
+    launch's status word, read back by band_status)."""
     lib = _lib.load()
     rows, W, _ = CLb.shape
     params = params or _lib.default_sgm_params()
@@ -51,12 +52,22 @@ def sgm_band(CLb, CRb, il_full, ir_full, D, shard: _lib.Shard, pass_mask=0x7F, k
                torch.empty((rows, W), dtype=torch.float32, device="cuda"), torch.empty((rows, W), dtype=torch.float32, device="cuda"))
     SLb, SRb, dl, dr = out
     nws = lib.mccnn_sgm_workspace_bytes(shard.H_full, W, D)
-    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    if ws is None:
+        ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
     _lib.check(lib.mccnn_sgm_sharded(CLb.data_ptr(), CRb.data_ptr(), il_full.data_ptr(), ir_full.data_ptr(), SLb.data_ptr(),
                                      SRb.data_ptr(), dl.data_ptr(), dr.data_ptr(), ws.data_ptr(), nws, W, D, C.byref(params),
                                      eng.EXACT, 1 if keep_volumes else 0, C.byref(shard), pass_mask,
                                      torch.cuda.current_stream().cuda_stream), "mccnn_sgm_sharded")
     return out
+
+
+def band_status(ws) -> int:
+    """Synchronises the stream; 0 = every scanline of the last mccnn_sgm_sharded launch got its hand-over, 1 = a wait hit the
+    deadline (a neighbour rank died / never launched): the outputs are invalid."""
+    st = C.c_int(0)
+    _lib.check(_lib.load().mccnn_sgm_shard_status(ws.data_ptr(), C.byref(st), torch.cuda.current_stream().cuda_stream),
+               "mccnn_sgm_shard_status")
+    return int(st.value)
 
 
 def emulate_bands(CL, CR, il, ir, D, world: int, epoch: int = 1):
@@ -86,7 +97,7 @@ def emulate_bands(CL, CR, il, ir, D, world: int, epoch: int = 1):
 class ShardedMatcher:
     """One pair per call, split by rows over the ranks of `group` (one process per GPU, NCCL)."""
 
-    def __init__(self, H: int, W: int, D: int, weights: dict, num_layers: int = 5, group=None):
+    def __init__(self, H: int, W: int, D: int, weights: dict, num_layers: int = 5, group=None, timeout_ms: int = 2000):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
 
@@ -107,6 +118,12 @@ class ShardedMatcher:
         self.prev = ptrs[self.rank - 1] if self.rank > 0 else None
         self.next = ptrs[self.rank + 1] if self.rank < self.world - 1 else None
         self.epoch = 0
+        self.timeout_ms = int(timeout_ms)
+        self.go = torch.ones(1, dtype=torch.int32, device="cuda")       # all-reduced (MIN) before every SGM launch
+        self.sgm_ws = torch.zeros(lib.mccnn_sgm_workspace_bytes(H, W, D), dtype=torch.uint8, device="cuda")
+        self.tc_ws = None
+        if D >= 512:   # the cost-volume variant mccnn_disparity_pipeline picks for wide bands (pipeline.cu)
+            self.tc_ws = torch.empty(lib.mccnn_cost_volume_tc_workspace_bytes(self.max_rows, W), dtype=torch.uint8, device="cuda")
         Dp = eng.disp_pitch(D)
         self.S = (torch.empty((self.rows, W, Dp), dtype=torch.float32, device="cuda"),
                   torch.empty((self.rows, W, Dp), dtype=torch.float32, device="cuda"))
@@ -127,10 +144,34 @@ class ShardedMatcher:
             left_full[r0:r0 + n].copy_(recv[r, 0, :n])
             right_full[r0:r0 + n].copy_(recv[r, 1, :n])
 
-    def match(self, il_band: torch.Tensor, ir_band: torch.Tensor):
-        """u8 bands [rows, W] of this rank -> (filtered left disparity, raw right WTA), whole maps on every rank."""
+    def _cost_volume(self, fl, fr):
+        if self.tc_ws is None:
+            return eng.cost_volume(fl, fr, self.D)
+        lib = _lib.load()
+        n, W = fl.shape[0], self.W
+        Dp = eng.disp_pitch(self.D)
+        CL = torch.empty((n, W, Dp), dtype=torch.float32, device="cuda")
+        CR = torch.empty((n, W, Dp), dtype=torch.float32, device="cuda")
+        _lib.check(lib.mccnn_cost_volume_tc(fl.data_ptr(), fr.data_ptr(), CL.data_ptr(), CR.data_ptr(), self.tc_ws.data_ptr(),
+                                            self.tc_ws.numel(), n, W, self.D, 1.0, torch.cuda.current_stream().cuda_stream),
+                   "mccnn_cost_volume_tc")
+        return CL, CR
+
+    def match(self, il_band: torch.Tensor, ir_band: torch.Tensor, check: bool = True):
+        """u8 bands [rows, W] of this rank -> (filtered left disparity, raw right WTA), whole maps on every rank.
+
+        No host round trip between the ranks: an all-reduce (MIN) of each rank's "my inputs are fine, I will launch" word
+        runs on the stream in front of the SGM launch. It is the device-side barrier that keeps a rank from overwriting
+        exchange slots its neighbours still read for the previous pair, and the kernels return at once when it is 0. With
+        check=True the status word of the launch (a hand-over that never came within timeout_ms) is read back at the end
+        and raises; check=False leaves that to a later call of status()."""
         dist, nl = self.dist, self.nl
         r0, n = self.row0, self.rows
+        ok = tuple(il_band.shape) == (n, self.W) and tuple(ir_band.shape) == (n, self.W) and il_band.dtype == torch.uint8 \
+            and ir_band.dtype == torch.uint8 and il_band.is_cuda and ir_band.is_cuda
+        self.go.fill_(1 if ok else 0)
+        if not ok:   # take part in this pair's collectives with an empty band so that the other ranks are told, then raise
+            il_band = ir_band = torch.zeros((n, self.W), dtype=torch.uint8, device="cuda")
         self.u8_send[0, :n].copy_(il_band)
         self.u8_send[1, :n].copy_(ir_band)
         self._gather(self.u8_send, self.u8_recv, self.il, self.ir)
@@ -138,14 +179,28 @@ class ShardedMatcher:
         for img in (self.il, self.ir):
             padded = eng.standardize_pad(img, nl)          # global statistics, zero padding at the image borders
             feats.append(eng.conv_tower(padded[r0:r0 + n + 2 * nl], self.packed, nl))  # band + 5-row halos
-        CL, CR = eng.cost_volume(feats[0], feats[1], self.D)
-        # neighbours must have finished the previous pair before their exchange slots are written again
-        dist.barrier(group=self.group)
+        CL, CR = self._cost_volume(feats[0], feats[1])
+        # on the stream, no host sync: neighbours have finished the previous pair's SGM (stream order) once this completes
+        dist.all_reduce(self.go, op=dist.ReduceOp.MIN, group=self.group)
         self.epoch += 1
-        shard = _shard(self.rank, self.world, self.H, r0, n, self.xchg.data_ptr(), self.prev, self.next, self.epoch)
+        shard = _shard(self.rank, self.world, self.H, r0, n, self.xchg.data_ptr(), self.prev, self.next, self.epoch,
+                       self.go.data_ptr(), self.timeout_ms)
         sgm_band(CL, CR, self.il, self.ir, self.D, shard, keep_volumes=False,
-                 out=(self.S[0], self.S[1], self.f_send[0, :n], self.f_send[1, :n]))
+                 out=(self.S[0], self.S[1], self.f_send[0, :n], self.f_send[1, :n]), ws=self.sgm_ws)
         self._gather(self.f_send, self.f_recv, self.dl, self.dr)
         fl, _ = eng.lr_flags(self.dl, self.dr, right=False)
         filled = eng.lrc_fill(self.dl, fl)
-        return eng.median5(filled, self.dl), self.dr
+        out = eng.median5(filled, self.dl), self.dr
+        if not ok:
+            raise ValueError(f"rank {self.rank}: bands must be CUDA u8 tensors of shape ({n}, {self.W}); the pair was abandoned on every rank")
+        if check:
+            self.status()
+        return out
+
+    def status(self):
+        """Raise if the last pair was abandoned (a rank reported bad inputs) or a hand-over never arrived."""
+        st = band_status(self.sgm_ws)   # synchronises the stream
+        if int(self.go.item()) == 0:
+            raise RuntimeError("sharded match: another rank reported invalid inputs; the pair was abandoned on every rank")
+        if st != 0:
+            raise RuntimeError(_lib.load().mccnn_last_error().decode(errors="replace"))

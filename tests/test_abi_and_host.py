@@ -40,7 +40,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_constants_and_sizes(lib):
     from scenedepthestimation_b200 import _lib
 
-    assert lib.mccnn_abi_version() == 3
+    assert lib.mccnn_abi_version() == 4
     assert [lib.mccnn_disp_pitch(d) for d in (1, 4, 80, 81, 228, 800)] == [4, 4, 80, 84, 228, 800]
     p = _lib.default_sgm_params()
     # process_functional.py:1141-1144, stored as fp32 (:149), reduced pair computed in fp64 then rounded (:141-142)
@@ -152,3 +152,49 @@ def test_synthetic_inputs_are_seeded():
     w = syn.glorot_weights()
     assert w["conv1/weights:0"].shape == (3, 3, 1, 64) and w["conv5/biases:0"].shape == (64,)
     assert abs(float(np.abs(w["conv2/weights:0"]).max()) - np.sqrt(6 / (576 + 576))) < 1e-3
+
+
+def test_weight_cache_key_is_content():
+    """Host logic of the weight caches (no GPU): equal arrays give equal keys whatever the dict object, any change gives a new key."""
+    from scenedepthestimation_b200 import process_functional as pf, synthetic as syn
+
+    a, b = syn.glorot_weights(seed=3), syn.glorot_weights(seed=3)
+    key = lambda w: pf._content_key(sorted(w.items()))
+    assert a is not b and key(a) == key(b)
+    b["conv2/biases:0"] = b["conv2/biases:0"].copy()
+    b["conv2/biases:0"][5] += np.float32(1e-6)
+    assert key(a) != key(b)
+    assert key(a) != key({k: v.astype(np.float64) for k, v in a.items()})
+    cache = {}
+    for i in range(10):
+        pf._cache_put(cache, i, i)
+    assert list(cache) == [6, 7, 8, 9]
+
+
+def test_net_variable_store_without_gpu(tmp_path):
+    """mc_cnn_brunch drop-in: branches alias one weight dict (scope.reuse_variables(), mc_cnn_brunch.py:73-75)."""
+    from scenedepthestimation_b200 import mc_cnn_brunch as mb, synthetic as syn
+
+    mb.reset_default_graph()
+    x = np.zeros((2, 11, 11, 1), np.float32)
+    with pytest.raises(ValueError):
+        mb.Net(x, num_of_conv_layers=5, is_branch=True)
+    first = mb.Net(x, num_of_conv_layers=5)
+    twin = mb.Net(x, num_of_conv_layers=5, is_branch=True)
+    other = mb.Net(x, num_of_conv_layers=4)              # another configuration has its own variables
+    assert twin.weights is first.weights and other.weights is not first.weights
+    w = syn.glorot_weights(seed=42)
+    np.save(tmp_path / "w.npy", w)
+    twin.weights_path = str(tmp_path / "w.npy")
+    twin.load_initial_weights()
+    assert all(np.array_equal(first.weights[k], w[k]) for k in w)
+
+
+def test_output_dtype_contract():
+    from scenedepthestimation_b200 import match_single as ms
+
+    assert ms.output_dtype(128, 1) is np.uint8 and ms.output_dtype(128, 2) is np.uint8 and ms.output_dtype(256, 1) is np.uint8
+    assert ms.output_dtype(257, 1) is np.uint16 and ms.output_dtype(129, 2) is np.uint16 and ms.output_dtype(800, 1) is np.uint16
+    d = np.array([[0.0, 3.75, 254.0, 399.5]], np.float32)
+    assert np.array_equal(ms.encode_disparity(d, 128, 2), np.array([[0, 6, 252, 30]], np.uint8))   # the reference's wrap, kept
+    assert np.array_equal(ms.encode_disparity(d, 400, 2), np.array([[0, 6, 508, 798]], np.uint16))

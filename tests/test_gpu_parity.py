@@ -696,3 +696,136 @@ def test_entry_points_reject_bad_arguments(eng):
     with pytest.raises(ValueError):
         t.step(np.zeros((4, 5, 5)), np.zeros((3, 5, 5)), np.zeros((4, 5, 5)))
     assert t.step(*tr.synthetic_patches(1, 5, 0)) >= 0.0  # a batch of one
+
+
+def test_cli_large_disparity_range_writes_16_bit(eng, tmp_path, monkeypatch):
+    """match_single.py:55 / match.py:90 write astype('uint8'): it wraps as soon as a (scaled) disparity exceeds 255. With the
+    range a parameter the CLIs write 16-bit PNGs there (same integer values, no wrap) and error_calculate reads either depth.
+    D = 400 through match_single, match (sequential and streamed) and the metric."""
+    cv2 = pytest.importorskip("cv2")
+    from scenedepthestimation_b200 import error_calculate as ec, match, match_single, process_functional as pf, synthetic as syn
+
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("eval"), os.makedirs("test")
+    D = 400
+    w = syn.glorot_weights()
+    il, ir, gt = syn.textured_pair(40, 520, D, 6)
+    assert gt.max() > 255
+    cv2.imwrite("eval/left_1.png", il), cv2.imwrite("eval/right_1.png", ir)
+    match_single.main(["-i", "1", "-f", "wide", "--weights", "random", "--ndisp", str(D), "--pfm"])
+    got = cv2.imread("result/wide/ld1.png", cv2.IMREAD_UNCHANGED)
+    dl, _ = pf.match_pair(il, ir, w, ndisp=D)
+    assert got.dtype == np.uint16 and dl.max() > 255
+    assert np.array_equal(got, dl.astype(np.uint16))               # truncation toward zero, nothing wrapped
+    assert not np.array_equal(got, dl.astype(np.uint8))            # what the reference's cast would have written
+    pfm, _ = ec.load_pfm("result/wide/ld1.pfm")
+    assert np.array_equal(pfm[:, :, 0], dl)
+    assert match_single.output_dtype(128, 1) is np.uint8 and match_single.output_dtype(128, 2) is np.uint8
+    assert match_single.output_dtype(129, 2) is np.uint16 and match_single.output_dtype(257, 1) is np.uint16
+    # the reference's range keeps its format bit for bit
+    assert match_single.match_images(il, ir, w, 128, 2).dtype == np.uint8
+    for i in (1, 2):
+        cv2.imwrite(f"test/left_{i}.jpg", il), cv2.imwrite(f"test/right_{i}.jpg", ir)
+    a, b = cv2.imread("test/left_1.jpg", cv2.IMREAD_GRAYSCALE), cv2.imread("test/right_1.jpg", cv2.IMREAD_GRAYSCALE)
+    exp = match.match_batch([(a, b)], w, ndisp=D, scale=2)[0]
+    assert exp.dtype == np.uint16 and exp.max() > 511
+    for depth in (1, 2):
+        match.main(["--weights", "random", "--ndisp", str(D), "--first", "1", "--last", "2", "--depth", str(depth),
+                    "--out-dir", f"./d{depth}/"])
+        for i in (1, 2):
+            assert np.array_equal(cv2.imread(f"d{depth}/ld{i}.png", cv2.IMREAD_UNCHANGED), exp), (depth, i)
+    full = cv2.resize(gt.astype(np.float32) * 2.0, (520, 40))
+    rate = ec.error_rate(got, full)
+    d, t = got.astype(np.float64), full / 2.0
+    valid = np.isfinite(t) & (t != 0)
+    assert rate == pytest.approx(float(np.sum(valid & (np.abs(d - t) > 1))) / d.size)
+    assert rate < ec.error_rate(dl.astype(np.uint8), full)         # the wrapped map scores worse against the ground truth
+
+
+def test_weight_caches_follow_content_not_identity(eng):
+    """process_functional caches packed weights by a digest of the arrays: a NEW dict (CPython reuses the address of a freed one)
+    or an in-place update must never be served the previous dict's device blob."""
+    import gc
+
+    from scenedepthestimation_b200 import process_functional as pf, synthetic as syn
+
+    il, ir, _ = syn.textured_pair(40, 64, 24, 3)
+    outs, ids = [], set()
+    for seed in (1, 2, 3, 4, 5, 6):
+        w = syn.glorot_weights(seed=seed)
+        ids.add(id(w))
+        outs.append(pf.match_pair(il, ir, w, ndisp=24)[0])
+        exp = pf.match_pair(il, ir, dict(syn.glorot_weights(seed=seed)), ndisp=24)[0]
+        assert np.array_equal(outs[-1], exp)
+        del w
+        gc.collect()
+    assert any(not np.array_equal(outs[0], o) for o in outs[1:])
+    w = syn.glorot_weights(seed=1)
+    a = pf.match_pair(il, ir, w, ndisp=24)[0]
+    w["conv3/weights:0"] = w["conv3/weights:0"] * np.float32(-1.0)   # same dict object, new values
+    b = pf.match_pair(il, ir, w, ndisp=24)[0]
+    assert np.array_equal(a, outs[0]) and not np.array_equal(a, b)
+    assert len(pf._weights_cache) <= pf._CACHE_SLOTS
+    hw = syn.glorot_fc_weights(gain=2.0)
+    c = pf.match_pair(il, ir, w, ndisp=24, head=hw)[0]
+    hw2 = {k: (v * np.float32(0.5) if k == "fc2/weights:0" else v) for k, v in hw.items()}
+    d = pf.match_pair(il, ir, w, ndisp=24, head=hw2)[0]
+    assert np.array_equal(c, pf.match_pair(il, ir, w, ndisp=24, head=dict(hw))[0]) and len(pf._head_cache) <= pf._CACHE_SLOTS
+    assert not np.array_equal(c, d)
+
+
+def test_net_branches_share_variables_and_batch_in_one_launch(eng, tmp_path):
+    """mc_cnn_brunch.py:73-75: a Net built with is_branch=True re-uses the first Net's variables; load_initial_weights on one
+    branch is seen by the twins. A batch of 11x11 patches (train.py's feed) runs as one launch and equals per-patch runs."""
+    from oracle import conv_tower as ct
+    from scenedepthestimation_b200 import mc_cnn_brunch as mb, synthetic as syn
+
+    mb.reset_default_graph()
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((16, 11, 11, 1)).astype(np.float32)
+    y = rng.standard_normal((16, 11, 11, 1)).astype(np.float32)
+    with pytest.raises(ValueError):
+        mb.Net(y, num_of_conv_layers=5, is_branch=True)
+    left = mb.Net(x, num_of_conv_layers=5, batch_size=16)
+    right = mb.Net(y, num_of_conv_layers=5, batch_size=16, is_branch=True)
+    assert right.weights is left.weights
+    before = right.features.copy()
+    w = syn.glorot_weights(seed=99)
+    np.save(tmp_path / "w.npy", w)
+    left.weights_path = str(tmp_path / "w.npy")
+    left.load_initial_weights()
+    after = right.features
+    assert after.shape == (16, 1, 1, 64) and not np.array_equal(before, after)
+    for n in (0, 7, 15):
+        exp = ct.conv_tower(y[n:n + 1], w, 5)
+        np.testing.assert_allclose(after[n], exp, rtol=0, atol=2e-6)
+    right.save_weights_dict(file_name=str(tmp_path / "out.npy"))
+    back = np.load(tmp_path / "out.npy", allow_pickle=True).item()
+    assert all(np.array_equal(back[k], w[k]) for k in w)
+
+
+def test_sharded_handover_wait_is_bounded(eng):
+    """mccnn_sgm_sharded as rank 1 of 2 with nobody on the other side: the scanlines of the downward pass wait for a hand-over
+    that never comes. The wait must end at the deadline (not spin for ever), every warp must leave, and the status word must say
+    so; with the go flag at 0 the kernels must return at once without touching the status."""
+    import time
+
+    from scenedepthestimation_b200 import _lib, sharded as sh, synthetic as syn
+
+    H, W, D = 24, 40, 16
+    il, ir = syn.noise_pair(H, W, 1)
+    fl, fr = syn.unit_features(H, W, 64, 1)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    nx = _lib.load().mccnn_sgm_shard_exchange_bytes(W)
+    xchg = torch.zeros(nx, dtype=torch.uint8, device="cuda")
+    ws = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    band = (12, 12)
+    for go_value, want in ((1, 1), (0, 0)):
+        go = torch.full((1,), go_value, dtype=torch.int32, device="cuda")
+        shard = sh._shard(1, 2, H, band[0], band[1], xchg.data_ptr(), xchg.data_ptr(), None, 7, go.data_ptr(), 40)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sh.sgm_band(CL[band[0]:], CR[band[0]:], dev(il), dev(ir), D, shard, pass_mask=1, ws=ws)
+        st = sh.band_status(ws)
+        dt = time.perf_counter() - t0
+        assert st == want and dt < 5.0, (go_value, st, dt)

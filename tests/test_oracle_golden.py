@@ -23,6 +23,25 @@ def test_oracle_matches_reference_kernels(path):
     assert bool(g["dr_fill_untouched"])  # LRC_kernel never writes the right output (App. A6)
 
 
+def test_oracle_matches_reference_c2_output():
+    """The reference's own disparity_compute_by_gpu output on BASELINE config 2 (695x555, its hard-coded 128 disparities; run on a
+    B200 by tools/ref_gpu_probe.py --time-c2 on the seed-1001 inputs) against the oracle."""
+    from scenedepthestimation_b200 import synthetic as syn
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_c2_dl.npz"))
+    W, H, D = syn.CONFIGS["c2"]
+    il, ir, _ = syn.textured_pair(H, W, D, 1001)
+    fl, fr, _ = syn.correlated_features(H, W, D, 64, 1001)
+    final, dr, k = st.disparity_pipeline(il, ir, fl, fr, 128, keep=True)
+    if g["dl"].dtype == np.uint8:   # first-round file: the map as match_single.py:55 would encode it
+        assert np.array_equal(final.astype(np.uint8), g["dl"])
+        return
+    assert bool(g["e2e_equals_stepwise"])
+    assert np.array_equal(final.view(np.int32), g["dl"].view(np.int32))
+    for key in ("dl_wta", "dr_wta", "flag_l", "dl_fill", "dl_final"):
+        assert np.array_equal(k[key], g[key]), f"{key} differs from the reference kernels at c2"
+
+
 def test_oracle_per_path_order():
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_tiny_6x10.npz"))
     cl, cr = st.cost_volume(g["fl"], g["fr"], 128)

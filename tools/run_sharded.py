@@ -17,6 +17,20 @@ def main():
     m = sharded.ShardedMatcher(H, W, D, weights)
     r0, n = m.row0, m.rows
     bl, br = torch.from_numpy(il[r0:r0 + n]).cuda(), torch.from_numpy(ir[r0:r0 + n]).cuda()
+    if len(sys.argv) > 2 and sys.argv[2] == "fault":
+        # one rank hands in a band of the wrong shape: EVERY rank must raise for this pair (nobody waits in a kernel), and the
+        # next, well-formed pair must work again
+        raised = False
+        try:
+            m.match(bl[:-1] if rank == world - 1 else bl, br)
+        except (ValueError, RuntimeError) as exc:
+            raised = True
+            print(f"[rank {rank}] abandoned pair raised: {type(exc).__name__}: {str(exc)[:90]}", flush=True)
+        flag = torch.tensor([1 if raised else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            print("fault injection: some rank did not raise", flush=True)
+            sys.exit(2)
     dl, dr = m.match(bl, br)
     torch.cuda.synchronize()
     ok = True
@@ -30,7 +44,7 @@ def main():
             eng.match_pair(torch.from_numpy(il).cuda(), torch.from_numpy(ir).cuda(), m.packed, D, 5)
             torch.cuda.synchronize(); t.append(time.perf_counter() - t0)
         print(f"[single] {min(t) * 1e3:.2f} ms", flush=True)
-        eng._ws._buf = None
+        eng._ws.clear()
         torch.cuda.empty_cache()
     ts = []
     for _ in range(4):
