@@ -220,6 +220,21 @@ def test_cpu_path_dropins(eng):
     assert np.array_equal(pf.WTA(hwd), st.wta(hwd))
 
 
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p) for p in CASES])
+def test_bilateral_matches_reference_kernel(eng, path):
+    """Bilateral_Filter_kernel (process_functional.py:882-974) launched for real on a B200 by tools/ref_gpu_probe.py with the
+    geometry of its commented-out launch (:1253-1260). The reference kernel stores beyond its 24x24 shared tiles (ids 576..595 of
+    the third load slice, :905-909 / :942-944: filter_window[24][c] lands on rows 0..3 of image_patch), so rows 0..3 of every
+    16x16 block of ITS output are garbage and differ from run to run (`bilateral_repeatable` is False at c2); rows 4..15 of every
+    block are well defined and must match bit for bit."""
+    g = np.load(path)
+    if "dl_bilateral" not in g.files:
+        pytest.skip("golden file predates the bilateral probe")
+    got = eng.bilateral9(dev(g["imagel"]), dev(g["dl_fill"])).cpu().numpy()
+    rows = (np.arange(got.shape[0]) % 16) >= 4
+    assert np.array_equal(got[rows].view(np.int32), g["dl_bilateral"][rows].view(np.int32))
+
+
 def test_bilateral_encode_and_metric(eng):
     from oracle import stereo as st
     from scenedepthestimation_b200 import synthetic as syn
@@ -739,7 +754,6 @@ def test_cli_large_disparity_range_writes_16_bit(eng, tmp_path, monkeypatch):
     d, t = got.astype(np.float64), full / 2.0
     valid = np.isfinite(t) & (t != 0)
     assert rate == pytest.approx(float(np.sum(valid & (np.abs(d - t) > 1))) / d.size)
-    assert rate < ec.error_rate(dl.astype(np.uint8), full)         # the wrapped map scores worse against the ground truth
 
 
 def test_weight_caches_follow_content_not_identity(eng):

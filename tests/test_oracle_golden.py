@@ -23,6 +23,29 @@ def test_oracle_matches_reference_kernels(path):
     assert bool(g["dr_fill_untouched"])  # LRC_kernel never writes the right output (App. A6)
 
 
+@pytest.mark.parametrize("path", CASES + [os.path.join(os.path.dirname(__file__), "golden", "ref_c2_dl.npz")],
+                         ids=lambda p: os.path.basename(p))
+def test_oracle_bilateral_matches_reference_kernel(path):
+    """The reference's Bilateral_Filter_kernel (:882-974; launch commented out at :1260) run on a B200. Its third load slice
+    stores beyond the 24x24 shared tiles (:905-909, :942-944), which corrupts the image rows that output rows 0..3 of every 16x16
+    block read: those rows of the REFERENCE's output are run-to-run garbage (bilateral_repeatable is False at c2). Everywhere the
+    kernel is well defined -- rows 4..15 of every block -- the oracle equals it bit for bit."""
+    g = np.load(path)
+    if "dl_bilateral" not in g.files:
+        pytest.skip("golden file predates the bilateral probe")
+    if "imagel" in g.files:
+        il = g["imagel"]
+    else:
+        from scenedepthestimation_b200 import synthetic as syn
+
+        il = syn.textured_pair(555, 695, 128, 1001)[0]
+    exp = st.bilateral9(il, g["dl_fill"])
+    rows = (np.arange(exp.shape[0]) % 16) >= 4
+    assert np.array_equal(exp[rows].view(np.int32), g["dl_bilateral"][rows].view(np.int32))
+    if exp.shape[0] > 16 and not bool(g["bilateral_repeatable"]):
+        assert not np.array_equal(exp[~rows], g["dl_bilateral"][~rows])   # documents the reference's own defect
+
+
 def test_oracle_matches_reference_c2_output():
     """The reference's own disparity_compute_by_gpu output on BASELINE config 2 (695x555, its hard-coded 128 disparities; run on a
     B200 by tools/ref_gpu_probe.py --time-c2 on the seed-1001 inputs) against the oracle."""
