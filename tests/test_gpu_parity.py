@@ -220,7 +220,7 @@ def test_cpu_path_dropins(eng):
     assert np.array_equal(pf.WTA(hwd), st.wta(hwd))
 
 
-@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p) for p in CASES])
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
 def test_bilateral_matches_reference_kernel(eng, path):
     """Bilateral_Filter_kernel (process_functional.py:882-974) launched for real on a B200 by tools/ref_gpu_probe.py with the
     geometry of its commented-out launch (:1253-1260). The reference kernel stores beyond its 24x24 shared tiles (ids 576..595 of
