@@ -42,9 +42,15 @@ enum {
     MCCNN_EWORKSPACE = -3 /* workspace too small */
 };
 
-/* SGM arithmetic: MCCNN_SGM_EXACT reproduces the reference bit for bit (fp64 path state, fp32 S
- * rounded once per path in launch order, process_functional.py:265-343, 1166-1202). */
-enum { MCCNN_SGM_EXACT = 0 };
+/* SGM arithmetic.
+ * MCCNN_SGM_EXACT (default everywhere) reproduces the reference bit for bit: fp64 path state, fp32 S rounded once per path
+ *   in launch order (process_functional.py:265-343, 1166-1202), fp64-accumulated cost volume (:120-131).
+ * MCCNN_SGM_FUSED is this library's opt-in throughput mode, held to north_star's tolerance instead (costs and aggregated
+ *   costs within 1e-4 relative; disparities equal except at near-ties, measured by tools/fused_census.py): the same
+ *   recurrence, extents, wraps and penalties with fp32 path state, the 8 contributions added to S in the order down,
+ *   down-right, up, left, down-left, right, up-right, up-left (4 sweeps over the volumes instead of 7, csrc/sgm_fused.cu),
+ *   and, inside mccnn_disparity_pipeline / mccnn_match_pair, an fp32-accumulated cost volume. */
+enum { MCCNN_SGM_EXACT = 0, MCCNN_SGM_FUSED = 1 };
 
 typedef struct {
     float P1;       /* 2.3   process_functional.py:1141 (stored as fp32, :149) */
@@ -109,6 +115,10 @@ int mccnn_conv_tower_fp32(const float* padded, const void* packed_weights, float
  * accumulator, entries never written = fill (1.0 in the reference). CR may be NULL. */
 int mccnn_cost_volume(const float* fl, const float* fr, float* CL, float* CR,
                       int H, int W, int D, float fill, void* stream);
+/* MCCNN_SGM_FUSED's cost volume: the same layout, fills and pads, fp32 FMA accumulation instead of the reference's fp64
+ * accumulator (|difference| <= 4e-6 on unit-norm features; not bit-identical to the reference). */
+int mccnn_cost_volume_fast(const float* fl, const float* fr, float* CL, float* CR,
+                           int H, int W, int D, float fill, void* stream);
 /* Tensor-core variant, same contract and the same bits out: the exact sum of f*g is taken from tcgen05 MMAs on 8-bit
  * slices of the features, the fp32 rounding residuals of the reference's products from the CUDA cores, and every
  * evaluation whose rounding cannot be proven is redone with the literal loop (csrc/cost_volume_tc.cu).
@@ -170,7 +180,7 @@ int mccnn_cbca(const float* vol_in, float* vol_out, float* tmp, const uint8_t* a
  *  SL, SR   : aggregated volumes (written; need no initialisation). With keep_volumes == 0 the
  *             final contents are unspecified (the last pass does not store S).
  *  dispL/R  : fp32 [H][W] raw winner-takes-all maps
- *  workspace: mccnn_sgm_workspace_bytes(H, W, D) bytes. */
+ *  workspace: mccnn_sgm_workspace_bytes(H, W, D) bytes, 256-byte aligned (one size serves both modes). */
 size_t mccnn_sgm_workspace_bytes(int H, int W, int D);
 int mccnn_sgm(const float* CL, const float* CR, const uint8_t* imageL, const uint8_t* imageR,
               float* SL, float* SR, float* dispL, float* dispR,

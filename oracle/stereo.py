@@ -236,6 +236,96 @@ def sgm_all_paths(cl, cr, pen_l, pen_r, keep_each=False):
     return (sl, sr, each) if keep_each else (sl, sr)
 
 
+# --------------------------------------------------------------------------- SGM, "fused" arithmetic (MCCNN_SGM_FUSED)
+# Not a reference mode: the opt-in mode of this repo that gives up the reference's fp64 path state and its per-path fp32
+# rounding ORDER of S to run the 8 paths in 4 sweeps (csrc/sgm_fused.cu). Same recurrence, same traversal extents, wraps,
+# restarts and penalty rule as above (:265-343, :346-797); what changes is (a) the path state, the minimum and the
+# hand-over min + P2 are fp32, (b) the contributions are added into the fp32 S in the order of FUSED_PATH_ORDER, each add
+# rounded once. The kernels follow exactly this arithmetic, so they are compared with it value for value; how far the mode
+# is from the reference (exact) mode is measured separately (tools/fused_census.py).
+FUSED_PATH_ORDER = (0, 4, 1, 3, 6, 2, 5, 7)   # down, down-right, up (raw cost), left, down-left, right, up-right, up-left
+
+
+@njit(cache=True)
+def _sgm_step_f32(cvol, svol, row, col, ndisp, P1, P2, old, new, min_cost, min_cost_P2, restart):
+    inf = np.float32(np.inf)
+    if restart:
+        for d in range(ndisp):
+            new[d] = cvol[row, col, d]
+    else:
+        for d in range(ndisp):
+            pre = old[d - 1] if d > 0 else inf
+            nxt = old[d + 1] if d < ndisp - 1 else inf
+            a = min(pre, nxt) + P1
+            b = min(old[d], min_cost_P2)
+            new[d] = cvol[row, col, d] + (min(a, b) - min_cost)
+    for d in range(ndisp):
+        svol[row, col, d] = svol[row, col, d] + new[d]
+    m = new[0]
+    for d in range(1, ndisp):
+        m = min(m, new[d])
+    m = m + np.float32(0.0)
+    return m, m + P2
+
+
+@njit(parallel=True, cache=True)
+def sgm_path_f32(cvol, svol, pen, path):
+    """sgm_path with fp32 state (the fused mode's arithmetic); the "up" path (P1 = P2 = 0) is the plain add it reduces to."""
+    rows, cols, ndisp = cvol.shape
+    dy, dx, ch = _PATH_DY[path], _PATH_DX[path], _PATH_CH[path]
+    horizontal = dy == 0
+    nlines = rows if horizontal else cols
+    max_iter = (cols - 1) if horizontal else (rows - 1)
+    if path == 1:
+        for row in prange(1, rows):
+            for col in range(cols):
+                for d in range(ndisp):
+                    svol[row, col, d] = svol[row, col, d] + cvol[row, col, d]
+        return svol
+    for line in prange(nlines):
+        old = np.ones(ndisp, np.float32)
+        new = np.ones(ndisp, np.float32)
+        min_cost = np.float32(1.0)
+        min_cost_P2 = np.float32(1.0)
+        if horizontal:
+            row = np.int64(line)
+            col = np.int64(0) if dx > 0 else np.int64(cols - 1)
+        else:
+            row = np.int64(0) if dy > 0 else np.int64(rows - 1)
+            col = np.int64(line)
+        for it in range(max_iter):
+            restart = it == 0
+            if it > 0:
+                row += dy
+                col += dx
+                if col >= cols:
+                    col = 0
+                    restart = True
+                if col < 0:
+                    col = cols - 1
+                    restart = True
+            prow, pcol = row - dy, col - dx
+            P1 = np.float32(0.0)
+            if prow >= 0 and prow < rows and pcol >= 0 and pcol < cols:
+                P1 = pen[prow, pcol, ch]
+            P2 = pen[row, col, ch + 1]
+            min_cost, min_cost_P2 = _sgm_step_f32(cvol, svol, row, col, ndisp, P1, P2, old, new, min_cost, min_cost_P2, restart)
+            tmp = old
+            old = new
+            new = tmp
+    return svol
+
+
+def sgm_all_paths_fused(cl, cr, pen_l, pen_r):
+    """The fused mode's S volumes: fp32 state, contributions added in FUSED_PATH_ORDER."""
+    sl = np.zeros_like(cl)
+    sr = np.zeros_like(cr)
+    for p in FUSED_PATH_ORDER:
+        sgm_path_f32(cl, sl, pen_l, p)
+        sgm_path_f32(cr, sr, pen_r, p)
+    return sl, sr
+
+
 # --------------------------------------------------------------------------- WTA
 @njit(parallel=True, cache=True)
 def wta(svol):

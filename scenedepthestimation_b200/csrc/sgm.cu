@@ -26,6 +26,10 @@
 #include "common.cuh"
 
 namespace mccnn {
+// MCCNN_SGM_FUSED: csrc/sgm_fused.cu
+size_t sgm_fused_workspace_bytes(int H, int W, int D);
+int run_sgm_fused(const float* CL, const float* CR, const uint8_t* imageL, const uint8_t* imageR, float* SL, float* SR, float* dispL,
+                  float* dispR, void* workspace, int H, int W, int D, const mccnn_sgm_params* p, int keep_volumes, cudaStream_t stream);
 namespace {
 
 enum SgmMode { SGM_MID = 0, SGM_FIRST_FUSED = 1, SGM_LAST_WTA = 2 };
@@ -584,8 +588,10 @@ int check_common(const void* C, int H, int W, int D) {
 using namespace mccnn;
 
 extern "C" size_t mccnn_sgm_workspace_bytes(int H, int W, int D) {
-    (void)H; (void)W; (void)D;
-    return 256;  // 8 scanline counters
+    if (H < 1 || W < 1 || D < 1) return 0;
+    // exact mode: 64 words (scanline counters + the status word of sharded launches); the fused mode's hand-over rings and
+    // flags follow (one size for both modes, so that a workspace serves either)
+    return 256 + sgm_fused_workspace_bytes(H, W, D);
 }
 
 static int run_sgm(const float* CL, const float* CR, const uint8_t* imageL, const uint8_t* imageR, float* SL, float* SR,
@@ -688,11 +694,16 @@ extern "C" int mccnn_sgm(const float* CL, const float* CR, const uint8_t* imageL
     if (int e = check_common(CL, H, W, D)) return e;
     MCCNN_REQUIRE(CR && SL && SR && imageL && imageR && dispL && dispR && params && workspace, MCCNN_EINVAL,
                   "mccnn_sgm: null argument");
-    MCCNN_REQUIRE(mode == MCCNN_SGM_EXACT, MCCNN_EINVAL, "mccnn_sgm: unknown mode %d", mode);
+    MCCNN_REQUIRE(mode == MCCNN_SGM_EXACT || mode == MCCNN_SGM_FUSED, MCCNN_EINVAL, "mccnn_sgm: unknown mode %d", mode);
     MCCNN_REQUIRE(workspace_bytes >= mccnn_sgm_workspace_bytes(H, W, D), MCCNN_EWORKSPACE, "mccnn_sgm: workspace too small");
     MCCNN_REQUIRE(aligned16(CL) && aligned16(CR) && aligned16(SL) && aligned16(SR), MCCNN_EALIGN,
                   "mccnn_sgm: volumes must be 16-byte aligned");
     MCCNN_REQUIRE(params->P1 >= 0 && params->P1_red >= 0, MCCNN_EINVAL, "mccnn_sgm: negative P1");
+    if (mode == MCCNN_SGM_FUSED) {
+        MCCNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, MCCNN_EALIGN, "mccnn_sgm: workspace must be 256-byte aligned");
+        return run_sgm_fused(CL, CR, imageL, imageR, SL, SR, dispL, dispR, reinterpret_cast<char*>(workspace) + 256, H, W, D, params,
+                             keep_volumes, stream);
+    }
     return run_sgm(CL, CR, imageL, imageR, SL, SR, dispL, dispR, workspace, H, W, D, params, keep_volumes, nullptr, 0x7f, stream);
 }
 
@@ -713,8 +724,8 @@ extern "C" int mccnn_sgm_sharded(const float* CLb, const float* CRb, const uint8
     if (int e = check_common(CLb, H, W, D)) return e;
     MCCNN_REQUIRE(CRb && SLb && SRb && imageL && imageR && dispLb && dispRb && params && workspace, MCCNN_EINVAL,
                   "mccnn_sgm_sharded: null argument");
-    MCCNN_REQUIRE(mode == MCCNN_SGM_EXACT, MCCNN_EINVAL, "mccnn_sgm_sharded: unknown mode %d", mode);
-    MCCNN_REQUIRE(workspace_bytes >= mccnn_sgm_workspace_bytes(H, W, D), MCCNN_EWORKSPACE, "mccnn_sgm_sharded: workspace too small");
+    MCCNN_REQUIRE(mode == MCCNN_SGM_EXACT, MCCNN_EINVAL, "mccnn_sgm_sharded: mode %d is not supported (exact only)", mode);
+    MCCNN_REQUIRE(workspace_bytes >= 256, MCCNN_EWORKSPACE, "mccnn_sgm_sharded: workspace too small");
     MCCNN_REQUIRE(aligned16(CLb) && aligned16(CRb) && aligned16(SLb) && aligned16(SRb), MCCNN_EALIGN,
                   "mccnn_sgm_sharded: volumes must be 16-byte aligned");
     MCCNN_REQUIRE(shard->world >= 1 && shard->rank >= 0 && shard->rank < shard->world && shard->rows >= 1 && shard->row0 >= 0 &&

@@ -1,0 +1,730 @@
+// Semi-global matching, FUSED mode (MCCNN_SGM_FUSED, sm_100a): the 8 paths in 4 sweeps instead of the exact mode's 7 passes.
+//
+// Same recurrence, traversal extents, column wraps, restarts and penalty rule as the reference (SGM_Interation,
+// process_functional.py:265-343; the 8 path kernels :346-797; penalties :134-262; WTA :800-837) -- see sgm.cu for the
+// contract. What this mode gives up, and why it is opt-in: the reference keeps the path state in fp64 and rounds S to fp32
+// once per path IN LAUNCH ORDER (:1166-1202), which forces one read-modify-write pass of S per path (76 B per evaluation and
+// side, sgm.cu). Here the path state is fp32 and the contributions are added into S in the order
+//     down, down-right, up (raw cost), left, down-left, right, up-right, up-left
+// so that two paths share every sweep: 8 + 12 + 12 + 8 = 40 B per evaluation and side. oracle/stereo.py::sgm_all_paths_fused
+// restates exactly this arithmetic (the kernels are compared with it value for value); tools/fused_census.py measures the
+// distance to the exact mode.
+//
+// Sweep structure. A sweep pairs a path that runs ALONG a unit (a column for sweep 0, an image row for sweeps 1 and 2; its
+// state never leaves the owning warp's registers) with the diagonal path whose predecessor pixel is the previous step of
+// the NEIGHBOURING unit:
+//     sweep 0: unit = column x, steps down the rows:      down (own)  + down-right (from column x-1, row y-1) + raw cost
+//     sweep 1: unit = row y,    steps from right to left: left (own)  + down-left  (from row y-1, column x+1)
+//     sweep 2: unit = row y,    steps from left to right: right (own) + up-right   (from row y+1, column x-1)
+//     sweep 3: unit = diagonal scanline (as in sgm.cu):   up-left + winner-takes-all, nothing handed over
+// One warp owns a unit; lane l holds NPL consecutive disparities. Unit u at step t needs the diagonal state unit u-1 produced
+// at step t-1, so the warps of a chain advance in lock step, each one step behind nothing: the hand-over only makes a warp
+// wait when its neighbour is late. The state (one row of D floats + its minimum) travels through a 2-slot ring in shared
+// memory between warps of a CTA, through an 8-slot ring in global memory (L2-resident) between the last warp of a CTA and
+// the first warp of the next one, and through a T-slot global buffer from the last warp of the chain to the first one,
+// which by then works on the next round of units (unit u -> warp u mod n). The grid is launched cooperatively: every warp
+// of a chain must be resident.
+// Cost and S rows stream through shared memory with 1-D bulk copies + mbarriers, as in sgm.cu.
+#include "common.cuh"
+
+namespace mccnn {
+namespace {
+
+constexpr int FW = 8;       // warps per CTA of the chain kernel
+constexpr int RING = 2;     // hand-over slots between warps of one CTA (shared memory)
+constexpr int GRING = 8;    // hand-over slots between neighbouring CTAs (global memory)
+constexpr int FSTAGES = 2;  // rows in flight per warp and stream
+constexpr int FLAG_STRIDE = 32;  // unsigned words between two flags (one 128-byte line each)
+constexpr int MAX_CHAIN_CTAS = 512;
+constexpr float kInf = __builtin_huge_valf();
+
+struct FusedArgs {
+    const float* C[2];
+    float* S[2];
+    const unsigned char* img[2];
+    float* disp[2];
+    int H, W, D, Dp;
+    int sweep;        // 0, 1, 2: see above
+    int U, T;         // units per side, steps per unit
+    int ctas;         // CTAs per chain (one chain per side)
+    float P1, P2, P1r, P2r;
+    int threshold;
+    int subpixel;
+    int store_s;
+    float* glink;     // global hand-over buffers of this launch: [side][ctas x GRING slots | wrap: T slots][slot_floats]
+    unsigned* gflags; // [side][ctas][2][FLAG_STRIDE]: produced / consumed counters of the link leaving CTA c
+    int slot_floats;  // 32 * NPL + 4
+    unsigned* counter;  // sweep 3: scanline counter
+};
+
+// ------------------------------------------------------------------------------------------------ small device helpers
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_cta_smem(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_smem(unsigned* p, unsigned v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ float warp_min_f32(float v) {
+    int k = __float_as_int(v);
+    k ^= (k >> 31) & 0x7fffffff;  // order-preserving float -> int
+    k = __reduce_min_sync(0xffffffffu, k);
+    k ^= (k >> 31) & 0x7fffffff;
+    return __int_as_float(k) + 0.0f;  // -0 and +0 are one value
+}
+
+template <int N>
+__device__ __forceinline__ float tree_min_f32(const float (&v)[N]) {
+    float t[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = v[i];
+#pragma unroll
+    for (int stride = 1; stride < N; stride *= 2)
+#pragma unroll
+        for (int i = 0; i + stride < N; i += 2 * stride) t[i] = fminf(t[i], t[i + stride]);
+    return t[0];
+}
+
+template <int NPL>
+__device__ __forceinline__ void load_row(const float* buf, int lane, float (&v)[NPL]) {
+    const float* p = buf + lane * NPL;
+    if constexpr (NPL % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < NPL / 4; j++) {
+            const float4 q = reinterpret_cast<const float4*>(p)[j];
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+        }
+    } else if constexpr (NPL % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < NPL / 2; j++) {
+            const float2 q = reinterpret_cast<const float2*>(p)[j];
+            v[2 * j] = q.x; v[2 * j + 1] = q.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPL; j++) v[j] = p[j];
+    }
+}
+
+template <int NPL>
+__device__ __forceinline__ void store_row(float* buf, int lane, const float (&v)[NPL]) {
+    float* p = buf + lane * NPL;
+    if constexpr (NPL % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < NPL / 4; j++)
+            reinterpret_cast<float4*>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else if constexpr (NPL % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < NPL / 2; j++) reinterpret_cast<float2*>(p)[j] = make_float2(v[2 * j], v[2 * j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPL; j++) p[j] = v[j];
+    }
+}
+
+// global-memory twins (L2 only: the other SM's data must never be served from this SM's L1)
+template <int NPL>
+__device__ __forceinline__ void load_row_cg(const float* buf, int lane, float (&v)[NPL]) {
+    const float* p = buf + lane * NPL;
+    if constexpr (NPL % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < NPL / 4; j++) {
+            const float4 q = __ldcg(reinterpret_cast<const float4*>(p) + j);
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPL; j++) v[j] = __ldcg(p + j);
+    }
+}
+template <int NPL>
+__device__ __forceinline__ void store_row_cg(float* buf, int lane, const float (&v)[NPL]) {
+    float* p = buf + lane * NPL;
+    if constexpr (NPL % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < NPL / 4; j++)
+            __stcg(reinterpret_cast<float4*>(p) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPL; j++) __stcg(p + j, v[j]);
+    }
+}
+
+// One step of the recurrence, in place: L <- c + (min(min(L[d-1], L[d+1]) + P1, L[d], minL + P2) - minL).
+// min(a + P1, b + P1) == min(a, b) + P1 in floating point (rounding is monotonic). Out-of-range neighbours are +INF: the
+// reference's clamps L[-1] -> L[0], L[D] -> L[D-1] (:300-303) never win against L[d] itself.
+template <int NPL>
+__device__ __forceinline__ void dp_step(float (&L)[NPL], const float (&c)[NPL], float minL, float P1, float P2, int lane) {
+    float up = __shfl_up_sync(0xffffffffu, L[NPL - 1], 1);
+    float dn = __shfl_down_sync(0xffffffffu, L[0], 1);
+    if (lane == 0) up = kInf;
+    if (lane == 31) dn = kInf;
+    const float mp2 = minL + P2;
+    float prev = up;
+#pragma unroll
+    for (int j = 0; j < NPL; j++) {
+        const float next = (j + 1 < NPL) ? L[j + 1 < NPL ? j + 1 : j] : dn;
+        const float m = fminf(fminf(prev, next) + P1, fminf(L[j], mp2));
+        prev = L[j];
+        L[j] = c[j] + (m - minL);
+    }
+}
+
+// first strict minimum over d of this warp's row (:805-811), optional parabola refinement (:813-819), as in sgm.cu
+__device__ __forceinline__ float subpixel_refine_f(int idx, int D, float cm, float c, float cp) {
+    if (idx <= 0 || idx >= D - 1) return (float)idx;
+    const float num = cp - cm;
+    const double den = 2.0 * ((double)(cm + cp) - 2.0 * (double)c);
+    if (!(den > 0.0)) return (float)idx;
+    return (float)((double)idx - (double)num / den);
+}
+
+template <int NPL>
+__device__ __forceinline__ float warp_wta(const float (&so)[NPL], int lane, int D, int subpixel) {
+    const int d0 = lane * NPL;
+    float best = kInf, bl = 0.f, br = 0.f;
+    int bj = 0;
+    {
+        best = fminf(tree_min_f32<NPL>(so), best) + 0.0f;
+        unsigned hit[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < NPL; j++) hit[j & 3] |= (so[j] == best) ? (1u << j) : 0u;
+        const unsigned any = (hit[0] | hit[1]) | (hit[2] | hit[3]);
+        bj = any ? __ffs(any) - 1 : 0;
+    }
+    if (subpixel) {
+        float left = __shfl_up_sync(0xffffffffu, so[NPL - 1], 1);
+        const float right_edge = __shfl_down_sync(0xffffffffu, so[0], 1);
+#pragma unroll
+        for (int j = 0; j < NPL; j++) {
+            const float nxt = (j + 1 < NPL) ? so[j + 1 < NPL ? j + 1 : j] : right_edge;
+            if (j == bj) { bl = left; br = nxt; }
+            left = so[j];
+        }
+    }
+    int k = __float_as_int(best);
+    k ^= (k >> 31) & 0x7fffffff;
+    const int mk = __reduce_min_sync(0xffffffffu, k);
+    const unsigned who = __ballot_sync(0xffffffffu, k == mk);
+    const int src = __ffs(who) - 1;
+    const int idx = __shfl_sync(0xffffffffu, d0 + bj, src);
+    float outv = (float)idx;
+    if (subpixel) {
+        const float c = __shfl_sync(0xffffffffu, best, src);
+        const float cm = __shfl_sync(0xffffffffu, bl, src), cp = __shfl_sync(0xffffffffu, br, src);
+        outv = subpixel_refine_f(idx, D, cm, c, cp);
+    }
+    return outv;
+}
+
+// ------------------------------------------------------------------------------------------------ sweeps 0, 1, 2
+template <int NPL, bool READS>
+__global__ void __launch_bounds__(FW * 32) sgm_chain_kernel(const FusedArgs a) {
+    constexpr int ROWF = 32 * NPL;
+    constexpr int NIN = READS ? 2 : 1;
+    constexpr int PER_WARP = ROWF * (FSTAGES * NIN + 1 + RING);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* wbase = reinterpret_cast<float*>(smem_raw) + (size_t)warp * PER_WARP;
+    float* inbuf = wbase;                            // [FSTAGES][NIN][ROWF]
+    float* outbuf = wbase + ROWF * FSTAGES * NIN;    // [ROWF]
+    float* ring = outbuf + ROWF;                     // [RING][ROWF]: the link warp -> warp + 1
+    float* tail = reinterpret_cast<float*>(smem_raw) + (size_t)FW * PER_WARP;
+    float* ringmin = tail;                                                       // [FW][RING]
+    unsigned* prodc = reinterpret_cast<unsigned*>(tail + FW * RING);             // [FW] rows published on the link leaving warp w
+    unsigned* consc = prodc + FW;                                                // [FW] rows the reader of that link is done with
+    uint64_t* bars = reinterpret_cast<uint64_t*>(consc + FW) + warp * FSTAGES;   // (FW * (RING + 2) floats: a multiple of 8 bytes)
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < FSTAGES; s++) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+        prodc[warp] = 0u;
+        consc[warp] = 0u;
+    }
+    // tails [Dp, 32 * NPL) of the row buffers stay +INF for ever (the bulk copies bring Dp floats): those disparities never win
+    for (int i = lane; i < ROWF * FSTAGES * NIN; i += 32) inbuf[i] = kInf;
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    const int side = blockIdx.x / a.ctas, cta = blockIdx.x - side * a.ctas;
+    const int n = a.ctas * FW;                 // warps of this chain
+    const int w = cta * FW + warp;             // position in the chain
+    const float* __restrict__ Cv = a.C[side];
+    float* __restrict__ Sv = a.S[side];
+    const unsigned char* __restrict__ img = a.img[side];
+    const int W = a.W, H = a.H, T = a.T;
+    const uint32_t copy_bytes = (uint32_t)a.Dp * 4u;
+    const size_t pitch = (size_t)a.Dp;
+
+    // links. The one that leaves CTA c for CTA c + 1 is global link c; link ctas - 1 closes the ring (T slots).
+    const bool in_local = warp > 0, out_local = warp < FW - 1;
+    const int lin = cta == 0 ? a.ctas - 1 : cta - 1, lout = cta;
+    const size_t side_floats = ((size_t)a.ctas * GRING + (size_t)T) * a.slot_floats;
+    auto link_base = [&](int l) { return a.glink + (size_t)side * side_floats + (size_t)l * GRING * a.slot_floats; };
+    const unsigned depth_in = in_local ? RING : (lin == a.ctas - 1 ? (unsigned)T : GRING);
+    const unsigned depth_out = out_local ? RING : (lout == a.ctas - 1 ? (unsigned)T : GRING);
+    const float* gin = link_base(lin);
+    float* gout = link_base(lout);
+    unsigned* gprod_in = a.gflags + ((size_t)(side * a.ctas + lin) * 2 + 0) * FLAG_STRIDE;
+    unsigned* gcons_in = a.gflags + ((size_t)(side * a.ctas + lin) * 2 + 1) * FLAG_STRIDE;
+    unsigned* gprod_out = a.gflags + ((size_t)(side * a.ctas + lout) * 2 + 0) * FLAG_STRIDE;
+    unsigned* gcons_out = a.gflags + ((size_t)(side * a.ctas + lout) * 2 + 1) * FLAG_STRIDE;
+    const float* lring_in = ring - PER_WARP;   // the previous warp's ring (only dereferenced when in_local)
+
+    // geometry of the sweep: pixel(u, t), the step along the unit and the offset to the neighbouring unit's pixel
+    const int dpix = a.sweep == 0 ? W : (a.sweep == 1 ? -1 : 1);
+    const int upoff = a.sweep == 0 ? -1 : (a.sweep == 1 ? -W : W);
+
+    uint32_t gstep = 0;  // rows consumed by this warp so far (stage ring position / mbarrier phase)
+
+    int round = 0;
+    for (int u = w; u < a.U; u += n, round++) {
+        const long long pix0 = a.sweep == 0 ? (long long)u : (a.sweep == 1 ? (long long)u * W + (W - 1) : (long long)(H - 1 - u) * W);
+        const bool has_up = u >= 1;
+        const bool diag_unit = a.sweep == 0 ? true : (u <= a.U - 2);
+        // the producer of my input link works on unit u - 1: same round, or the previous one across the closing link
+        const unsigned qbase_in = (unsigned)((w == 0 ? round - 1 : round)) * (unsigned)T;   // only used when has_up
+        const unsigned qbase_out = (unsigned)round * (unsigned)T;
+
+        long long lpix = pix0;  // pixel of the next row to prefetch
+        auto issue_load = [&](uint32_t g) {
+            const size_t off = (size_t)lpix * pitch;
+            const int st = g % FSTAGES;
+            float* dst = inbuf + (size_t)st * NIN * ROWF;
+            mbar_expect_tx_elect(&bars[st], copy_bytes * NIN);
+            bulk_g2s_elect(dst, Cv + off, copy_bytes, &bars[st]);
+            if constexpr (READS) bulk_g2s_elect(dst + ROWF, Sv + off, copy_bytes, &bars[st]);
+            lpix += dpix;
+        };
+        {
+            const int pre = min(FSTAGES, T);
+            for (int k = 0; k < pre; k++) issue_load(gstep + k);
+        }
+        // image values of the next 32 steps of this unit and of the neighbouring unit (lane l: step tb + l)
+        auto img_own = [&](int t) -> int { return (int)img[pix0 + (long long)min(t, T - 1) * dpix]; };
+        auto img_up = [&](int t) -> int { return has_up ? (int)img[pix0 + upoff + (long long)min(t, T - 1) * dpix] : 0; };
+        int blk_own = img_own(lane), blk_up = img_up(lane);
+        int nblk_own = img_own(32 + lane), nblk_up = img_up(32 + lane);
+        int i_prev_own = 0, i_prev_up = 0;
+
+        float Lo[NPL];   // state of the path that runs along this unit
+        float mo = 0.f;
+#pragma unroll
+        for (int j = 0; j < NPL; j++) Lo[j] = 0.f;
+
+        long long pix = pix0;
+        for (int t = 0; t < T; t++, pix += dpix) {
+            const int st = gstep % FSTAGES;
+            mbar_wait(&bars[st], (gstep / FSTAGES) & 1u);
+            float cf[NPL], so[NPL];
+            const float* ib = inbuf + (size_t)st * NIN * ROWF;
+            load_row<NPL>(ib, lane, cf);
+            if constexpr (READS) load_row<NPL>(ib + ROWF, lane, so);
+
+            if ((t & 31) == 0 && t > 0) {
+                blk_own = nblk_own; blk_up = nblk_up;
+                nblk_own = img_own(t + 32 + lane); nblk_up = img_up(t + 32 + lane);
+            }
+            const int i_cur = __shfl_sync(0xffffffffu, blk_own, t & 31);
+            const int i_upcur = __shfl_sync(0xffffffffu, blk_up, t & 31);
+
+            const bool own_active = t <= T - 2;
+            const bool diag_active = diag_unit && (a.sweep != 0 || t <= T - 2);
+
+            // ---- the path along the unit
+            if (own_active) {
+                if (t == 0) {
+#pragma unroll
+                    for (int j = 0; j < NPL; j++) Lo[j] = cf[j];
+                } else {
+                    const int dn = i_cur - i_prev_own;
+                    const bool full = (dn >= 0) && (dn <= a.threshold);
+                    dp_step<NPL>(Lo, cf, mo, full ? a.P1 : a.P1r, full ? a.P2 : a.P2r, lane);
+                }
+                mo = warp_min_f32(tree_min_f32<NPL>(Lo));
+            }
+            if constexpr (READS) {
+                if (own_active) {
+#pragma unroll
+                    for (int j = 0; j < NPL; j++) so[j] = so[j] + Lo[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NPL; j++) so[j] = own_active ? Lo[j] : 0.0f;
+            }
+
+            // ---- the diagonal path: predecessor = step t - 1 of unit u - 1
+            if (diag_active) {
+                float Ld[NPL];
+                float md;
+                if (t == 0 || !has_up) {
+#pragma unroll
+                    for (int j = 0; j < NPL; j++) Ld[j] = cf[j];
+                } else {
+                    const unsigned q = qbase_in + (unsigned)(t - 1);   // index of the row I need on my input link
+                    if (in_local) {
+                        if (lane == 0)
+                            while (ld_acquire_cta_smem(&prodc[warp - 1]) < q + 1u) __nanosleep(20);
+                        __syncwarp();
+                        const unsigned slot = q % RING;
+                        load_row<NPL>(lring_in + (size_t)slot * ROWF, lane, Ld);
+                        md = ringmin[(warp - 1) * RING + slot];
+                    } else {
+                        if (lane == 0) {
+                            while (ld_relaxed_gpu(gprod_in) < q + 1u) __nanosleep(40);
+                            fence_acq_rel_gpu();
+                        }
+                        __syncwarp();
+                        const float* src = gin + (size_t)(q % depth_in) * a.slot_floats;
+                        load_row_cg<NPL>(src, lane, Ld);
+                        md = __ldcg(src + ROWF);
+                    }
+                    const int dn = i_cur - i_prev_up;
+                    const bool full = (dn >= 0) && (dn <= a.threshold);
+                    dp_step<NPL>(Ld, cf, md, full ? a.P1 : a.P1r, full ? a.P2 : a.P2r, lane);
+                }
+                md = warp_min_f32(tree_min_f32<NPL>(Ld));
+#pragma unroll
+                for (int j = 0; j < NPL; j++) so[j] = so[j] + Ld[j];
+
+                // hand the new state to unit u + 1 (row qo of my output link), once its reader is done with the slot
+                const unsigned qo = qbase_out + (unsigned)t;
+                if (out_local) {
+                    if (qo + 1u > RING) {
+                        if (lane == 0)
+                            while (ld_acquire_cta_smem(&consc[warp]) < qo + 1u - RING) __nanosleep(20);   // (0xffffffff = reader gone)
+                        __syncwarp();
+                    }
+                    const unsigned slot = qo % RING;
+                    store_row<NPL>(ring + (size_t)slot * ROWF, lane, Ld);
+                    if (lane == 0) ringmin[warp * RING + slot] = md;
+                    __syncwarp();
+                    if (lane == 0) st_release_cta_smem(&prodc[warp], qo + 1u);
+                } else {
+                    if (qo + 1u > depth_out) {
+                        if (lane == 0) {
+                            while (ld_relaxed_gpu(gcons_out) < qo + 1u - depth_out) __nanosleep(40);
+                            fence_acq_rel_gpu();
+                        }
+                        __syncwarp();
+                    }
+                    float* dst = gout + (size_t)(qo % depth_out) * a.slot_floats;
+                    store_row_cg<NPL>(dst, lane, Ld);
+                    if (lane == 0) __stcg(dst + ROWF, md);
+                    __syncwarp();
+                    if (lane == 0) {
+                        fence_acq_rel_gpu();
+                        st_relaxed_gpu(gprod_out, qo + 1u);
+                    }
+                }
+            }
+            // my input link: everything up to the row of step t - 1 is consumed (whether it was needed or not)
+            if (has_up && t >= 1 && !(w == 0 && round == 0)) {
+                __syncwarp();
+                if (lane == 0) {
+                    if (in_local) {
+                        st_release_cta_smem(&consc[warp - 1], qbase_in + (unsigned)t);
+                    } else {
+                        fence_acq_rel_gpu();
+                        st_relaxed_gpu(gcons_in, qbase_in + (unsigned)t);
+                    }
+                }
+            }
+
+            // ---- the "up" path adds the raw cost on rows >= 1 (its penalties are never written, sgm.cu); sweep 0 only
+            if constexpr (!READS) {
+                if (t >= 1) {  // sweep 0: y = t
+#pragma unroll
+                    for (int j = 0; j < NPL; j++) so[j] = so[j] + cf[j];
+                }
+            }
+
+            // ---- S row out: staged, one bulk store per row
+            bulk_wait_read_elect<0>();  // the store of the previous step has left the staging row
+            __syncwarp();
+            store_row<NPL>(outbuf, lane, so);
+            fence_proxy_async_smem();
+            __syncwarp();
+            bulk_s2g_commit_elect(Sv + (size_t)pix * pitch, outbuf, copy_bytes);
+
+            i_prev_own = i_cur;
+            i_prev_up = i_upcur;
+            __syncwarp();   // every lane has consumed the stage: refill it
+            if (t + FSTAGES < T) issue_load(gstep + FSTAGES);
+            gstep++;
+        }
+        // the unit is done: its input link is consumed to the end of the producer's round
+        if (has_up && !(w == 0 && round == 0)) {
+            __syncwarp();
+            if (lane == 0) {
+                if (in_local) {
+                    st_release_cta_smem(&consc[warp - 1], qbase_in + (unsigned)T);
+                } else {
+                    fence_acq_rel_gpu();
+                    st_relaxed_gpu(gcons_in, qbase_in + (unsigned)T);
+                }
+            }
+        }
+    }
+    // no more units for this warp: whatever still arrives on its input link is not needed
+    __syncwarp();
+    if (lane == 0) {
+        if (in_local) {
+            st_release_cta_smem(&consc[warp - 1], 0xffffffffu);
+        } else {
+            fence_acq_rel_gpu();
+            st_relaxed_gpu(gcons_in, 0xffffffffu);
+        }
+    }
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.wait_group 0;\n\t"
+        "}" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ sweep 3
+// up-left path + winner-takes-all: one warp per diagonal scanline (start column at the bottom row, column - 1 per step,
+// wrapping modulo W with a restart), S is read, the sum goes to the WTA and, if asked for, back to S.
+constexpr int LW = 4;  // warps per CTA
+
+template <int NPL, bool STORE>
+__global__ void __launch_bounds__(LW * 32) sgm_fused_last_kernel(const FusedArgs a) {
+    constexpr int ROWF = 32 * NPL;
+    constexpr int PER_WARP = ROWF * (FSTAGES * 2 + (STORE ? 1 : 0));
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* wbase = reinterpret_cast<float*>(smem_raw) + (size_t)warp * PER_WARP;
+    float* inbuf = wbase;
+    float* outbuf = wbase + ROWF * FSTAGES * 2;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)LW * PER_WARP * sizeof(float)) + warp * FSTAGES;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < FSTAGES; s++) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    for (int i = lane; i < ROWF * FSTAGES * 2; i += 32) inbuf[i] = kInf;
+    fence_proxy_async_smem();
+    __syncwarp();
+
+    const int W = a.W, H = a.H;
+    const uint32_t copy_bytes = (uint32_t)a.Dp * 4u;
+    const size_t pitch = (size_t)a.Dp;
+    uint32_t gstep = 0;
+    for (;;) {
+        unsigned q = 0;
+        if (lane == 0) q = atomicAdd(a.counter, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= 2u * (unsigned)W) break;
+        const int side = (int)q / W, line = (int)q - side * W;
+        const float* __restrict__ Cv = a.C[side];
+        float* __restrict__ Sv = a.S[side];
+        const unsigned char* __restrict__ img = a.img[side];
+        auto col_at = [&](int t) -> int {
+            int c = (line - t) % W;
+            return c < 0 ? c + W : c;
+        };
+        int lrow = H - 1, lcol = line;
+        auto issue_load = [&](uint32_t g) {
+            const size_t off = ((size_t)lrow * W + lcol) * pitch;
+            const int st = g % FSTAGES;
+            float* dst = inbuf + (size_t)st * 2 * ROWF;
+            mbar_expect_tx_elect(&bars[st], copy_bytes * 2);
+            bulk_g2s_elect(dst, Cv + off, copy_bytes, &bars[st]);
+            bulk_g2s_elect(dst + ROWF, Sv + off, copy_bytes, &bars[st]);
+            lrow -= 1;
+            lcol = lcol == 0 ? W - 1 : lcol - 1;
+        };
+        {
+            const int pre = min(FSTAGES, H);
+            for (int k = 0; k < pre; k++) issue_load(gstep + k);
+        }
+        auto image_at = [&](int t) -> int {
+            const int tt = min(t, H - 1);
+            return (int)img[(size_t)(H - 1 - tt) * W + col_at(tt)];
+        };
+        int blk = image_at(lane), nblk = image_at(32 + lane);
+        int i_prev = 0;
+        float L[NPL];
+        float mL = 0.f;
+#pragma unroll
+        for (int j = 0; j < NPL; j++) L[j] = 0.f;
+        int row = H - 1, col = line;
+        for (int t = 0; t < H; t++) {
+            const int st = gstep % FSTAGES;
+            mbar_wait(&bars[st], (gstep / FSTAGES) & 1u);
+            float cf[NPL], so[NPL];
+            const float* ib = inbuf + (size_t)st * 2 * ROWF;
+            load_row<NPL>(ib, lane, cf);
+            load_row<NPL>(ib + ROWF, lane, so);
+            if ((t & 31) == 0 && t > 0) {
+                blk = nblk;
+                nblk = image_at(t + 32 + lane);
+            }
+            const int i_cur = __shfl_sync(0xffffffffu, blk, t & 31);
+            if (t <= H - 2) {
+                if (t == 0 || col == W - 1) {   // first pixel, or the scanline has just wrapped around the image
+#pragma unroll
+                    for (int j = 0; j < NPL; j++) L[j] = cf[j];
+                } else {
+                    const int dn = i_cur - i_prev;
+                    const bool full = (dn >= 0) && (dn <= a.threshold);
+                    dp_step<NPL>(L, cf, mL, full ? a.P1 : a.P1r, full ? a.P2 : a.P2r, lane);
+                }
+                mL = warp_min_f32(tree_min_f32<NPL>(L));
+#pragma unroll
+                for (int j = 0; j < NPL; j++) so[j] = so[j] + L[j];
+            }
+            i_prev = i_cur;
+            if constexpr (STORE) {
+                bulk_wait_read_elect<0>();
+                __syncwarp();
+                store_row<NPL>(outbuf, lane, so);
+                fence_proxy_async_smem();
+                __syncwarp();
+                bulk_s2g_commit_elect(Sv + ((size_t)row * W + col) * pitch, outbuf, copy_bytes);
+            }
+            const float outv = warp_wta<NPL>(so, lane, a.D, a.subpixel);
+            if (lane == 0) a.disp[side][(size_t)row * W + col] = outv;
+            __syncwarp();
+            if (t + FSTAGES < H) issue_load(gstep + FSTAGES);
+            gstep++;
+            row -= 1;
+            col = col == 0 ? W - 1 : col - 1;
+        }
+    }
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.wait_group 0;\n\t"
+        "}" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+inline int npl_for(int D) {
+    static const int kSizes[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 13, 16, 20, 25, 32};
+    const int need = ceil_div(D, 32);
+    for (int s : kSizes)
+        if (need <= s) return s;
+    return 0;
+}
+
+struct FusedLayout {
+    size_t flags, counter, links, end;
+    int slot_floats;
+};
+
+FusedLayout fused_layout(int H, int W, int D) {
+    FusedLayout l{};
+    const int npl = npl_for(D);
+    l.slot_floats = 32 * (npl ? npl : 32) + 4;
+    size_t o = 0;
+    l.flags = o; o += (size_t)3 * 2 * MAX_CHAIN_CTAS * 2 * FLAG_STRIDE * sizeof(unsigned);   // 3 sweeps x 2 sides x links x {prod, cons}
+    l.counter = o; o += 256;
+    l.links = o; o += (size_t)2 * ((size_t)MAX_CHAIN_CTAS * GRING + (size_t)(H > W ? H : W)) * l.slot_floats * sizeof(float);
+    l.end = (o + 255) & ~(size_t)255;
+    return l;
+}
+
+template <int NPL, bool READS>
+int launch_chain(FusedArgs a, cudaStream_t stream) {
+    constexpr int ROWF = 32 * NPL;
+    constexpr int NIN = READS ? 2 : 1;
+    const size_t smem = (size_t)FW * ROWF * (FSTAGES * NIN + 1 + RING) * sizeof(float) + (size_t)FW * (RING + 2) * sizeof(float) +
+                        (size_t)FW * FSTAGES * sizeof(uint64_t);
+    int per_sm = 0;
+    if (int e = kernel_setup<sgm_chain_kernel<NPL, READS>>(FW * 32, smem, &per_sm)) return e;
+    MCCNN_REQUIRE(per_sm >= 1, MCCNN_EINVAL, "sgm_chain_kernel<%d>: does not fit on an SM (smem %zu)", NPL, smem);
+    int ctas = (sm_count() * per_sm) / 2;   // one chain per side; every CTA must be resident (cooperative launch)
+    if (ctas > MAX_CHAIN_CTAS) ctas = MAX_CHAIN_CTAS;
+    const int need = ceil_div(a.U, FW);
+    if (ctas > need) ctas = need;
+    // full rounds: the units of a side are dealt to ctas * FW warps; keep the last round as full as the others
+    const int rounds = ceil_div(a.U, ctas * FW);
+    ctas = ceil_div(ceil_div(a.U, rounds), FW);
+    MCCNN_REQUIRE(ctas >= 1, MCCNN_EINVAL, "sgm_chain_kernel: no resident CTA available");
+    a.ctas = ctas;
+    void* params[] = {&a};
+    MCCNN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sgm_chain_kernel<NPL, READS>), dim3(2 * ctas), dim3(FW * 32), params,
+                                           smem, stream));
+    return 0;
+}
+
+template <int NPL, bool STORE>
+int launch_last(const FusedArgs& a, cudaStream_t stream) {
+    constexpr int ROWF = 32 * NPL;
+    const size_t smem = (size_t)LW * ROWF * (FSTAGES * 2 + (STORE ? 1 : 0)) * sizeof(float) + (size_t)LW * FSTAGES * sizeof(uint64_t);
+    int per_sm = 0;
+    if (int e = kernel_setup<sgm_fused_last_kernel<NPL, STORE>>(LW * 32, smem, &per_sm)) return e;
+    MCCNN_REQUIRE(per_sm >= 1, MCCNN_EINVAL, "sgm_fused_last_kernel<%d>: does not fit on an SM (smem %zu)", NPL, smem);
+    int grid = sm_count() * per_sm;
+    const int need = ceil_div(2 * a.W, LW);
+    if (grid > need) grid = need;
+    sgm_fused_last_kernel<NPL, STORE><<<grid, LW * 32, smem, stream>>>(a);
+    MCCNN_LAUNCH_CHECK("sgm_fused_last_kernel");
+    return 0;
+}
+
+template <int NPL>
+int run_fused_npl(FusedArgs a, int keep_volumes, cudaStream_t stream, unsigned* flags) {
+    for (int sweep = 0; sweep < 3; sweep++) {
+        a.sweep = sweep;
+        a.U = sweep == 0 ? a.W : a.H;
+        a.T = sweep == 0 ? a.H : a.W;
+        a.gflags = flags + (size_t)sweep * 2 * MAX_CHAIN_CTAS * 2 * FLAG_STRIDE;
+        if (int e = (sweep == 0 ? launch_chain<NPL, false>(a, stream) : launch_chain<NPL, true>(a, stream))) return e;
+    }
+    a.store_s = keep_volumes;
+    return keep_volumes ? launch_last<NPL, true>(a, stream) : launch_last<NPL, false>(a, stream);
+}
+
+}  // namespace
+
+size_t sgm_fused_workspace_bytes(int H, int W, int D) { return fused_layout(H, W, D).end; }
+
+int run_sgm_fused(const float* CL, const float* CR, const uint8_t* imageL, const uint8_t* imageR, float* SL, float* SR, float* dispL,
+                  float* dispR, void* workspace, int H, int W, int D, const mccnn_sgm_params* p, int keep_volumes,
+                  cudaStream_t stream) {
+    const FusedLayout l = fused_layout(H, W, D);
+    char* ws = reinterpret_cast<char*>(workspace);
+    MCCNN_CUDA(cudaMemsetAsync(ws + l.flags, 0, l.links - l.flags, stream));
+    FusedArgs a{};
+    a.C[0] = CL; a.C[1] = CR;
+    a.S[0] = SL; a.S[1] = SR;
+    a.img[0] = imageL; a.img[1] = imageR;
+    a.disp[0] = dispL; a.disp[1] = dispR;
+    a.H = H; a.W = W; a.D = D; a.Dp = disp_pitch(D);
+    a.P1 = p->P1; a.P2 = p->P2; a.P1r = p->P1_red; a.P2r = p->P2_red;
+    a.threshold = p->threshold;
+    a.subpixel = p->subpixel;
+    a.glink = reinterpret_cast<float*>(ws + l.links);
+    a.slot_floats = l.slot_floats;
+    a.counter = reinterpret_cast<unsigned*>(ws + l.counter);
+    unsigned* flags = reinterpret_cast<unsigned*>(ws + l.flags);
+    switch (npl_for(D)) {
+#define MCCNN_FUSED_CASE(N) \
+    case N: return run_fused_npl<N>(a, keep_volumes, stream, flags);
+        MCCNN_FUSED_CASE(1) MCCNN_FUSED_CASE(2) MCCNN_FUSED_CASE(3) MCCNN_FUSED_CASE(4) MCCNN_FUSED_CASE(5) MCCNN_FUSED_CASE(6)
+        MCCNN_FUSED_CASE(7) MCCNN_FUSED_CASE(8) MCCNN_FUSED_CASE(10) MCCNN_FUSED_CASE(13) MCCNN_FUSED_CASE(16) MCCNN_FUSED_CASE(20)
+        MCCNN_FUSED_CASE(25) MCCNN_FUSED_CASE(32)
+#undef MCCNN_FUSED_CASE
+    }
+    set_error("sgm (fused): D=%d exceeds the supported maximum of 1024", D);
+    return MCCNN_EINVAL;
+}
+
+}  // namespace mccnn

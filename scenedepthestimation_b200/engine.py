@@ -14,7 +14,16 @@ from . import _lib
 
 FEATURES = 64
 FC_UNITS = 384  # MCCNN_FC_UNITS: hidden width of the MC-CNN-accurate head
-EXACT = 0  # MCCNN_SGM_EXACT
+EXACT = 0  # MCCNN_SGM_EXACT: the reference's arithmetic, bit for bit (default everywhere)
+FUSED = 1  # MCCNN_SGM_FUSED: opt-in throughput mode (fp32 SGM state, 4 sweeps, fp32-accumulated cost volume; 1e-4 contract)
+
+
+def _mode(mode) -> int:
+    if mode in (EXACT, "exact", None):
+        return EXACT
+    if mode in (FUSED, "fused"):
+        return FUSED
+    raise ValueError(f"unknown SGM mode {mode!r} (use 'exact' or 'fused')")
 
 
 def _require_cuda():
@@ -129,6 +138,17 @@ def cost_volume(fl: torch.Tensor, fr: torch.Tensor, D: int, fill: float = 1.0, r
     return CL, CR
 
 
+def cost_volume_fast(fl: torch.Tensor, fr: torch.Tensor, D: int, fill: float = 1.0, right: bool = True):
+    """The fused mode's cost volume: fp32 FMA accumulation (not the reference's bits; |difference| <= 4e-6)."""
+    H, W, F = fl.shape
+    assert F == FEATURES and fr.shape == fl.shape
+    Dp = disp_pitch(D)
+    CL = torch.empty((H, W, Dp), dtype=torch.float32, device="cuda")
+    CR = torch.empty((H, W, Dp), dtype=torch.float32, device="cuda") if right else None
+    _lib.check(_lib.load().mccnn_cost_volume_fast(_p(fl), _p(fr), _p(CL), _p(CR), H, W, D, float(fill), _stream()), "mccnn_cost_volume_fast")
+    return CL, CR
+
+
 def cost_volume_tc(fl: torch.Tensor, fr: torch.Tensor, D: int, fill: float = 1.0, right: bool = True):
     """Tensor-core variant of cost_volume: same contract, same bits."""
     lib = _lib.load()
@@ -224,8 +244,8 @@ def cbca(CL, CR, imageL, imageR, D: int, iters: int = 2, L1: int = 14, tau: int 
     return CL, CR
 
 
-def sgm(CL, CR, imageL, imageR, D: int, params=None, keep_volumes: bool = True):
-    """8-path SGM + fused WTA. Returns (SL, SR, dispL, dispR)."""
+def sgm(CL, CR, imageL, imageR, D: int, params=None, keep_volumes: bool = True, mode=EXACT):
+    """8-path SGM + fused WTA. Returns (SL, SR, dispL, dispR). mode: EXACT (reference bits) or FUSED (4 sweeps, fp32 state)."""
     lib = _lib.load()
     H, W, Dp = CL.shape
     params = params or _lib.default_sgm_params()
@@ -235,7 +255,7 @@ def sgm(CL, CR, imageL, imageR, D: int, params=None, keep_volumes: bool = True):
     nws = lib.mccnn_sgm_workspace_bytes(H, W, D)
     ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
     _lib.check(lib.mccnn_sgm(_p(CL), _p(CR), _p(imageL), _p(imageR), _p(SL), _p(SR), _p(dl), _p(dr), _p(ws), nws,
-                             H, W, D, C.byref(params), EXACT, 1 if keep_volumes else 0, _stream()), "mccnn_sgm")
+                             H, W, D, C.byref(params), _mode(mode), 1 if keep_volumes else 0, _stream()), "mccnn_sgm")
     return SL, SR, dl, dr
 
 
@@ -328,7 +348,7 @@ def bad_pixels(disp_int, gt_half):
 
 # ------------------------------------------------------------------------------ whole path
 def disparity_pipeline(imageL, imageR, fl, fr, D: int, params=None, stage_ms: np.ndarray | None = None,
-                       out=None, workspace: torch.Tensor | None = None):
+                       out=None, workspace: torch.Tensor | None = None, mode=EXACT):
     """mccnn_disparity_pipeline on device tensors -> (dispL filtered, dispR raw WTA)."""
     lib = _lib.load()
     H, W = imageL.shape
@@ -339,7 +359,7 @@ def disparity_pipeline(imageL, imageR, fl, fr, D: int, params=None, stage_ms: np
                                           torch.empty((H, W), dtype=torch.float32, device="cuda"))
     sm = stage_ms.ctypes.data if stage_ms is not None else None
     _lib.check(lib.mccnn_disparity_pipeline(_p(imageL), _p(imageR), _p(fl), _p(fr), _p(dl), _p(dr), _p(ws), ws.numel(),
-                                            H, W, D, C.byref(params), EXACT, sm, _stream()), "mccnn_disparity_pipeline")
+                                            H, W, D, C.byref(params), _mode(mode), sm, _stream()), "mccnn_disparity_pipeline")
     return dl, dr
 
 
@@ -352,7 +372,7 @@ def match_accurate_workspace_bytes(H: int, W: int, D: int, num_layers: int = 5) 
 
 
 def match_pair(imageL, imageR, packed, D: int, num_layers: int = 5, params=None, stage_ms: np.ndarray | None = None,
-               out=None, workspace: torch.Tensor | None = None, head: "FcHeadWeights | None" = None):
+               out=None, workspace: torch.Tensor | None = None, head: "FcHeadWeights | None" = None, mode=EXACT):
     """mccnn_match_pair on device u8 images -> (dispL filtered, dispR raw WTA); with `head` the matching cost is the
     MC-CNN-accurate decision head (mccnn_match_pair_accurate)."""
     lib = _lib.load()
@@ -365,9 +385,9 @@ def match_pair(imageL, imageR, packed, D: int, num_layers: int = 5, params=None,
     sm = stage_ms.ctypes.data if stage_ms is not None else None
     if head is not None:
         _lib.check(lib.mccnn_match_pair_accurate(_p(imageL), _p(imageR), _p(packed), C.byref(head.c), _p(dl), _p(dr), _p(ws),
-                                                 ws.numel(), H, W, D, num_layers, C.byref(params), EXACT, sm, _stream()),
+                                                 ws.numel(), H, W, D, num_layers, C.byref(params), _mode(mode), sm, _stream()),
                    "mccnn_match_pair_accurate")
     else:
         _lib.check(lib.mccnn_match_pair(_p(imageL), _p(imageR), _p(packed), _p(dl), _p(dr), _p(ws), ws.numel(), H, W, D,
-                                        num_layers, C.byref(params), EXACT, sm, _stream()), "mccnn_match_pair")
+                                        num_layers, C.byref(params), _mode(mode), sm, _stream()), "mccnn_match_pair")
     return dl, dr

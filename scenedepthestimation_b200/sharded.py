@@ -51,7 +51,7 @@ def sgm_band(CLb, CRb, il_full, ir_full, D, shard: _lib.Shard, pass_mask=0x7F, k
         out = (torch.empty_like(CLb), torch.empty_like(CRb),
                torch.empty((rows, W), dtype=torch.float32, device="cuda"), torch.empty((rows, W), dtype=torch.float32, device="cuda"))
     SLb, SRb, dl, dr = out
-    nws = lib.mccnn_sgm_workspace_bytes(shard.H_full, W, D)
+    nws = 256   # the exact-mode words only (counters + status); the fused mode's rings are not used by sharded launches
     if ws is None:
         ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
     _lib.check(lib.mccnn_sgm_sharded(CLb.data_ptr(), CRb.data_ptr(), il_full.data_ptr(), ir_full.data_ptr(), SLb.data_ptr(),
@@ -120,7 +120,7 @@ class ShardedMatcher:
         self.epoch = 0
         self.timeout_ms = int(timeout_ms)
         self.go = torch.ones(1, dtype=torch.int32, device="cuda")       # all-reduced (MIN) before every SGM launch
-        self.sgm_ws = torch.zeros(lib.mccnn_sgm_workspace_bytes(H, W, D), dtype=torch.uint8, device="cuda")
+        self.sgm_ws = torch.zeros(256, dtype=torch.uint8, device="cuda")
         self.tc_ws = None
         if D >= 512:   # the cost-volume variant mccnn_disparity_pipeline picks for wide bands (pipeline.cu)
             self.tc_ws = torch.empty(lib.mccnn_cost_volume_tc_workspace_bytes(self.max_rows, W), dtype=torch.uint8, device="cuda")

@@ -1,0 +1,139 @@
+"""MCCNN_SGM_FUSED (csrc/sgm_fused.cu): the opt-in throughput mode. Two kinds of checks, kept apart on purpose:
+
+  * the kernels against oracle.stereo.sgm_all_paths_fused, the CPU restatement of THIS mode's arithmetic (fp32 path state,
+    contributions added in FUSED_PATH_ORDER): value for value, every shape the exact mode is tested on;
+  * the mode against the reference-exact mode, inside north_star's tolerance: cost volumes and aggregated costs within 1e-4
+    relative, disparity maps equal except at near-ties (the census of tools/fused_census.py, asserted here on small cases).
+The default path and every bit-exact test of the exact mode are untouched by this mode."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from scenedepthestimation_b200 import engine
+
+    return engine
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _inputs(H, W, D, kind, seed):
+    from scenedepthestimation_b200 import synthetic as syn
+
+    if kind == "tex":
+        il, ir, _ = syn.textured_pair(H, W, D, seed)
+        fl, fr, _ = syn.correlated_features(H, W, D, 64, seed)
+    else:
+        il, ir = syn.noise_pair(H, W, seed)
+        fl, fr = syn.unit_features(H, W, 64, seed)
+    return il, ir, fl, fr
+
+
+SHAPES = [(6, 10, 8, "noise"), (20, 48, 32, "tex"), (40, 24, 128, "noise"), (9, 300, 128, "tex"), (33, 65, 1, "tex"),
+          (17, 19, 3, "noise"), (50, 130, 80, "tex"), (64, 40, 228, "noise"), (30, 70, 400, "tex"), (12, 20, 1000, "noise"),
+          (3, 3, 5, "noise"), (100, 9, 33, "noise"), (5, 700, 20, "tex"), (21, 1300, 40, "tex"), (1300, 11, 24, "noise")]
+
+
+@pytest.mark.parametrize("H,W,D,kind", SHAPES)
+def test_fused_sgm_equals_fused_oracle(eng, H, W, D, kind):
+    """Every sweep of the fused mode (hand-over rings inside a CTA, between CTAs and around the chain, several rounds of units
+    per warp when the image has more rows / columns than the chain has warps, column wraps of the diagonals, D from 1 to 1000)."""
+    from oracle import stereo as st
+
+    il, ir, fl, fr = _inputs(H, W, D, kind, H * 7 + W)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    SL, SR, dl, dr = eng.sgm(CL, CR, dev(il), dev(ir), D, keep_volumes=True, mode="fused")
+    cl, cr = CL[..., :D].cpu().numpy(), CR[..., :D].cpu().numpy()
+    esl, esr = st.sgm_all_paths_fused(cl, cr, st.sgm_penalties(il), st.sgm_penalties(ir))
+    assert np.array_equal(SL[..., :D].cpu().numpy(), esl) and np.array_equal(SR[..., :D].cpu().numpy(), esr)
+    assert np.array_equal(dl.cpu().numpy(), st.wta(esl)) and np.array_equal(dr.cpu().numpy(), st.wta(esr))
+    # the variant that does not store S in its last sweep gives the same maps; two runs are identical
+    _, _, dl2, dr2 = eng.sgm(CL, CR, dev(il), dev(ir), D, keep_volumes=False, mode="fused")
+    assert torch.equal(dl, dl2) and torch.equal(dr, dr2)
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c5"])
+def test_fused_sgm_equals_fused_oracle_full_size(eng, cfg):
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import synthetic as syn
+
+    W, H, D = syn.CONFIGS[cfg]
+    il, ir, fl, fr = _inputs(H, W, D, "tex", 3000 + int(cfg[1]))
+    CL, CR = eng.cost_volume_fast(dev(fl), dev(fr), D)
+    SL, SR, dl, dr = eng.sgm(CL, CR, dev(il), dev(ir), D, keep_volumes=True, mode="fused")
+    cl, cr = CL[..., :D].cpu().numpy(), CR[..., :D].cpu().numpy()
+    esl, esr = st.sgm_all_paths_fused(cl, cr, st.sgm_penalties(il), st.sgm_penalties(ir))
+    assert np.array_equal(SL[..., :D].cpu().numpy(), esl) and np.array_equal(SR[..., :D].cpu().numpy(), esr)
+    assert np.array_equal(dl.cpu().numpy(), st.wta(esl)) and np.array_equal(dr.cpu().numpy(), st.wta(esr))
+
+
+@pytest.mark.parametrize("H,W,D,kind", [(40, 200, 64, "tex"), (24, 90, 128, "noise"), (16, 2000, 800, "tex")])
+def test_fast_cost_volume_within_tolerance(eng, H, W, D, kind):
+    """mccnn_cost_volume_fast (fp32 FMA accumulation) against the reference-exact volume: north_star's bar is 1e-4 relative;
+    on unit-norm features (|cost| <= 1) the measured difference is a few 1e-7. Fills and pads are identical."""
+    _, _, fl, fr = _inputs(H, W, D, kind, 5)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    FL, FR = eng.cost_volume_fast(dev(fl), dev(fr), D)
+    for a, b in ((CL, FL), (CR, FR)):
+        fin = torch.isfinite(a)
+        assert torch.equal(fin, torch.isfinite(b))
+        diff = (a[fin] - b[fin]).abs()
+        assert float(diff.max()) <= 4e-6
+        assert float((diff / a[fin].abs().clamp(min=1.0)).max()) <= 1e-4
+        assert torch.equal(a == 1.0, b == 1.0) or float(((a == 1.0) != (b == 1.0)).float().mean()) < 1e-6
+
+
+@pytest.mark.parametrize("H,W,D,kind", [(60, 200, 64, "tex"), (48, 160, 128, "tex"), (40, 120, 80, "noise")])
+def test_fused_mode_within_tolerance_of_exact(eng, H, W, D, kind):
+    """The whole fused pipeline (fast cost volume + 4-sweep SGM) against the exact one: aggregated costs within 1e-4 relative,
+    and every pixel whose disparity differs is a near-tie of the exact aggregated volume (second-best cost within 1e-4 relative
+    of the best)."""
+    il, ir, fl, fr = _inputs(H, W, D, kind, 11)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    SL, SR, dl, dr = eng.sgm(CL, CR, dev(il), dev(ir), D, keep_volumes=True)
+    FL, FR = eng.cost_volume_fast(dev(fl), dev(fr), D)
+    TL, TR, fdl, fdr = eng.sgm(FL, FR, dev(il), dev(ir), D, keep_volumes=True, mode="fused")
+    for S, T, d, fd in ((SL, TL, dl, fdl), (SR, TR, dr, fdr)):
+        S, T = S[..., :D], T[..., :D]
+        rel = ((S - T).abs() / S.abs().clamp(min=1.0)).max()
+        assert float(rel) <= 1e-4, float(rel)
+        differ = d != fd
+        if bool(differ.any()):
+            best = S.min(dim=-1).values
+            at_fused = torch.gather(S, 2, fd.long().unsqueeze(-1)).squeeze(-1)
+            gap = (at_fused - best) / best.abs().clamp(min=1.0)
+            assert float(gap[differ].max()) <= 1e-4, "a disparity changed where the exact volume has no near-tie"
+    # end to end through the pipeline entry point
+    out_e = eng.disparity_pipeline(dev(il), dev(ir), dev(fl), dev(fr), D)
+    out_f = eng.disparity_pipeline(dev(il), dev(ir), dev(fl), dev(fr), D, mode="fused")
+    frac = float((out_e[0] != out_f[0]).float().mean())
+    assert frac <= 0.02, frac
+
+
+def test_fused_mode_is_opt_in_and_validated(eng):
+    """Default = exact; an unknown mode is refused; the sharded entry point is exact-only."""
+    from scenedepthestimation_b200 import _lib
+
+    with pytest.raises(ValueError):
+        eng._mode("fast")
+    assert eng._mode(None) == eng.EXACT and eng._mode("fused") == eng.FUSED
+    il, ir, fl, fr = _inputs(12, 20, 8, "noise", 1)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), 8)
+    lib = _lib.load()
+    S = torch.empty_like(CL)
+    d = torch.empty((12, 20), device="cuda")
+    ws = torch.empty(lib.mccnn_sgm_workspace_bytes(12, 20, 8), dtype=torch.uint8, device="cuda")
+    p = _lib.default_sgm_params()
+    import ctypes as C
+
+    rc = lib.mccnn_sgm(CL.data_ptr(), CR.data_ptr(), dev(il).data_ptr(), dev(ir).data_ptr(), S.data_ptr(), S.data_ptr(), d.data_ptr(),
+                       d.data_ptr(), ws.data_ptr(), ws.numel(), 12, 20, 8, C.byref(p), 7, 1, None)
+    assert rc == -1 and b"unknown mode" in lib.mccnn_last_error()
