@@ -26,13 +26,15 @@
 // of a chain must be resident.
 // Cost and S rows stream through shared memory with 1-D bulk copies + mbarriers, as in sgm.cu.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace mccnn {
 namespace {
 
-constexpr int FW = 8;       // warps per CTA of the chain kernel
+constexpr int FW_MAX = 8;   // warps per CTA of the chain kernel (6 for rows of 1024 floats: shared memory)
 constexpr int RING = 2;     // hand-over slots between warps of one CTA (shared memory)
 constexpr int GRING = 8;    // hand-over slots between neighbouring CTAs (global memory)
+constexpr int INR = 4;      // rows of the global input link prefetched into shared memory (per CTA)
 constexpr int FSTAGES = 2;  // rows in flight per warp and stream
 constexpr int FLAG_STRIDE = 32;  // unsigned words between two flags (one 128-byte line each)
 constexpr int MAX_CHAIN_CTAS = 512;
@@ -55,6 +57,7 @@ struct FusedArgs {
     unsigned* gflags; // [side][ctas][2][FLAG_STRIDE]: produced / consumed counters of the link leaving CTA c
     int slot_floats;  // 32 * NPL + 4
     unsigned* counter;  // sweep 3: scanline counter
+    int debug;          // development only (MCCNN_FUSED_DEBUG): bit 0 = never wait for a hand-over (wrong results, timing only)
 };
 
 // ------------------------------------------------------------------------------------------------ small device helpers
@@ -67,6 +70,25 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned* p, unsigned v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all_elect() {   // full completion (writes performed), not just the source reads
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.wait_group %0;\n\t"
+        "}" ::"n"(N)
+        : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire_cta_smem(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
@@ -229,26 +251,48 @@ __device__ __forceinline__ float warp_wta(const float (&so)[NPL], int lane, int 
 }
 
 // ------------------------------------------------------------------------------------------------ sweeps 0, 1, 2
+// Shared-memory layout of the chain kernel (floats unless noted):
+//   per warp : inbuf [FSTAGES][NIN][ROWF] | outbuf [ROWF] | ring [RING][SLOTF]   (SLOTF = ROWF + 4: the row and, at [ROWF], its minimum)
+//   per CTA  : inring [INR][SLOTF]  rows prefetched from the previous CTA's global ring (read by warp 0 only)
+//              prodc [FW], consc [FW] (unsigned)   counters of the links between the warps of the CTA
+//              mbarriers: FSTAGES per warp, then INR for inring
+template <int NPL>
+struct ChainSmem {
+    static constexpr int FW = NPL > 25 ? 6 : FW_MAX;
+    static constexpr int ROWF = 32 * NPL;
+    static constexpr int SLOTF = ROWF + 4;
+    static constexpr int per_warp(int nin) { return ROWF * (FSTAGES * nin + 1) + RING * SLOTF; }
+    static constexpr size_t bytes(int nin) {
+        return (size_t)FW * per_warp(nin) * 4 + (size_t)INR * SLOTF * 4 + (size_t)2 * FW * 4 + (size_t)(FW * FSTAGES + INR) * 8;
+    }
+};
+
 template <int NPL, bool READS>
-__global__ void __launch_bounds__(FW * 32) sgm_chain_kernel(const FusedArgs a) {
-    constexpr int ROWF = 32 * NPL;
+__global__ void __launch_bounds__(ChainSmem<NPL>::FW * 32) sgm_chain_kernel(const FusedArgs a) {
+    using L = ChainSmem<NPL>;
+    constexpr int FW = L::FW;
+    constexpr int ROWF = L::ROWF, SLOTF = L::SLOTF;
     constexpr int NIN = READS ? 2 : 1;
-    constexpr int PER_WARP = ROWF * (FSTAGES * NIN + 1 + RING);
+    constexpr int PER_WARP = L::per_warp(NIN);
+    constexpr uint32_t SLOT_BYTES = SLOTF * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* wbase = reinterpret_cast<float*>(smem_raw) + (size_t)warp * PER_WARP;
     float* inbuf = wbase;                            // [FSTAGES][NIN][ROWF]
     float* outbuf = wbase + ROWF * FSTAGES * NIN;    // [ROWF]
-    float* ring = outbuf + ROWF;                     // [RING][ROWF]: the link warp -> warp + 1
-    float* tail = reinterpret_cast<float*>(smem_raw) + (size_t)FW * PER_WARP;
-    float* ringmin = tail;                                                       // [FW][RING]
-    unsigned* prodc = reinterpret_cast<unsigned*>(tail + FW * RING);             // [FW] rows published on the link leaving warp w
+    float* ring = outbuf + ROWF;                     // [RING][SLOTF]: the link warp -> warp + 1 (or the staging rows of the global link)
+    float* inring = reinterpret_cast<float*>(smem_raw) + (size_t)FW * PER_WARP;   // [INR][SLOTF]
+    unsigned* prodc = reinterpret_cast<unsigned*>(inring + INR * SLOTF);         // [FW] rows published on the link leaving warp w
     unsigned* consc = prodc + FW;                                                // [FW] rows the reader of that link is done with
-    uint64_t* bars = reinterpret_cast<uint64_t*>(consc + FW) + warp * FSTAGES;   // (FW * (RING + 2) floats: a multiple of 8 bytes)
+    uint64_t* bars_all = reinterpret_cast<uint64_t*>(consc + FW);
+    uint64_t* bars = bars_all + warp * FSTAGES;
+    uint64_t* inbars = bars_all + FW * FSTAGES;                                  // [INR]
 
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < FSTAGES; s++) mbar_init(&bars[s], 1);
+        if (warp == 0)
+            for (int s = 0; s < INR; s++) mbar_init(&inbars[s], 1);
         mbar_fence_init();
         prodc[warp] = 0u;
         consc[warp] = 0u;
@@ -269,12 +313,14 @@ __global__ void __launch_bounds__(FW * 32) sgm_chain_kernel(const FusedArgs a) {
     const size_t pitch = (size_t)a.Dp;
 
     // links. The one that leaves CTA c for CTA c + 1 is global link c; link ctas - 1 closes the ring (T slots).
+    // A global link is a FIFO of rows: the producer pushes one row per step of every unit it hands over (T per unit, payload
+    // or not), the consumer pops T rows per unit; row index = round * T + step.
     const bool in_local = warp > 0, out_local = warp < FW - 1;
     const int lin = cta == 0 ? a.ctas - 1 : cta - 1, lout = cta;
-    const size_t side_floats = ((size_t)a.ctas * GRING + (size_t)T) * a.slot_floats;
-    auto link_base = [&](int l) { return a.glink + (size_t)side * side_floats + (size_t)l * GRING * a.slot_floats; };
-    const unsigned depth_in = in_local ? RING : (lin == a.ctas - 1 ? (unsigned)T : GRING);
-    const unsigned depth_out = out_local ? RING : (lout == a.ctas - 1 ? (unsigned)T : GRING);
+    const size_t side_floats = ((size_t)a.ctas * GRING + (size_t)T) * SLOTF;
+    auto link_base = [&](int l) { return a.glink + (size_t)side * side_floats + (size_t)l * GRING * SLOTF; };
+    const unsigned depth_in = lin == a.ctas - 1 ? (unsigned)T : (unsigned)GRING;
+    const unsigned depth_out = lout == a.ctas - 1 ? (unsigned)T : (unsigned)GRING;
     const float* gin = link_base(lin);
     float* gout = link_base(lout);
     unsigned* gprod_in = a.gflags + ((size_t)(side * a.ctas + lin) * 2 + 0) * FLAG_STRIDE;
@@ -287,7 +333,44 @@ __global__ void __launch_bounds__(FW * 32) sgm_chain_kernel(const FusedArgs a) {
     const int dpix = a.sweep == 0 ? W : (a.sweep == 1 ? -1 : 1);
     const int upoff = a.sweep == 0 ? -1 : (a.sweep == 1 ? -W : W);
 
-    uint32_t gstep = 0;  // rows consumed by this warp so far (stage ring position / mbarrier phase)
+    uint32_t gstep = 0;      // rows consumed by this warp so far (stage ring position / mbarrier phase)
+    // global input link (warp 0 only): rows [popped, fetched) sit in inring or are on their way; rows < avail are in global memory
+    unsigned fetched = 0, avail = 0;
+    // global output link (warp FW - 1 only): rows < pushed have been handed to the copy engine, rows < published are visible
+    unsigned cons_seen = 0;
+    bool pending_pub = false;
+    unsigned pending_q = 0;
+
+    // copy every row that is available and fits into inring: global slot -> shared slot, completion on the slot's mbarrier
+    // Ordering on the global links. The producer's rows reach L2 through the copy engine and it writes the counter only after
+    // cp.async.bulk.wait_group has reported them complete; the consumer reads the counter from L2 (relaxed.gpu bypasses L1) and
+    // only then lets the copy engine read the rows from L2, the copy being control-dependent on the counter's value. No
+    // gpu-scope acquire / release fence sits in the step: measured, a fence per step in the two boundary warps of every CTA
+    // is what the whole chain then waits for. fence.proxy.async orders the generic-proxy counter access against the
+    // async-proxy copies of the same thread.
+    auto fetch_rows = [&](unsigned popped) {
+        if (fetched < avail && fetched < popped + INR) fence_proxy_async_global();
+        while (fetched < avail && fetched < popped + INR) {
+            const unsigned sl = fetched % INR;
+            mbar_expect_tx_elect(&inbars[sl], SLOT_BYTES);
+            bulk_g2s_elect(inring + (size_t)sl * SLOTF, gin + (size_t)(fetched % depth_in) * SLOTF, SLOT_BYTES, &inbars[sl]);
+            fetched++;
+        }
+    };
+    // pop row q (it must be the next one): make sure it has been fetched, wait for it, free its global slot
+    auto pop_row = [&](unsigned q) -> const float* {
+        if (fetched <= q) {   // not even requested yet: the producer was late when we last looked
+            while (avail <= q) {
+                unsigned v = 0;
+                if (lane == 0) v = ld_relaxed_gpu(gprod_in);
+                avail = __shfl_sync(0xffffffffu, v, 0);
+                if (avail <= q) __nanosleep(100);
+            }
+            fetch_rows(q);
+        }
+        mbar_wait(&inbars[q % INR], (q / INR) & 1u);
+        return inring + (size_t)(q % INR) * SLOTF;
+    };
 
     int round = 0;
     for (int u = w; u < a.U; u += n, round++) {
@@ -297,6 +380,8 @@ __global__ void __launch_bounds__(FW * 32) sgm_chain_kernel(const FusedArgs a) {
         // the producer of my input link works on unit u - 1: same round, or the previous one across the closing link
         const unsigned qbase_in = (unsigned)((w == 0 ? round - 1 : round)) * (unsigned)T;   // only used when has_up
         const unsigned qbase_out = (unsigned)round * (unsigned)T;
+        const bool gin_active = !in_local && has_up && !(a.debug & 2);      // this unit pops T rows from the global input link
+        const bool gout_active = !out_local && diag_unit && !(a.debug & 2);  // this unit pushes T rows onto the global output link
 
         long long lpix = pix0;  // pixel of the next row to prefetch
         auto issue_load = [&](uint32_t g) {
@@ -326,6 +411,12 @@ __global__ void __launch_bounds__(FW * 32) sgm_chain_kernel(const FusedArgs a) {
 
         long long pix = pix0;
         for (int t = 0; t < T; t++, pix += dpix) {
+            // the counters of the global links are read at the top of the step and used further down: their L2 latency
+            // hides behind the own path
+            unsigned avail_new = 0, cons_new = 0;
+            if (gin_active && lane == 0) avail_new = ld_relaxed_gpu(gprod_in);
+            if (gout_active && lane == 0) cons_new = ld_relaxed_gpu(gcons_out);
+
             const int st = gstep % FSTAGES;
             mbar_wait(&bars[st], (gstep / FSTAGES) & 1u);
             float cf[NPL], so[NPL];
@@ -364,32 +455,40 @@ __global__ void __launch_bounds__(FW * 32) sgm_chain_kernel(const FusedArgs a) {
 #pragma unroll
                 for (int j = 0; j < NPL; j++) so[j] = own_active ? Lo[j] : 0.0f;
             }
+            // Every lane has consumed this stage's cost (and S) row in arithmetic (the recurrence and the minimum read every
+            // cf[j], the add every so[j]; refills only happen for t <= T - 3, where the own path is active), so all its shared
+            // loads have returned: refill the stage NOW, most of a step earlier than at the end of the step.
+            __syncwarp();
+            if (t + FSTAGES < T) issue_load(gstep + FSTAGES);
+
+            // ---- global input link: request every row that has become available (they are used one or more steps later)
+            if (gin_active) {
+                avail = max(avail, __shfl_sync(0xffffffffu, avail_new, 0));
+                fetch_rows(qbase_in + (unsigned)max(t - 1, 0));
+            }
+            if (gout_active) cons_seen = max(cons_seen, __shfl_sync(0xffffffffu, cons_new, 0));
 
             // ---- the diagonal path: predecessor = step t - 1 of unit u - 1
+            const float* grow = nullptr;
+            if (gin_active && t >= 1) grow = pop_row(qbase_in + (unsigned)(t - 1));   // popped whether it is needed or not (FIFO)
+            float md = 0.f;
             if (diag_active) {
                 float Ld[NPL];
-                float md;
-                if (t == 0 || !has_up) {
+                if (t == 0 || !has_up || ((a.debug & 2) && !in_local)) {
 #pragma unroll
                     for (int j = 0; j < NPL; j++) Ld[j] = cf[j];
                 } else {
-                    const unsigned q = qbase_in + (unsigned)(t - 1);   // index of the row I need on my input link
                     if (in_local) {
-                        if (lane == 0)
+                        const unsigned q = qbase_in + (unsigned)(t - 1);   // index of the row I need on my input link
+                        if (lane == 0 && !(a.debug & 1))
                             while (ld_acquire_cta_smem(&prodc[warp - 1]) < q + 1u) __nanosleep(20);
                         __syncwarp();
-                        const unsigned slot = q % RING;
-                        load_row<NPL>(lring_in + (size_t)slot * ROWF, lane, Ld);
-                        md = ringmin[(warp - 1) * RING + slot];
+                        const float* src = lring_in + (size_t)(q % RING) * SLOTF;
+                        load_row<NPL>(src, lane, Ld);
+                        md = src[ROWF];
                     } else {
-                        if (lane == 0) {
-                            while (ld_relaxed_gpu(gprod_in) < q + 1u) __nanosleep(40);
-                            fence_acq_rel_gpu();
-                        }
-                        __syncwarp();
-                        const float* src = gin + (size_t)(q % depth_in) * a.slot_floats;
-                        load_row_cg<NPL>(src, lane, Ld);
-                        md = __ldcg(src + ROWF);
+                        load_row<NPL>(grow, lane, Ld);
+                        md = grow[ROWF];
                     }
                     const int dn = i_cur - i_prev_up;
                     const bool full = (dn >= 0) && (dn <= a.threshold);
@@ -399,48 +498,63 @@ __global__ void __launch_bounds__(FW * 32) sgm_chain_kernel(const FusedArgs a) {
 #pragma unroll
                 for (int j = 0; j < NPL; j++) so[j] = so[j] + Ld[j];
 
-                // hand the new state to unit u + 1 (row qo of my output link), once its reader is done with the slot
+                // hand the new state to unit u + 1 (row qo of my output link)
                 const unsigned qo = qbase_out + (unsigned)t;
                 if (out_local) {
-                    if (qo + 1u > RING) {
+                    if (qo + 1u > RING && !(a.debug & 1)) {   // once its reader is done with the slot (0xffffffff = reader gone)
                         if (lane == 0)
-                            while (ld_acquire_cta_smem(&consc[warp]) < qo + 1u - RING) __nanosleep(20);   // (0xffffffff = reader gone)
+                            while (ld_acquire_cta_smem(&consc[warp]) < qo + 1u - RING) __nanosleep(20);
                         __syncwarp();
                     }
-                    const unsigned slot = qo % RING;
-                    store_row<NPL>(ring + (size_t)slot * ROWF, lane, Ld);
-                    if (lane == 0) ringmin[warp * RING + slot] = md;
+                    float* dst = ring + (size_t)(qo % RING) * SLOTF;
+                    store_row<NPL>(dst, lane, Ld);
+                    if (lane == 0) dst[ROWF] = md;
                     __syncwarp();
                     if (lane == 0) st_release_cta_smem(&prodc[warp], qo + 1u);
-                } else {
-                    if (qo + 1u > depth_out) {
-                        if (lane == 0) {
-                            while (ld_relaxed_gpu(gcons_out) < qo + 1u - depth_out) __nanosleep(40);
-                            fence_acq_rel_gpu();
-                        }
-                        __syncwarp();
-                    }
-                    float* dst = gout + (size_t)(qo % depth_out) * a.slot_floats;
-                    store_row_cg<NPL>(dst, lane, Ld);
-                    if (lane == 0) __stcg(dst + ROWF, md);
-                    __syncwarp();
-                    if (lane == 0) {
-                        fence_acq_rel_gpu();
-                        st_relaxed_gpu(gprod_out, qo + 1u);
-                    }
+                } else if (gout_active) {
+                    // stage the row in my (otherwise unused) ring; the copy that last read this slot was committed two steps ago
+                    // and is waited for below, before the row of the previous step is published
+                    float* dst = ring + (size_t)(qo % RING) * SLOTF;
+                    store_row<NPL>(dst, lane, Ld);
+                    if (lane == 0) dst[ROWF] = md;
                 }
             }
-            // my input link: everything up to the row of step t - 1 is consumed (whether it was needed or not)
-            if (has_up && t >= 1 && !(w == 0 && round == 0)) {
+            // my input link inside the CTA: everything up to the row of step t - 1 is consumed (whether it was needed or not)
+            if (in_local && has_up && t >= 1) {
                 __syncwarp();
-                if (lane == 0) {
-                    if (in_local) {
-                        st_release_cta_smem(&consc[warp - 1], qbase_in + (unsigned)t);
-                    } else {
-                        fence_acq_rel_gpu();
-                        st_relaxed_gpu(gcons_in, qbase_in + (unsigned)t);
+                if (lane == 0) st_release_cta_smem(&consc[warp - 1], qbase_in + (unsigned)t);
+            }
+            if (gin_active && t >= 1) {
+                // the row's copy out of global memory completed before pop_row returned and its shared copy has been read in
+                // arithmetic: both slots are free
+                __syncwarp();
+                if (lane == 0) st_relaxed_gpu(gcons_in, qbase_in + (unsigned)t);
+            }
+            if (gout_active) {
+                // FIFO push of row qo = qbase_out + t, one bulk copy shared -> global per step (payload or not).
+                // 1. publish the previous row: its copy was committed a step ago
+                if (pending_pub) {
+                    bulk_wait_all_elect<1>();   // all but the latest group (the S row of the previous step) are complete
+                    fence_proxy_async_global();
+                    __syncwarp();
+                    if (lane == 0) st_relaxed_gpu(gprod_out, pending_q + 1u);
+                }
+                // 2. the global slot must have been popped by the reader
+                const unsigned qo = qbase_out + (unsigned)t;
+                if (qo + 1u > depth_out && !(a.debug & 1)) {
+                    while (cons_seen < qo + 1u - depth_out) {
+                        unsigned v = 0;
+                        if (lane == 0) v = ld_relaxed_gpu(gcons_out);
+                        cons_seen = __shfl_sync(0xffffffffu, v, 0);
+                        if (cons_seen < qo + 1u - depth_out) __nanosleep(100);
                     }
                 }
+                // 3. shared -> global
+                fence_proxy_async_smem();
+                __syncwarp();
+                bulk_s2g_commit_elect(gout + (size_t)(qo % depth_out) * SLOTF, ring + (size_t)(qo % RING) * SLOTF, SLOT_BYTES);
+                pending_pub = true;
+                pending_q = qo;
             }
 
             // ---- the "up" path adds the raw cost on rows >= 1 (its penalties are never written, sgm.cu); sweep 0 only
@@ -451,8 +565,9 @@ __global__ void __launch_bounds__(FW * 32) sgm_chain_kernel(const FusedArgs a) {
                 }
             }
 
-            // ---- S row out: staged, one bulk store per row
-            bulk_wait_read_elect<0>();  // the store of the previous step has left the staging row
+            // ---- S row out: staged, one bulk store per row. The store of the previous step has left the staging row (the
+            // hand-over copy committed a moment ago may still be reading ITS row).
+            if (gout_active) bulk_wait_read_elect<1>(); else bulk_wait_read_elect<0>();
             __syncwarp();
             store_row<NPL>(outbuf, lane, so);
             fence_proxy_async_smem();
@@ -461,32 +576,37 @@ __global__ void __launch_bounds__(FW * 32) sgm_chain_kernel(const FusedArgs a) {
 
             i_prev_own = i_cur;
             i_prev_up = i_upcur;
-            __syncwarp();   // every lane has consumed the stage: refill it
-            if (t + FSTAGES < T) issue_load(gstep + FSTAGES);
             gstep++;
         }
-        // the unit is done: its input link is consumed to the end of the producer's round
-        if (has_up && !(w == 0 && round == 0)) {
+        // the unit is done
+        if (in_local && has_up) {   // its input link is consumed to the end of the producer's round
             __syncwarp();
-            if (lane == 0) {
-                if (in_local) {
-                    st_release_cta_smem(&consc[warp - 1], qbase_in + (unsigned)T);
-                } else {
-                    fence_acq_rel_gpu();
-                    st_relaxed_gpu(gcons_in, qbase_in + (unsigned)T);
-                }
-            }
+            if (lane == 0) st_release_cta_smem(&consc[warp - 1], qbase_in + (unsigned)T);
+        }
+        if (gin_active) {           // FIFO: pop the row of the producer's last step too
+            pop_row(qbase_in + (unsigned)(T - 1));
+            __syncwarp();
+            if (lane == 0) st_relaxed_gpu(gcons_in, qbase_in + (unsigned)T);
+        }
+        if (gout_active && pending_pub) {   // publish the last row of the unit
+            bulk_wait_all_elect<0>();
+            fence_proxy_async_global();
+            __syncwarp();
+            if (lane == 0) st_relaxed_gpu(gprod_out, pending_q + 1u);
+            pending_pub = false;
         }
     }
     // no more units for this warp: whatever still arrives on its input link is not needed
     __syncwarp();
     if (lane == 0) {
-        if (in_local) {
+        if (in_local)
             st_release_cta_smem(&consc[warp - 1], 0xffffffffu);
-        } else {
-            fence_acq_rel_gpu();
+        else
             st_relaxed_gpu(gcons_in, 0xffffffffu);
-        }
+    }
+    // rows requested from the global link but never popped must have landed before the CTA's shared memory goes away
+    if (!in_local) {
+        for (unsigned q = (fetched > INR ? fetched - INR : 0u); q < fetched; q++) mbar_wait(&inbars[q % INR], (q / INR) & 1u);
     }
     asm volatile(
         "{\n\t"
@@ -642,10 +762,9 @@ FusedLayout fused_layout(int H, int W, int D) {
 
 template <int NPL, bool READS>
 int launch_chain(FusedArgs a, cudaStream_t stream) {
-    constexpr int ROWF = 32 * NPL;
     constexpr int NIN = READS ? 2 : 1;
-    const size_t smem = (size_t)FW * ROWF * (FSTAGES * NIN + 1 + RING) * sizeof(float) + (size_t)FW * (RING + 2) * sizeof(float) +
-                        (size_t)FW * FSTAGES * sizeof(uint64_t);
+    constexpr int FW = ChainSmem<NPL>::FW;
+    const size_t smem = ChainSmem<NPL>::bytes(NIN);
     int per_sm = 0;
     if (int e = kernel_setup<sgm_chain_kernel<NPL, READS>>(FW * 32, smem, &per_sm)) return e;
     MCCNN_REQUIRE(per_sm >= 1, MCCNN_EINVAL, "sgm_chain_kernel<%d>: does not fit on an SM (smem %zu)", NPL, smem);
@@ -681,7 +800,12 @@ int launch_last(const FusedArgs& a, cudaStream_t stream) {
 
 template <int NPL>
 int run_fused_npl(FusedArgs a, int keep_volumes, cudaStream_t stream, unsigned* flags) {
+    const char* env_mask = getenv("MCCNN_FUSED_SWEEPS");
+    const int mask = env_mask ? atoi(env_mask) : 15;
+    const char* env_dbg = getenv("MCCNN_FUSED_DEBUG");
+    a.debug = env_dbg ? atoi(env_dbg) : 0;
     for (int sweep = 0; sweep < 3; sweep++) {
+        if (!(mask & (1 << sweep))) continue;
         a.sweep = sweep;
         a.U = sweep == 0 ? a.W : a.H;
         a.T = sweep == 0 ? a.H : a.W;
@@ -689,6 +813,7 @@ int run_fused_npl(FusedArgs a, int keep_volumes, cudaStream_t stream, unsigned* 
         if (int e = (sweep == 0 ? launch_chain<NPL, false>(a, stream) : launch_chain<NPL, true>(a, stream))) return e;
     }
     a.store_s = keep_volumes;
+    if (!(mask & 8)) return 0;
     return keep_volumes ? launch_last<NPL, true>(a, stream) : launch_last<NPL, false>(a, stream);
 }
 
