@@ -25,9 +25,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-def kernels_per_step(D: int) -> int:
+def kernels_per_step(D: int, mode: str = "exact") -> int:
     """standardise (2x2) + conv (2x5) + cost volume + SGM passes + L-R flags, fill (2), median. The cost volume is one band-GEMM
-    launch, or for D >= 512 the tensor-core variant: 2 slice kernels, fill, main kernel, fix-up (pipeline.cu)."""
+    launch, or for D >= 512 the tensor-core variant: 2 slice kernels, fill, main kernel, fix-up (pipeline.cu). Fused mode: one
+    cost-volume launch and 4 SGM sweeps."""
+    if mode == "fused":
+        return 2 * 2 + 2 * 5 + 1 + 4 + 4
     return 2 * 2 + 2 * 5 + (5 if D >= 512 else 1) + 7 + 4
 
 
@@ -40,6 +43,9 @@ def parse():
     ap.add_argument("--config", default=None, help="c1..c5 (SURVEY.md App. B); the metric is quoted on c4 (default; c3 with --arch accurate)")
     ap.add_argument("--arch", default="fast", choices=["fast", "accurate"], help="matching cost: MC-CNN-fast dot product (the reference's "
                     "net, the headline) or the MC-CNN-accurate fully-connected decision head (BASELINE config 3; own oracle)")
+    ap.add_argument("--mode", default="exact", choices=["exact", "fused"], help="exact (default, the headline): the reference's arithmetic "
+                    "bit for bit. fused: the opt-in throughput mode (fp32 SGM state, 8 paths in 4 sweeps, fp32-accumulated cost volume; "
+                    "held to north_star's 1e-4 tolerance, census in profiles/)")
     ap.add_argument("--batch", type=int, default=0, help="pairs per step per GPU (default 1; 32 for c5 = 256 pairs over 8 ranks), "
                     "kept in flight on --depth CUDA streams like match.py's streamed loop")
     ap.add_argument("--depth", type=int, default=3)
@@ -184,7 +190,10 @@ def main():
                           "+ 8-path SGM + WTA + L-R check/fill + 5x5 median",
               "pairs_per_step_per_gpu": batch, "parallelism": f"pair-per-rank x{world}" + (f", {a.depth} pairs in flight per GPU" if batch > 1 else ""),
               "l2": f"per-step working set (4 fp32 volumes per pair in flight, {4 * evals * 4 / 1e9:.1f} GB each set) exceeds the 126 MB L2; no flush needed",
-              "arithmetic": "reference-exact (fp64 SGM state and cost accumulator, fp32 S rounded per path in reference order)" if a.arch == "fast" else
+              "arithmetic": ("fused mode (opt-in): fp32 SGM path state, 8 contributions added to S in 4 sweeps, fp32-accumulated cost volume; "
+                             "within north_star's 1e-4 of the reference-exact mode, disparities equal except at near-ties (profiles/r02_fused_census.json)")
+                            if a.mode == "fused" else
+                            "reference-exact (fp64 SGM state and cost accumulator, fp32 S rounded per path in reference order)" if a.arch == "fast" else
                             "decision head: fp16 operands, fp32 accumulation on tcgen05 (own oracle, |d cost| <= 2e-3); SGM and post-processing reference-exact"}
 
     if a.impl == "reference":
@@ -246,7 +255,7 @@ def main():
 
     def step():
         if batch == 1:
-            eng.match_pair(d_il, d_ir, packed, D, 5, out=out, workspace=ws, head=head)
+            eng.match_pair(d_il, d_ir, packed, D, 5, out=out, workspace=ws, head=head, mode=a.mode)
             return
         cur = torch.cuda.current_stream()
         for st, _, _ in slots:
@@ -254,7 +263,7 @@ def main():
         for i in range(batch):
             st, w_, o_ = slots[i % len(slots)]
             with torch.cuda.stream(st):
-                eng.match_pair(d_il, d_ir, packed, D, 5, out=o_, workspace=w_)
+                eng.match_pair(d_il, d_ir, packed, D, 5, out=o_, workspace=w_, mode=a.mode)
         for st, _, _ in slots:
             cur.wait_stream(st)
 
@@ -290,7 +299,7 @@ def main():
         from scenedepthestimation_b200 import match as match_mod
 
         del slots[:]
-        streamed = match_mod.StreamedMatcher(H, W, weights, ndisp=D, scale=1, depth=a.depth)
+        streamed = match_mod.StreamedMatcher(H, W, weights, ndisp=D, scale=1, depth=a.depth, mode=a.mode)
 
     def e2e_step():
         if streamed is not None:  # match.py's loop: host u8 pairs in, host u8 disparity maps out, `depth` pairs in flight
@@ -298,7 +307,7 @@ def main():
                 streamed.submit(il, ir, i)
             streamed.drain()
             return
-        dl_, dr_ = eng.match_pair(h_il.cuda(non_blocking=True), h_ir.cuda(non_blocking=True), packed, D, 5, out=out, workspace=ws, head=head)
+        dl_, dr_ = eng.match_pair(h_il.cuda(non_blocking=True), h_ir.cuda(non_blocking=True), packed, D, 5, out=out, workspace=ws, head=head, mode=a.mode)
         h_dl.copy_(dl_, non_blocking=True)
         h_dr.copy_(dr_, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller holds the result on the host
@@ -325,13 +334,15 @@ def main():
     stage = np.zeros(7, np.float32)
     reps = max(3, a.steps)
     for _ in range(reps):
-        eng.match_pair(d_il, d_ir, packed, D, 5, stage_ms=stage, out=out, workspace=ws, head=head)
+        eng.match_pair(d_il, d_ir, packed, D, 5, stage_ms=stage, out=out, workspace=ws, head=head, mode=a.mode)
     stage /= reps
-    sgm_launch_ms = float(stage[3]) / 7.0
+    n_sgm = 4 if a.mode == "fused" else 7
+    sgm_launch_ms = float(stage[3]) / n_sgm
     peak, peak_src = load_peaks()
-    alg_bytes_launch = 16.0 * evals / 7.0
+    alg_bytes_launch = 16.0 * evals / n_sgm
     achieved = alg_bytes_launch / (sgm_launch_ms * 1e-3) / 1e9
-    roofline = {"kernel": "sgm_scan_kernel (7 launches per pair: down+up fused, right, left, 4 diagonals, last + WTA)",
+    roofline = {"kernel": "sgm_chain_kernel x3 + sgm_fused_last_kernel (4 sweeps per pair: down+down-right+up, left+down-left, right+up-right, up-left+WTA)"
+                if a.mode == "fused" else "sgm_scan_kernel (7 launches per pair: down+up fused, right, left, 4 diagonals, last + WTA)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None,
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "avg_launch_ms": sgm_launch_ms,
@@ -355,7 +366,7 @@ def main():
                     "stage_ms": {"features": float(stage[0]), "cost_volume": float(stage[1]), "sgm": float(stage[3]),
                                  "lr_check_fill": float(stage[5]), "median": float(stage[6])}}
     tr = os.path.join(ROOT, "profiles", "sgm_traffic.json")
-    if os.path.exists(tr) and a.config == "c4" and head is None:  # the ncu capture is of the c4 launch
+    if os.path.exists(tr) and a.config == "c4" and head is None and a.mode == "exact":  # the ncu capture is of the c4 launch
         with open(tr) as f:
             t = json.load(f)
         roofline["traffic"] = t.get("dram_bytes_per_launch")
@@ -369,7 +380,8 @@ def main():
             tpk = float(json.load(f).get("bf16_tflops", tpk))
     sm_clk_hz, n_sm = 1.965e9, torch.cuda.get_device_properties(0).multi_processor_count
     conv_flop = 2.0 * H * W * 2 * (9 * 64 + 4 * 9 * 64 * 64)  # both images, useful fp32-equivalent FLOP
-    real_sgm_bytes = 76.0 * 2 * evals                          # the order-exact schedule: 8 + 5 x 12 + 8 bytes per evaluation and side
+    # bytes the SGM launches really move per evaluation and side: the order-exact schedule 8 + 5 x 12 + 8, the fused sweeps 8 + 12 + 12 + 8
+    real_sgm_bytes = (40.0 if a.mode == "fused" else 76.0) * 2 * evals
     stage_rooflines = {
         "conv_tower": {"bound": "tensor", "useful_tflops": conv_flop / (float(stage[0]) * 1e-3) / 1e12,
                        "issued_tflops": 3 * conv_flop / (float(stage[0]) * 1e-3) / 1e12, "peak_tflops": tpk,
@@ -377,9 +389,13 @@ def main():
                        "note": "fp32-class accuracy from fp16 MMAs: hi*hi + hi*lo + lo*hi, 3 MMAs per k-step"},
         "sgm_real_traffic": {"bound": "hbm", "bytes_per_pair": real_sgm_bytes, "achieved_gbs": real_sgm_bytes / (float(stage[3]) * 1e-3) / 1e9,
                              "peak_gbs": peak, "frac": real_sgm_bytes / (float(stage[3]) * 1e-3) / 1e9 / peak,
-                             "note": "what the 7 launches really move (ncu: no re-reads); the reference's per-path fp32 rounding of S fixes the pass structure"},
+                             "note": "what the 4 sweeps move: 40 B per evaluation and side" if a.mode == "fused" else
+                                     "what the 7 launches really move (ncu: no re-reads); the reference's per-path fp32 rounding of S fixes the pass structure"},
     }
-    if head is None:
+    if head is None and a.mode == "fused":
+        stage_rooflines["cost_volume"] = {"bound": "hbm (fp32-accumulated band GEMM)", "algorithmic_gbs": (2 * evals * 4 + 2 * H * W * 256) / (float(stage[1]) * 1e-3) / 1e9,
+                                          "peak_gbs": peak, "frac": (2 * evals * 4 + 2 * H * W * 256) / (float(stage[1]) * 1e-3) / 1e9 / peak}
+    elif head is None:
         prod = 64.0 * evals  # products of the exact cost volume (one value serves both volumes)
         stage_rooflines["cost_volume"] = {"bound": "fp32 pipe (exact fp64-accumulate contract)", "products_per_clk_per_sm":
                                           prod / (float(stage[1]) * 1e-3) / sm_clk_hz / n_sm, "pipe_limit_products_per_clk_per_sm": 128.0 / 3,
@@ -390,7 +406,7 @@ def main():
     # ---- N > 1: the same pair ALSO split by rows over all ranks (strong scaling of one pair): NVLink
     # peer-memory hand-off of the SGM path state inside the scan kernels, all_gather of the image / WTA bands
     sharded = None
-    if world > 1 and batch == 1 and head is None:
+    if world > 1 and batch == 1 and head is None and a.mode == "exact":
         try:
             from scenedepthestimation_b200 import sharded as sh
 
@@ -451,13 +467,14 @@ def main():
         emit(json.dumps({
             "metric": "pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(3, a.warmup), "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64" if head is None else "f16 x f16 -> f32 (head), f64 (SGM state)", "data": "synthetic", "config": config,
+            "vs_baseline": None, "dtype": ("f32" if a.mode == "fused" else "f64") if head is None else "f16 x f16 -> f32 (head), f64 (SGM state)",
+            "mode": a.mode, "data": "synthetic", "config": config,
             "gdisp_evals_per_sec": value * evals / 1e9,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 2 * H * W * batch,
                     "d2h_bytes_per_step": (2 * H * W * 4 if batch == 1 else H * W) * batch,
                     "api": "engine.match_pair (mccnn_match_pair) with pinned host u8 images in, host fp32 maps out" if batch == 1 else
                            "match.StreamedMatcher (match.py's loop): host u8 pairs in, host u8 disparity maps out"},
-            "gpu_launches": (kernels_per_step(D) + (3 if head is not None else 0) - (4 if head is not None and D >= 512 else 0)) * a.steps * batch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": (kernels_per_step(D, a.mode) + (3 if head is not None else 0) - (4 if head is not None and D >= 512 and a.mode == "exact" else 0)) * a.steps * batch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "single_pair_sharded": sharded}))
     if world > 1:
         dist.destroy_process_group()

@@ -50,7 +50,7 @@ class StreamedMatcher:
     host buffers and its own workspace, so the H2D copy, the kernels and the D2H copy of consecutive pairs overlap
     (and the latency-bound small-D kernels of two pairs share the SMs). Results come back in submission order."""
 
-    def __init__(self, H, W, weights, ndisp=128, scale=2, depth=2, num_layers=5):
+    def __init__(self, H, W, weights, ndisp=128, scale=2, depth=2, num_layers=5, mode="exact"):
         import torch
 
         from . import engine as eng
@@ -60,6 +60,7 @@ class StreamedMatcher:
         eng._require_cuda()
         self.torch, self.eng = torch, eng
         self.H, self.W, self.D, self.scale, self.nl = H, W, int(ndisp), int(scale), num_layers
+        self.mode = eng._mode(mode)   # "exact" (the reference's bits, default) or "fused" (opt-in throughput mode)
         self.wide = output_dtype(ndisp, scale) is np.uint16   # 16-bit maps where the reference's uint8 would wrap
         odt = torch.int16 if self.wide else torch.uint8       # int16 storage, reinterpreted as uint16 on the host
         self.packed = pf._load_weights(weights, num_layers)
@@ -92,7 +93,8 @@ class StreamedMatcher:
         slot["h_in"][1].copy_(torch.from_numpy(np.ascontiguousarray(right_u8)))
         with torch.cuda.stream(slot["stream"]):
             slot["d_in"].copy_(slot["h_in"], non_blocking=True)
-            eng.match_pair(slot["d_in"][0], slot["d_in"][1], self.packed, self.D, self.nl, out=slot["disp"], workspace=slot["ws"])
+            eng.match_pair(slot["d_in"][0], slot["d_in"][1], self.packed, self.D, self.nl, out=slot["disp"], workspace=slot["ws"],
+                           mode=self.mode)
             lib = eng._lib.load()
             if self.wide:   # trunc(d) * scale in 16 bits: mccnn_encode_u16 takes the scale as a power of two or the map is scaled after
                 eng._lib.check(lib.mccnn_encode_u16(slot["disp"][0].data_ptr(), slot["d_out"].data_ptr(), self.H, self.W, 0,

@@ -126,7 +126,7 @@ def WTA1(left_cost_volume):
     return _e.wta_dhw(_e._dev(left_cost_volume, torch.float32)).cpu().numpy()
 
 
-def disparity_compute_by_gpu(imagel, imager, featuresl, featuresr, detail_time, ndisp=None, params=None):
+def disparity_compute_by_gpu(imagel, imager, featuresl, featuresr, detail_time, ndisp=None, params=None, mode="exact"):
     """process_functional.py:1093-1267: u8 images + features -> (left disparity, right disparity, detail_time)."""
     _e._require_cuda()
     assert imagel.shape == imager.shape
@@ -134,7 +134,7 @@ def disparity_compute_by_gpu(imagel, imager, featuresl, featuresr, detail_time, 
     il, ir = _e._dev(imagel, torch.uint8), _e._dev(imager, torch.uint8)
     fl, fr = _e._dev(featuresl, torch.float32), _e._dev(featuresr, torch.float32)
     stage = np.zeros(7, np.float32)
-    dl, dr = _e.disparity_pipeline(il, ir, fl, fr, D, params=params, stage_ms=stage)
+    dl, dr = _e.disparity_pipeline(il, ir, fl, fr, D, params=params, stage_ms=stage, mode=mode)
     if detail_time is not None:
         detail_time += (stage / 1000.0).astype(detail_time.dtype)  # the reference accumulates seconds
     return dl.cpu().numpy(), dr.cpu().numpy(), detail_time
@@ -163,17 +163,18 @@ def _load_head(head):
     return _head_cache[key]
 
 
-def match_pair(left_u8, right_u8, checkpoint, ndisp=None, patch=11, detail_time=None, params=None, head=None):
+def match_pair(left_u8, right_u8, checkpoint, ndisp=None, patch=11, detail_time=None, params=None, head=None, mode="exact"):
     """Fused match_single.py:34-55: u8 pair -> (left disparity f32, right raw WTA f32), one C call. `head` (weights dict
     or .npy path with fc1..fc4) switches the matching cost to the MC-CNN-accurate decision head.
-    Weight dicts are recognised by content (a digest of the arrays), so a new or an updated dict is always repacked."""
+    Weight dicts are recognised by content (a digest of the arrays), so a new or an updated dict is always repacked.
+    mode="fused" selects the opt-in throughput mode (engine.FUSED: 1e-4 contract instead of the reference's bits)."""
     _e._require_cuda()
     D = int(NDISP if ndisp is None else ndisp)
     nl = patch // 2
     packed = _load_weights(checkpoint, nl)
     il, ir = _e._dev(left_u8, torch.uint8), _e._dev(right_u8, torch.uint8)
     stage = np.zeros(7, np.float32) if detail_time is not None else None
-    dl, dr = _e.match_pair(il, ir, packed, D, nl, params=params, stage_ms=stage, head=_load_head(head))
+    dl, dr = _e.match_pair(il, ir, packed, D, nl, params=params, stage_ms=stage, head=_load_head(head), mode=mode)
     if detail_time is not None:
         detail_time += (stage / 1000.0).astype(detail_time.dtype)
     return dl.cpu().numpy(), dr.cpu().numpy()
