@@ -119,6 +119,12 @@ int mccnn_cost_volume(const float* fl, const float* fr, float* CL, float* CR,
  * accumulator (|difference| <= 4e-6 on unit-norm features; not bit-identical to the reference). */
 int mccnn_cost_volume_fast(const float* fl, const float* fr, float* CL, float* CR,
                            int H, int W, int D, float fill, void* stream);
+/* The same on the tensor cores: features split into two fp16 numbers each, hi.hi + hi.lo + lo.hi accumulated in fp32 by
+ * tcgen05.mma (csrc/cost_volume_fast_tc.cu); |difference to the exact volume| ~1e-6. workspace:
+ * mccnn_cost_volume_fast_tc_workspace_bytes(H, W) bytes, 256-byte aligned. */
+size_t mccnn_cost_volume_fast_tc_workspace_bytes(int H, int W);
+int mccnn_cost_volume_fast_tc(const float* fl, const float* fr, float* CL, float* CR, void* workspace, size_t workspace_bytes,
+                              int H, int W, int D, float fill, void* stream);
 /* Tensor-core variant, same contract and the same bits out: the exact sum of f*g is taken from tcgen05 MMAs on 8-bit
  * slices of the features, the fp32 rounding residuals of the reference's products from the CUDA cores, and every
  * evaluation whose rounding cannot be proven is redone with the literal loop (csrc/cost_volume_tc.cu).

@@ -49,6 +49,8 @@ SIGNATURES = {
     "mccnn_conv_tower_fp32": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
     "mccnn_cost_volume": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "mccnn_cost_volume_fast": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "mccnn_cost_volume_fast_tc_workspace_bytes": (_sz, [_i, _i]),
+    "mccnn_cost_volume_fast_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp]),
     "mccnn_cost_volume_tc_workspace_bytes": (_sz, [_i, _i]),
     "mccnn_cost_volume_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _vp]),
     "mccnn_fc_matrix_blocks_bytes": (_sz, []),

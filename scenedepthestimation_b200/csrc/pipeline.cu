@@ -132,7 +132,13 @@ static int run_pipeline(const uint8_t* imageL, const uint8_t* imageR, const floa
         if (int e = mccnn_cost_volume_accurate(fl, fr, head, CL, CR, ws + l.fc_ws, l.end - l.fc_ws, H, W, D, 1.0f, stream)) return e;
     } else if (mode == MCCNN_SGM_FUSED) {
         // opt-in tolerance mode: fp32-accumulated cost volume (1e-4 contract of north_star, not the reference's bits)
-        if (int e = mccnn_cost_volume_fast(fl, fr, CL, CR, H, W, D, 1.0f, stream)) return e;
+        // (tensor-core band GEMM; its fp16 operand planes borrow the S volumes, idle until SGM)
+        const size_t ft_ws = mccnn_cost_volume_fast_tc_workspace_bytes(H, W);
+        if (ft_ws <= l.dl_wta - l.SL) {
+            if (int e = mccnn_cost_volume_fast_tc(fl, fr, CL, CR, ws + l.SL, l.dl_wta - l.SL, H, W, D, 1.0f, stream)) return e;
+        } else {
+            if (int e = mccnn_cost_volume_fast(fl, fr, CL, CR, H, W, D, 1.0f, stream)) return e;
+        }
     } else if (D >= 512 && tc_ws <= l.dl_wta - l.SL) {
         if (int e = mccnn_cost_volume_tc(fl, fr, CL, CR, ws + l.SL, l.dl_wta - l.SL, H, W, D, 1.0f, stream)) return e;
     } else {

@@ -31,7 +31,7 @@
 namespace mccnn {
 namespace {
 
-constexpr int FW_MAX = 8;   // warps per CTA of the chain kernel (6 for rows of 1024 floats: shared memory)
+constexpr int FW_MAX = 12;  // warps per CTA of the chain kernel (10 for rows of 1024 floats: shared memory)
 constexpr int RING = 2;     // hand-over slots between warps of one CTA (shared memory)
 constexpr int GRING = 8;    // hand-over slots between neighbouring CTAs (global memory)
 constexpr int INR = 4;      // rows of the global input link prefetched into shared memory (per CTA)
@@ -256,24 +256,28 @@ __device__ __forceinline__ float warp_wta(const float (&so)[NPL], int lane, int 
 //   per CTA  : inring [INR][SLOTF]  rows prefetched from the previous CTA's global ring (read by warp 0 only)
 //              prodc [FW], consc [FW] (unsigned)   counters of the links between the warps of the CTA
 //              mbarriers: FSTAGES per warp, then INR for inring
-template <int NPL>
+// Rows in flight per warp: a sweep that reads S as well has 2 x (cost + S) rows under way per warp; the first sweep (cost
+// only) needs 4 stages to keep as many bytes in flight (measured on c4: 20.5 -> see profiles, the sweep is bound by bytes in
+// flight x latency, not by the 8 warps' instruction rate).
+template <int NPL, bool READS>
 struct ChainSmem {
-    static constexpr int FW = NPL > 25 ? 6 : FW_MAX;
+    static constexpr int FW = NPL > 25 ? 10 : FW_MAX;
+    static constexpr int STG = READS ? 1 : 2;
+    static constexpr int NIN = READS ? 2 : 1;
     static constexpr int ROWF = 32 * NPL;
     static constexpr int SLOTF = ROWF + 4;
-    static constexpr int per_warp(int nin) { return ROWF * (FSTAGES * nin + 1) + RING * SLOTF; }
-    static constexpr size_t bytes(int nin) {
-        return (size_t)FW * per_warp(nin) * 4 + (size_t)INR * SLOTF * 4 + (size_t)2 * FW * 4 + (size_t)(FW * FSTAGES + INR) * 8;
-    }
+    static constexpr int PER_WARP = ROWF * (STG * NIN + 1) + RING * SLOTF;
+    static constexpr size_t BYTES = (size_t)FW * PER_WARP * 4 + (size_t)INR * SLOTF * 4 + (size_t)2 * FW * 4 + (size_t)(FW * STG + INR) * 8;
 };
 
 template <int NPL, bool READS>
-__global__ void __launch_bounds__(ChainSmem<NPL>::FW * 32) sgm_chain_kernel(const FusedArgs a) {
-    using L = ChainSmem<NPL>;
+__global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kernel(const FusedArgs a) {
+    using L = ChainSmem<NPL, READS>;
     constexpr int FW = L::FW;
+    constexpr int FSTAGES = L::STG;   // (shadows the file-level default)
     constexpr int ROWF = L::ROWF, SLOTF = L::SLOTF;
-    constexpr int NIN = READS ? 2 : 1;
-    constexpr int PER_WARP = L::per_warp(NIN);
+    constexpr int NIN = L::NIN;
+    constexpr int PER_WARP = L::PER_WARP;
     constexpr uint32_t SLOT_BYTES = SLOTF * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -762,9 +766,8 @@ FusedLayout fused_layout(int H, int W, int D) {
 
 template <int NPL, bool READS>
 int launch_chain(FusedArgs a, cudaStream_t stream) {
-    constexpr int NIN = READS ? 2 : 1;
-    constexpr int FW = ChainSmem<NPL>::FW;
-    const size_t smem = ChainSmem<NPL>::bytes(NIN);
+    constexpr int FW = ChainSmem<NPL, READS>::FW;
+    const size_t smem = ChainSmem<NPL, READS>::BYTES;
     int per_sm = 0;
     if (int e = kernel_setup<sgm_chain_kernel<NPL, READS>>(FW * 32, smem, &per_sm)) return e;
     MCCNN_REQUIRE(per_sm >= 1, MCCNN_EINVAL, "sgm_chain_kernel<%d>: does not fit on an SM (smem %zu)", NPL, smem);

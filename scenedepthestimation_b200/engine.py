@@ -138,14 +138,22 @@ def cost_volume(fl: torch.Tensor, fr: torch.Tensor, D: int, fill: float = 1.0, r
     return CL, CR
 
 
-def cost_volume_fast(fl: torch.Tensor, fr: torch.Tensor, D: int, fill: float = 1.0, right: bool = True):
-    """The fused mode's cost volume: fp32 FMA accumulation (not the reference's bits; |difference| <= 4e-6)."""
+def cost_volume_fast(fl: torch.Tensor, fr: torch.Tensor, D: int, fill: float = 1.0, right: bool = True, tensor_cores: bool = True):
+    """The fused mode's cost volume (not the reference's bits; |difference| <= 4e-6): on the tensor cores (fp16 hi/lo split,
+    fp32 accumulation in TMEM), or with tensor_cores=False the CUDA-core band GEMM with fp32 FMA accumulation."""
+    lib = _lib.load()
     H, W, F = fl.shape
     assert F == FEATURES and fr.shape == fl.shape
     Dp = disp_pitch(D)
     CL = torch.empty((H, W, Dp), dtype=torch.float32, device="cuda")
     CR = torch.empty((H, W, Dp), dtype=torch.float32, device="cuda") if right else None
-    _lib.check(_lib.load().mccnn_cost_volume_fast(_p(fl), _p(fr), _p(CL), _p(CR), H, W, D, float(fill), _stream()), "mccnn_cost_volume_fast")
+    if tensor_cores:
+        nws = lib.mccnn_cost_volume_fast_tc_workspace_bytes(H, W)
+        ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.mccnn_cost_volume_fast_tc(_p(fl), _p(fr), _p(CL), _p(CR), _p(ws), nws, H, W, D, float(fill), _stream()),
+                   "mccnn_cost_volume_fast_tc")
+    else:
+        _lib.check(lib.mccnn_cost_volume_fast(_p(fl), _p(fr), _p(CL), _p(CR), H, W, D, float(fill), _stream()), "mccnn_cost_volume_fast")
     return CL, CR
 
 

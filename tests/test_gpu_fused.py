@@ -75,13 +75,19 @@ def test_fused_sgm_equals_fused_oracle_full_size(eng, cfg):
     assert np.array_equal(dl.cpu().numpy(), st.wta(esl)) and np.array_equal(dr.cpu().numpy(), st.wta(esr))
 
 
-@pytest.mark.parametrize("H,W,D,kind", [(40, 200, 64, "tex"), (24, 90, 128, "noise"), (16, 2000, 800, "tex")])
-def test_fast_cost_volume_within_tolerance(eng, H, W, D, kind):
-    """mccnn_cost_volume_fast (fp32 FMA accumulation) against the reference-exact volume: north_star's bar is 1e-4 relative;
-    on unit-norm features (|cost| <= 1) the measured difference is a few 1e-7. Fills and pads are identical."""
+@pytest.mark.parametrize("tensor_cores", [True, False])
+@pytest.mark.parametrize("H,W,D,kind", [(40, 200, 64, "tex"), (24, 90, 128, "noise"), (16, 2000, 800, "tex"), (7, 300, 33, "noise"),
+                                        (3, 129, 1, "tex"), (5, 50, 200, "noise"), (33, 1000, 400, "tex")])
+def test_fast_cost_volume_within_tolerance(eng, H, W, D, kind, tensor_cores):
+    """The fused mode's cost volumes -- tcgen05 band GEMM on an fp16 hi/lo split (mccnn_cost_volume_fast_tc) and the CUDA-core
+    band GEMM with fp32 FMA accumulation (mccnn_cost_volume_fast) -- against the reference-exact volume: north_star's bar is 1e-4
+    relative; on unit-norm features (|cost| <= 1) the measured difference is below 4e-6. Fills and pads are identical. Shapes
+    cover partial tiles in x and u, D = 1, D > W and rows shorter than a tile."""
     _, _, fl, fr = _inputs(H, W, D, kind, 5)
     CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
-    FL, FR = eng.cost_volume_fast(dev(fl), dev(fr), D)
+    FL, FR = eng.cost_volume_fast(dev(fl), dev(fr), D, tensor_cores=tensor_cores)
+    FL2, _ = eng.cost_volume_fast(dev(fl), dev(fr), D, right=False, tensor_cores=tensor_cores)
+    assert torch.equal(FL.view(torch.int32), FL2.view(torch.int32))
     for a, b in ((CL, FL), (CR, FR)):
         fin = torch.isfinite(a)
         assert torch.equal(fin, torch.isfinite(b))
