@@ -405,6 +405,42 @@ def main():
 
     # ---- N > 1: the same pair ALSO split by rows over all ranks (strong scaling of one pair): NVLink
     # peer-memory hand-off of the SGM path state inside the scan kernels, all_gather of the image / WTA bands
+    # ---- the opt-in fused mode on the same pair, reported BESIDE the reference-exact headline (never instead of it): device-
+    # resident pairs/s, stage times, and how the result compares with the exact mode's on this very pair
+    fused = None
+    if a.mode == "exact" and batch == 1 and head is None:
+        try:
+            ref_l, ref_r = [t.clone() for t in eng.match_pair(d_il, d_ir, packed, D, 5, out=out, workspace=ws)]
+            for _ in range(3):
+                eng.match_pair(d_il, d_ir, packed, D, 5, out=out, workspace=ws, mode="fused")
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(a.steps):
+                eng.match_pair(d_il, d_ir, packed, D, 5, out=out, workspace=ws, mode="fused")
+            f1.record()
+            barrier()
+            fms = torch.tensor([f0.elapsed_time(f1)], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(fms, op=dist.ReduceOp.MAX)
+            fstage = np.zeros(7, np.float32)
+            for _ in range(reps):
+                fl_, fr_ = eng.match_pair(d_il, d_ir, packed, D, 5, stage_ms=fstage, out=out, workspace=ws, mode="fused")
+            fstage /= reps
+            fused = {"mode": "fused (MCCNN_SGM_FUSED): fp32 SGM state, 8 paths in 4 sweeps, tcgen05 cost volume on an fp16 hi/lo split; "
+                             "north_star's 1e-4 contract, not the reference's bits",
+                     "pairs_per_sec": world * a.steps / (float(fms.item()) / 1e3), "ms_per_pair": float(fms.item()) / a.steps,
+                     "stage_ms": {"features": float(fstage[0]), "cost_volume": float(fstage[1]), "sgm": float(fstage[3]),
+                                  "lr_check_fill": float(fstage[5]), "median": float(fstage[6])},
+                     "sgm_hbm_frac_on_real_bytes": 40.0 * 2 * evals / (float(fstage[3]) * 1e-3) / 1e9 / peak,
+                     "sgm_hbm_frac_on_algorithmic_bytes": 16.0 * evals / (float(fstage[3]) * 1e-3) / 1e9 / peak,
+                     "cost_volume_hbm_frac": (2 * evals * 4 + 2 * H * W * 256) / (float(fstage[1]) * 1e-3) / 1e9 / peak,
+                     "vs_exact_on_this_pair": {"left_map_pixels_differ": int((fl_ != ref_l).sum()), "right_wta_pixels_differ": int((fr_ != ref_r).sum()),
+                                               "pixels": H * W, "left_max_abs_diff": float((fl_ - ref_l).abs().max())},
+                     "census": "profiles/r02_fused_census.json"}
+        except Exception as exc:  # the headline line must be printed whatever happens here
+            fused = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     sharded = None
     if world > 1 and batch == 1 and head is None and a.mode == "exact":
         try:
@@ -475,7 +511,7 @@ def main():
                     "api": "engine.match_pair (mccnn_match_pair) with pinned host u8 images in, host fp32 maps out" if batch == 1 else
                            "match.StreamedMatcher (match.py's loop): host u8 pairs in, host u8 disparity maps out"},
             "gpu_launches": (kernels_per_step(D, a.mode) + (3 if head is not None else 0) - (4 if head is not None and D >= 512 and a.mode == "exact" else 0)) * a.steps * batch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "single_pair_sharded": sharded}))
+            "fused_mode": fused, "single_pair_sharded": sharded}))
     if world > 1:
         dist.destroy_process_group()
 
