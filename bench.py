@@ -494,6 +494,45 @@ def main():
         except Exception as exc:  # the one-pair-per-rank line above must be printed whatever happens here
             sharded = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
+    # ---- N > 1: BASELINE config 5 as well -- 256 KITTI-shaped pairs (1242x375, 228 disparities) dealt evenly to the ranks, several
+    # pairs in flight per GPU on their own streams (device-resident inputs; exact arithmetic), so that the scaling record carries it
+    c5 = None
+    if world > 1 and a.config == "c4" and batch == 1 and head is None and a.mode == "exact":
+        try:
+            W5, H5, D5 = syn.CONFIGS["c5"]
+            per_rank = 256 // world
+            i5l, i5r, _, _ = make_pair("c5", 1000 + 5 + rank)
+            d5l, d5r = torch.from_numpy(i5l).cuda(), torch.from_numpy(i5r).cuda()
+            nws5 = eng.match_workspace_bytes(H5, W5, D5, 5)
+            slots5 = [(torch.cuda.Stream(), torch.empty(nws5, dtype=torch.uint8, device="cuda"),
+                       (torch.empty((H5, W5), device="cuda"), torch.empty((H5, W5), device="cuda"))) for _ in range(a.depth)]
+
+            def step5():
+                cur = torch.cuda.current_stream()
+                for st, _, _ in slots5:
+                    st.wait_stream(cur)
+                for i in range(per_rank):
+                    st, w_, o_ = slots5[i % len(slots5)]
+                    with torch.cuda.stream(st):
+                        eng.match_pair(d5l, d5r, packed, D5, 5, out=o_, workspace=w_)
+                for st, _, _ in slots5:
+                    cur.wait_stream(st)
+
+            step5()
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            step5()
+            c1.record()
+            barrier()
+            cms = torch.tensor([c0.elapsed_time(c1)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(cms, op=dist.ReduceOp.MAX)
+            c5 = {"workload": f"c5: {per_rank * world} KITTI-shaped pairs {W5}x{H5}, {D5} disparities, {per_rank} per rank, {a.depth} in flight per GPU",
+                  "pairs_per_sec": per_rank * world / (float(cms.item()) / 1e3), "ms_total": float(cms.item()), "scaling": "weak"}
+            del slots5
+        except Exception as exc:
+            c5 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         v, t, desc = cpu_sample(il, ir, weights, D, a.cpu_seconds, threads, head_w)
@@ -511,7 +550,7 @@ def main():
                     "api": "engine.match_pair (mccnn_match_pair) with pinned host u8 images in, host fp32 maps out" if batch == 1 else
                            "match.StreamedMatcher (match.py's loop): host u8 pairs in, host u8 disparity maps out"},
             "gpu_launches": (kernels_per_step(D, a.mode) + (3 if head is not None else 0) - (4 if head is not None and D >= 512 and a.mode == "exact" else 0)) * a.steps * batch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "fused_mode": fused, "single_pair_sharded": sharded}))
+            "fused_mode": fused, "single_pair_sharded": sharded, "pair_batch_c5": c5}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -40,7 +40,9 @@ def timing(cfg):
     il, ir = torch.from_numpy(il).cuda(), torch.from_numpy(ir).cuda()
     lib = eng._lib.load()
     for name, fn in (("cost_volume exact", eng.cost_volume), ("cost_volume fast", eng.cost_volume_fast)):
-        out = fn(fl, fr, D); torch.cuda.synchronize()
+        for _ in range(2):
+            out = fn(fl, fr, D); torch.cuda.synchronize()
+            del out
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); out = fn(fl, fr, D); e1.record(); torch.cuda.synchronize()
         print(f"{cfg} {name}: {e0.elapsed_time(e1):.2f} ms", flush=True)
@@ -50,7 +52,9 @@ def timing(cfg):
     del ce
     for mode in ("exact", "fused"):
         for keep in (False,):
-            r = eng.sgm(CL, CR, il, ir, D, keep_volumes=keep, mode=mode); torch.cuda.synchronize()
+            for _ in range(2):
+                r = eng.sgm(CL, CR, il, ir, D, keep_volumes=keep, mode=mode); torch.cuda.synchronize()
+                del r
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); r = eng.sgm(CL, CR, il, ir, D, keep_volumes=keep, mode=mode); e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
