@@ -537,6 +537,29 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         v, t, desc = cpu_sample(il, ir, weights, D, a.cpu_seconds, threads, head_w)
         cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc}
+        if head is None:
+            # config 1 (463x370, 80 disparities: the reference's own CPU-runnable case) always, as a WHOLE
+            # pair (nothing extrapolated), with this repo's time for the same pair beside it
+            try:
+                W1, H1, D1 = syn.CONFIGS["c1"]
+                i1l, i1r, _, _ = make_pair("c1", 1001)
+                t1 = cpu_hot_path_band(i1l, i1r, weights, D1, H1, threads)
+                t1 = min(t1, cpu_hot_path_band(i1l, i1r, weights, D1, H1, threads))
+                g1l, g1r = torch.from_numpy(i1l).cuda(), torch.from_numpy(i1r).cuda()
+                ws1 = torch.empty(eng.match_workspace_bytes(H1, W1, D1, 5), dtype=torch.uint8, device="cuda")
+                for _ in range(3):
+                    eng.match_pair(g1l, g1r, packed, D1, 5, workspace=ws1)
+                torch.cuda.synchronize()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(10):
+                    eng.match_pair(g1l, g1r, packed, D1, 5, workspace=ws1)
+                g1.record()
+                torch.cuda.synchronize()
+                cpu["config1_whole_pair"] = {"workload": f"c1: {W1}x{H1}, {D1} disparities, whole pair, whole hot path", "cpu_seconds": t1,
+                                             "cpu_pairs_per_sec": 1.0 / t1, "gpu_ms_per_pair": g0.elapsed_time(g1) / 10}
+            except Exception as exc:
+                cpu["config1_whole_pair"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
     if rank == 0:
         emit(json.dumps({
