@@ -2,8 +2,8 @@
 
 NumPy in / NumPy out, like the reference; everything between runs on the B200 through the
 C ABI (engine.py -> libmccnn_b200.so). Differences a caller can see:
-  * `checkpoint` is the reference's .npy weight dict (Net.save_weights_dict, mc_cnn_brunch.py:61-66)
-    or such a dict; a TF1 .ckpt cannot be read without TensorFlow and raises;
+  * `checkpoint` is the reference's .npy weight dict (Net.save_weights_dict, mc_cnn_brunch.py:61-66), such a dict, or
+    the prefix of a tf.train.Saver checkpoint, read without TensorFlow by tf_checkpoint.py;
   * the disparity count is a parameter (`ndisp`, default 128 = the reference's hard-coded range,
     process_functional.py:125) instead of a constant;
   * the device is the current torch CUDA device, not the reference's cuda.select_device(1) (:1095);
@@ -70,12 +70,20 @@ def _load_weights(checkpoint, num_layers):
         key = ("dict", _content_key((n, weights[n]) for n in names), num_layers)
     else:
         path = os.fspath(checkpoint)
-        if not path.endswith(".npy"):
+        from . import tf_checkpoint as _tfc
+
+        if path.endswith(".npy"):
+            key = ("file", path, os.path.getmtime(path), num_layers)
+            weights = None
+        elif _tfc.is_checkpoint_prefix(path):
+            # a tf.train.Saver checkpoint prefix (what the reference passes, process_functional.py:11,33): read by this repo's own
+            # reader of the tensor-bundle format (tf_checkpoint.py; TensorFlow is not needed)
+            key = ("ckpt", path, os.path.getmtime(path + ".index"), num_layers)
+            weights = _tfc.checkpoint_to_weights(path) if key not in _weights_cache else None
+        else:
             raise RuntimeError(
-                f"checkpoint {path!r}: TensorFlow checkpoints cannot be read without TensorFlow; export the weights with "
-                "Net.save_weights_dict (mc_cnn_brunch.py:61-66) and pass the .npy file (or the dict itself)")
-        key = ("file", path, os.path.getmtime(path), num_layers)
-        weights = None
+                f"checkpoint {path!r}: neither a .npy weight dict (Net.save_weights_dict, mc_cnn_brunch.py:61-66) nor the prefix of "
+                "a tf.train.Saver checkpoint (<prefix>.index / <prefix>.data-00000-of-00001)")
     if key not in _weights_cache:
         if weights is None:
             weights = np.load(checkpoint, encoding="bytes", allow_pickle=True).item()

@@ -66,12 +66,14 @@ def test_argument_errors_without_gpu(lib):
     assert lib.mccnn_sgm(1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 4096,
                          2, 2, 8, C.byref(p), 0, 0, None) == -1
     assert b"too small" in lib.mccnn_last_error()
-    assert lib.mccnn_sgm(1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 4096,
+    big = 1 << 40   # (one workspace size serves the exact and the fused mode: tens of MB)
+    assert lib.mccnn_sgm_workspace_bytes(8, 8, 16) > 4096 and lib.mccnn_sgm_workspace_bytes(0, 8, 16) == 0
+    assert lib.mccnn_sgm(1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, big,
                          8, 8, 2000, C.byref(p), 0, 0, None) == -1
-    assert lib.mccnn_sgm(1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 4096,
+    assert lib.mccnn_sgm(1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, big,
                          8, 8, 16, C.byref(p), 7, 0, None) == -1
     assert b"mode" in lib.mccnn_last_error()
-    assert lib.mccnn_sgm(1 << 20, (1 << 20) + 4, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 4096,
+    assert lib.mccnn_sgm(1 << 20, (1 << 20) + 4, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, big,
                          8, 8, 16, C.byref(p), 0, 0, None) == -2
     assert lib.mccnn_disparity_pipeline(1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 16,
                                         8, 8, 16, C.byref(p), 0, None, None) == -3
@@ -116,10 +118,10 @@ def test_no_cpu_fallback(monkeypatch):
                                     np.zeros((4, 4, 64), np.float32), np.zeros((4, 4, 64), np.float32), np.zeros(7, np.float32))
 
 
-def test_tf_checkpoint_is_refused_loudly():
+def test_unknown_checkpoint_is_refused_loudly():
     from scenedepthestimation_b200 import process_functional as pf
 
-    with pytest.raises(RuntimeError, match="TensorFlow"):
+    with pytest.raises(RuntimeError, match="neither a .npy weight dict"):
         pf._load_weights("./check_points_11_11/model_epoch14.ckpt", 5)
 
 
