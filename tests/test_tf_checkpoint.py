@@ -61,9 +61,10 @@ def test_tf_checkpoint_primitives():
     assert tfc.crc32c(bytes(32)) == 0x8A9136AA and tfc.crc32c(bytes([0xFF] * 32)) == 0x62A8AB43
     c = tfc.crc32c(b"foo")
     assert tfc.masked_crc(b"foo") == (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
-    # "abcd" x 5 then 70 x "z": literal 'abcd', copy (1-byte-offset form) of 16 at offset 4, literal 'z', overlapping copies of 64 + 5
-    stream = (bytes([90]) + bytes([3 << 2]) + b"abcd" + bytes([((16 - 4) << 2) | 1, 4]) + bytes([0 << 2]) + b"z"
-              + bytes([((64 - 1) << 2) | 2, 1, 0]) + bytes([((5 - 1) << 2) | 2, 1, 0]))
+    # "abcd" x 5 then 70 x "z": literal 'abcd', overlapping copies of 8 (1-byte-offset form) and 8 (4-byte-offset form) at offset 4,
+    # literal 'z', overlapping copies of 64 + 5 at offset 1 (2-byte-offset form)
+    stream = (bytes([90]) + bytes([3 << 2]) + b"abcd" + bytes([((8 - 4) << 2) | 1, 4]) + bytes([((8 - 1) << 2) | 3, 4, 0, 0, 0])
+              + bytes([0 << 2]) + b"z" + bytes([((64 - 1) << 2) | 2, 1, 0]) + bytes([((5 - 1) << 2) | 2, 1, 0]))
     assert tfc._snappy_decompress(stream) == b"abcd" * 5 + b"z" * 70
     items = sorted((f"conv{i}/weights".encode(), bytes([i]) * (i + 1)) for i in range(1, 40))
     block = tfc._build_block(items, restart_interval=4)
