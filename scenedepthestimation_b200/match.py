@@ -23,6 +23,8 @@ parser.add_argument("--image-dir", type=str, default="./test/")
 parser.add_argument("--out-dir", type=str, default="./disparity/")
 parser.add_argument("--first", type=int, default=1)
 parser.add_argument("--last", type=int, default=18)
+parser.add_argument("--mode", type=str, default="exact", choices=["exact", "fused"], help="exact: the reference's arithmetic bit for bit; "
+                    "fused: the opt-in throughput mode (1e-4 contract)")
 parser.add_argument("--depth", type=int, default=3, help="pairs in flight on separate CUDA streams (1 = the reference's "
                     "strictly sequential loop, with the per-stage times of match.py:95-103 printed at the end)")
 
@@ -32,7 +34,7 @@ def shard(ids, rank: int, world: int):
     return list(ids)[rank::world]
 
 
-def match_batch(pairs, weights, ndisp=128, scale=2, detail_time=None):
+def match_batch(pairs, weights, ndisp=128, scale=2, detail_time=None, mode="exact"):
     """pairs: iterable of (left_u8, right_u8) -> list of integer maps (match.py:90 writes uint8*2; uint16 where that would
     wrap, match_single.output_dtype)."""
     from . import process_functional as pf
@@ -40,7 +42,7 @@ def match_batch(pairs, weights, ndisp=128, scale=2, detail_time=None):
 
     out = []
     for left, right in pairs:
-        dl, _ = pf.match_pair(left, right, weights, ndisp=ndisp, detail_time=detail_time)
+        dl, _ = pf.match_pair(left, right, weights, ndisp=ndisp, detail_time=detail_time, mode=mode)
         out.append(encode_disparity(dl, ndisp, scale))
     return out
 
@@ -119,12 +121,12 @@ class StreamedMatcher:
         return out
 
 
-def match_stream(pairs, weights, ndisp=128, scale=2, depth=2):
+def match_stream(pairs, weights, ndisp=128, scale=2, depth=2, mode="exact"):
     """Generator over (left_u8, right_u8) pairs of one shape -> uint8 maps in order, `depth` pairs in flight."""
     m = None
     for i, (left, right) in enumerate(pairs):
         if m is None:
-            m = StreamedMatcher(left.shape[0], left.shape[1], weights, ndisp, scale, depth)
+            m = StreamedMatcher(left.shape[0], left.shape[1], weights, ndisp, scale, depth, mode=mode)
         r = m.submit(left, right, i)
         if r is not None:
             yield r[1]
@@ -162,7 +164,7 @@ def main(argv=None):
 
     if args.depth <= 1:
         for i in ids:
-            write(i, match_batch([read(i)], weights, args.ndisp, 2, detail_time)[0])
+            write(i, match_batch([read(i)], weights, args.ndisp, 2, detail_time, mode=args.mode)[0])
         names = ["features", "cost volume", '"*" cost aggregation', "SGM", "WTA & Subpixel refinement", "LR Check", "Filtering"]
         for n, t in zip(names, detail_time):
             print('time of {}: {}s'.format(n, t))
@@ -176,7 +178,7 @@ def main(argv=None):
             if m is not None:
                 for tag, img in m.drain():
                     write(tag, img)
-            m, shape = StreamedMatcher(left.shape[0], left.shape[1], weights, args.ndisp, 2, args.depth), left.shape
+            m, shape = StreamedMatcher(left.shape[0], left.shape[1], weights, args.ndisp, 2, args.depth, mode=args.mode), left.shape
         done = m.submit(left, right, i)
         if done is not None:
             write(*done)

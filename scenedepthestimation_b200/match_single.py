@@ -23,6 +23,8 @@ parser.add_argument("--weights", type=str, default="./check_points_11_11/model_e
 parser.add_argument("--ndisp", type=int, default=128, help="disparity range (the reference hard-codes 128)")
 parser.add_argument("--image-dir", type=str, default="./eval/")
 parser.add_argument("--scale", type=int, default=1, help="multiply the uint8 map (match_single_ui.py uses 2)")
+parser.add_argument("--mode", type=str, default="exact", choices=["exact", "fused"], help="exact: the reference's arithmetic bit for bit; "
+                    "fused: the opt-in throughput mode (1e-4 contract, about twice as fast on large pairs)")
 parser.add_argument("--pfm", action="store_true", help="also write the fp32 map as ./result/{file}/ld{id}.pfm")
 parser.add_argument("--head-weights", type=str, default=None, help="MC-CNN-accurate: .npy dict with fc1..fc4 (fc() naming of "
                     "mc_cnn_brunch.py:95-106), or 'random'; the matching cost is then the fully-connected decision head")
@@ -41,12 +43,12 @@ def encode_disparity(disparity_f32: np.ndarray, ndisp: int, scale: int = 1) -> n
     return (disparity_f32.astype(dt) * dt(scale)).astype(dt)
 
 
-def match_images(left_u8: np.ndarray, right_u8: np.ndarray, weights, ndisp: int = 128, scale: int = 1, head=None) -> np.ndarray:
+def match_images(left_u8: np.ndarray, right_u8: np.ndarray, weights, ndisp: int = 128, scale: int = 1, head=None, mode="exact") -> np.ndarray:
     """match_single.py:34-55 for in-memory images -> the integer map the reference would write (uint8; uint16 for ranges
     the reference's uint8 cannot hold, see output_dtype)."""
     from . import process_functional as pf
 
-    left_disparity, _ = pf.match_pair(left_u8, right_u8, weights, ndisp=ndisp, head=head)
+    left_disparity, _ = pf.match_pair(left_u8, right_u8, weights, ndisp=ndisp, head=head, mode=mode)
     return encode_disparity(left_disparity, ndisp, scale)
 
 
@@ -68,7 +70,7 @@ def main(argv=None):
     head = synthetic.glorot_fc_weights() if args.head_weights == 'random' else args.head_weights
     from . import process_functional as pf
 
-    left_disparity, _ = pf.match_pair(left, right, weights, ndisp=args.ndisp, head=head)
+    left_disparity, _ = pf.match_pair(left, right, weights, ndisp=args.ndisp, head=head, mode=args.mode)
     out_dir = './result/{}'.format(args.file)
     os.makedirs(out_dir, exist_ok=True)
     # 8-bit PNG as in the reference; 16-bit where uint8 would wrap (output_dtype)

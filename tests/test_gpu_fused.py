@@ -143,3 +143,40 @@ def test_fused_mode_is_opt_in_and_validated(eng):
     rc = lib.mccnn_sgm(CL.data_ptr(), CR.data_ptr(), dev(il).data_ptr(), dev(ir).data_ptr(), S.data_ptr(), S.data_ptr(), d.data_ptr(),
                        d.data_ptr(), ws.data_ptr(), ws.numel(), 12, 20, 8, C.byref(p), 7, 1, None)
     assert rc == -1 and b"unknown mode" in lib.mccnn_last_error()
+
+
+def test_fused_mode_through_the_drop_ins_and_optional_stages(eng, tmp_path, monkeypatch):
+    """The fused mode behind every entry a user has: process_functional, the streamed batch loop (several cooperative launches
+    in flight on their own streams), the CLIs' --mode flag; with the optional stages (sub-pixel refinement fused into the last
+    sweep, cross-based aggregation in front of it, bilateral filter behind it)."""
+    import os
+
+    cv2 = pytest.importorskip("cv2")
+    from oracle import stereo as st
+    from scenedepthestimation_b200 import match, match_single, process_functional as pf, synthetic as syn
+
+    H, W, D = 48, 160, 64
+    il, ir, fl, fr = _inputs(H, W, D, "tex", 21)
+    # sub-pixel refinement inside the last sweep == the oracle's refinement of the fused oracle's volume
+    prm = pf.sgm_params(subpixel=1)
+    CL, CR = eng.cost_volume_fast(dev(fl), dev(fr), D)
+    _, _, dl, dr = eng.sgm(CL, CR, dev(il), dev(ir), D, params=prm, keep_volumes=False, mode="fused")
+    esl, esr = st.sgm_all_paths_fused(CL[..., :D].cpu().numpy(), CR[..., :D].cpu().numpy(), st.sgm_penalties(il), st.sgm_penalties(ir))
+    assert np.array_equal(dl.cpu().numpy(), st.wta_subpixel(esl)) and np.array_equal(dr.cpu().numpy(), st.wta_subpixel(esr))
+    # pipeline with aggregation + bilateral in both modes: same stages, tolerance-close results
+    prm2 = pf.sgm_params(cbca_iters=1, bilateral=1)
+    a, _, _ = pf.disparity_compute_by_gpu(il, ir, fl, fr, None, ndisp=D, params=prm2)
+    b, _, _ = pf.disparity_compute_by_gpu(il, ir, fl, fr, None, ndisp=D, params=prm2, mode="fused")
+    assert float(np.mean(np.abs(a - b) > 1e-3)) <= 0.02
+    # streamed loop and CLIs
+    w = syn.glorot_weights()
+    pairs = [syn.textured_pair(H, W, D, 30 + i)[:2] for i in range(5)]
+    seq = match.match_batch(pairs, w, ndisp=D, scale=2, mode="fused")
+    streamed = list(match.match_stream(pairs, w, ndisp=D, scale=2, depth=3, mode="fused"))
+    assert len(streamed) == 5 and all(np.array_equal(x, y) for x, y in zip(seq, streamed))
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("eval")
+    cv2.imwrite("eval/left_0.png", pairs[0][0]), cv2.imwrite("eval/right_0.png", pairs[0][1])
+    match_single.main(["-i", "0", "-f", "f", "--weights", "random", "--ndisp", str(D), "--mode", "fused"])
+    got = cv2.imread("result/f/ld0.png", cv2.IMREAD_UNCHANGED)
+    assert np.array_equal(got, match_single.match_images(pairs[0][0], pairs[0][1], w, D, 1, mode="fused"))
