@@ -441,58 +441,72 @@ def main():
         except Exception as exc:  # the headline line must be printed whatever happens here
             fused = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
+    def sharded_pair(mode):
+        """One pair over all ranks in `mode`: ms per pair (device time, max over ranks) and the result compared, in the run, with
+        the single-GPU path of the same mode on rank 0."""
+        from scenedepthestimation_b200 import sharded as sh
+
+        eng._ws.clear()
+        torch.cuda.empty_cache()
+        il0, ir0, _, _ = make_pair(a.config, 1000 + 4)  # every rank cuts its band out of rank 0's pair
+        m = sh.ShardedMatcher(H, W, D, weights, mode=mode)
+        bl = torch.from_numpy(np.ascontiguousarray(il0[m.row0:m.row0 + m.rows])).cuda()
+        br = torch.from_numpy(np.ascontiguousarray(ir0[m.row0:m.row0 + m.rows])).cuda()
+        for _ in range(2):
+            m.match(bl, br)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(a.steps):
+            m.match(bl, br, check=False)   # no host round trip per pair; the status of the last pair is read below
+        s1.record()
+        barrier()
+        m.status()
+        sms = torch.tensor([s0.elapsed_time(s1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        # checked, not asserted: rank 0 runs the SAME pair through the single-GPU path and compares both output maps bit
+        # for bit with what the sharded run left on every rank (the maps are all-gathered, so each rank holds whole maps)
+        sdl, sdr = m.match(bl, br)
+        identical, max_diff = torch.ones(1, device="cuda", dtype=torch.int32), torch.zeros(1, device="cuda", dtype=torch.float64)
+        if rank == 0:
+            ws1 = torch.empty(eng.match_workspace_bytes(H, W, D, 5), dtype=torch.uint8, device="cuda")
+            rdl, rdr = eng.match_pair(torch.from_numpy(il0).cuda(), torch.from_numpy(ir0).cuda(), packed, D, 5, workspace=ws1, mode=mode)
+            same = torch.equal(sdl.view(torch.int32), rdl.view(torch.int32)) and torch.equal(sdr.view(torch.int32), rdr.view(torch.int32))
+            identical.fill_(1 if same else 0)
+            max_diff.fill_(max(float((sdl - rdl).abs().max()), float((sdr - rdr).abs().max())))
+            del ws1, rdl, rdr
+        # every rank holds the same gathered maps: a checksum over ranks must agree with rank 0's
+        chk = torch.stack([sdl.double().sum(), sdr.double().sum()])
+        chk_max, chk_min = chk.clone(), chk.clone()
+        dist.all_reduce(chk_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(chk_min, op=dist.ReduceOp.MIN)
+        dist.broadcast(identical, 0)
+        dist.broadcast(max_diff, 0)
+        del m
+        torch.cuda.empty_cache()
+        return {"ms_per_pair": float(sms.item()) / a.steps, "pairs_per_sec": a.steps / (float(sms.item()) / 1e3),
+                "scaling": "strong",
+                "bit_identical": bool(identical.item()) and bool(torch.equal(chk_max, chk_min)),
+                "max_abs_diff": float(max_diff.item()),
+                "checked_against": f"engine.match_pair (single-GPU path, {mode} mode) on the same pair, rank 0; both output maps compared as raw "
+                                   "bits; per-rank checksums of the gathered maps agree"}
+
     sharded = None
     if world > 1 and batch == 1 and head is None and a.mode == "exact":
+        del ws
         try:
-            from scenedepthestimation_b200 import sharded as sh
-
-            del ws
-            eng._ws.clear()
-            torch.cuda.empty_cache()
-            il0, ir0, _, _ = make_pair(a.config, 1000 + 4)  # every rank cuts its band out of rank 0's pair
-            m = sh.ShardedMatcher(H, W, D, weights)
-            bl = torch.from_numpy(np.ascontiguousarray(il0[m.row0:m.row0 + m.rows])).cuda()
-            br = torch.from_numpy(np.ascontiguousarray(ir0[m.row0:m.row0 + m.rows])).cuda()
-            for _ in range(2):
-                m.match(bl, br)
-            barrier()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            for _ in range(a.steps):
-                m.match(bl, br, check=False)   # no host round trip per pair; the status of the last pair is read below
-            s1.record()
-            barrier()
-            m.status()
-            sms = torch.tensor([s0.elapsed_time(s1)], device="cuda", dtype=torch.float64)
-            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
-            # checked, not asserted: rank 0 runs the SAME pair through the single-GPU path and compares both output maps bit
-            # for bit with what the sharded run left on every rank (the maps are all-gathered, so each rank holds whole maps)
-            sdl, sdr = m.match(bl, br)
-            identical, max_diff = torch.ones(1, device="cuda", dtype=torch.int32), torch.zeros(1, device="cuda", dtype=torch.float64)
-            if rank == 0:
-                ws1 = torch.empty(eng.match_workspace_bytes(H, W, D, 5), dtype=torch.uint8, device="cuda")
-                rdl, rdr = eng.match_pair(torch.from_numpy(il0).cuda(), torch.from_numpy(ir0).cuda(), packed, D, 5, workspace=ws1)
-                same = torch.equal(sdl.view(torch.int32), rdl.view(torch.int32)) and torch.equal(sdr.view(torch.int32), rdr.view(torch.int32))
-                identical.fill_(1 if same else 0)
-                max_diff.fill_(max(float((sdl - rdl).abs().max()), float((sdr - rdr).abs().max())))
-                del ws1, rdl, rdr
-            # every rank holds the same gathered maps: a checksum over ranks must agree with rank 0's
-            chk = torch.stack([sdl.double().sum(), sdr.double().sum()])
-            chk_max, chk_min = chk.clone(), chk.clone()
-            dist.all_reduce(chk_max, op=dist.ReduceOp.MAX)
-            dist.all_reduce(chk_min, op=dist.ReduceOp.MIN)
-            dist.broadcast(identical, 0)
-            dist.broadcast(max_diff, 0)
-            sharded = {"ms_per_pair": float(sms.item()) / a.steps, "pairs_per_sec": a.steps / (float(sms.item()) / 1e3),
-                       "scaling": "strong",
-                       "bit_identical": bool(identical.item()) and bool(torch.equal(chk_max, chk_min)),
-                       "max_abs_diff": float(max_diff.item()),
-                       "checked_against": "engine.match_pair (single-GPU path) on the same pair, rank 0; both output maps compared as raw bits; "
-                                          "per-rank checksums of the gathered maps agree",
-                       "partition": f"{world} row bands of one pair; conv/cost volume/horizontal SGM band-local, "
-                       "vertical+diagonal SGM path state handed over NVLink peer memory inside the scan kernel"}
+            sharded = sharded_pair("exact")
+            sharded["partition"] = (f"{world} row bands of one pair; conv/cost volume/horizontal SGM band-local, "
+                                    "vertical+diagonal SGM path state handed over NVLink peer memory inside the scan kernel")
         except Exception as exc:  # the one-pair-per-rank line above must be printed whatever happens here
             sharded = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        try:   # the opt-in fused mode on the same bands, beside the exact number (compared with the single-GPU FUSED result)
+            fs = sharded_pair("fused")
+            fs["partition"] = (f"{world} row bands; the two row sweeps of the fused SGM advance in lock step on all ranks (one fp32 state per "
+                               "step streamed to the neighbour over NVLink), the column and diagonal sweeps hand over per scanline")
+            sharded["fused_mode"] = fs
+        except Exception as exc:
+            sharded["fused_mode"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # ---- N > 1: BASELINE config 5 as well -- 256 KITTI-shaped pairs (1242x375, 228 disparities) dealt evenly to the ranks, several
     # pairs in flight per GPU on their own streams (device-resident inputs; exact arithmetic), so that the scaling record carries it

@@ -226,6 +226,21 @@ int mccnn_sgm_sharded(const float* CLb, const float* CRb, const uint8_t* imageL,
                       int W, int D, const mccnn_sgm_params* params, int mode, int keep_volumes,
                       const mccnn_shard* shard, int pass_mask, void* stream);
 
+/* The same split for the opt-in fused mode (MCCNN_SGM_FUSED, csrc/sgm_fused.cu): band-local volumes, whole images, neighbours'
+ * exchange buffers in peer memory. Sweeps 1 and 2 walk image rows, and a row needs only the PREVIOUS step of its neighbour row,
+ * so the bands of all ranks advance in lock step: the last row of a band streams one state per step into the next rank's buffer
+ * (bulk copies over NVLink, epoch-tagged counter), no pipeline fill. Sweep 0 (columns) and sweep 3 (diagonal scanlines) run
+ * through the ranks one after the other, their states handed over per column / scanline as in mccnn_sgm_sharded. The result
+ * equals the unsharded fused mode value for value.
+ *  exchange buffers: mccnn_sgm_fused_shard_exchange_bytes(W, D) bytes each; epoch, go_flag, timeout_ms as above
+ *  sweep_mask: bit s launches sweep s of 4 (15 = all); partial masks let a test run several bands on one GPU in dependency
+ *              order (sweeps 0, 1: bands top-down; sweeps 2, 3: bottom-up). */
+size_t mccnn_sgm_fused_shard_exchange_bytes(int W, int D);
+int mccnn_sgm_fused_sharded(const float* CLb, const float* CRb, const uint8_t* imageL, const uint8_t* imageR,
+                            float* SLb, float* SRb, float* dispLb, float* dispRb, void* workspace, size_t workspace_bytes,
+                            int W, int D, const mccnn_sgm_params* params, int keep_volumes,
+                            const mccnn_shard* shard, int sweep_mask, void* stream);
+
 /* After mccnn_sgm_sharded: synchronises the stream and returns the launch's status word in *status_host
  * (0 = every scanline got its hand-over; 1 = a wait hit the deadline, the outputs are invalid). */
 int mccnn_sgm_shard_status(const void* workspace, int* status_host, void* stream);

@@ -64,6 +64,8 @@ SIGNATURES = {
     "mccnn_sgm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _PP, _i, _i, _vp]),
     "mccnn_sgm_shard_exchange_bytes": (_sz, [_i]),
     "mccnn_sgm_sharded": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _PP, _i, _i, C.POINTER(Shard), _i, _vp]),
+    "mccnn_sgm_fused_shard_exchange_bytes": (_sz, [_i, _i]),
+    "mccnn_sgm_fused_sharded": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _PP, _i, C.POINTER(Shard), _i, _vp]),
     "mccnn_sgm_shard_status": (_i, [_vp, C.POINTER(_i), _vp]),
     "mccnn_sgm_single_path": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _PP, _i, _vp]),
     "mccnn_wta": (_i, [_vp, _vp, _i, _i, _i, _vp]),

@@ -30,6 +30,10 @@ namespace mccnn {
 size_t sgm_fused_workspace_bytes(int H, int W, int D);
 int run_sgm_fused(const float* CL, const float* CR, const uint8_t* imageL, const uint8_t* imageR, float* SL, float* SR, float* dispL,
                   float* dispR, void* workspace, int H, int W, int D, const mccnn_sgm_params* p, int keep_volumes, cudaStream_t stream);
+size_t sgm_fused_xchg_bytes(int W, int D);
+int run_sgm_fused_band(const float* CLb, const float* CRb, const uint8_t* imageL, const uint8_t* imageR, float* SLb, float* SRb,
+                       float* dispLb, float* dispRb, void* workspace, int W, int D, const mccnn_sgm_params* p, int keep_volumes,
+                       const mccnn_shard* sh, int sweep_mask, cudaStream_t stream);
 namespace {
 
 enum SgmMode { SGM_MID = 0, SGM_FIRST_FUSED = 1, SGM_LAST_WTA = 2 };
@@ -737,6 +741,39 @@ extern "C" int mccnn_sgm_sharded(const float* CLb, const float* CRb, const uint8
     MCCNN_REQUIRE(params->P1 >= 0 && params->P1_red >= 0, MCCNN_EINVAL, "mccnn_sgm_sharded: negative P1");
     return run_sgm(CLb, CRb, imageL, imageR, SLb, SRb, dispLb, dispRb, workspace, H, W, D, params, keep_volumes, shard,
                    pass_mask & 0x7f, stream);
+}
+
+extern "C" size_t mccnn_sgm_fused_shard_exchange_bytes(int W, int D) {
+    if (W < 1 || D < 1 || D > 1024) return 0;
+    return sgm_fused_xchg_bytes(W, D);
+}
+
+extern "C" int mccnn_sgm_fused_sharded(const float* CLb, const float* CRb, const uint8_t* imageL, const uint8_t* imageR, float* SLb,
+                                       float* SRb, float* dispLb, float* dispRb, void* workspace, size_t workspace_bytes, int W, int D,
+                                       const mccnn_sgm_params* params, int keep_volumes, const mccnn_shard* shard, int sweep_mask,
+                                       void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MCCNN_REQUIRE(shard != nullptr, MCCNN_EINVAL, "mccnn_sgm_fused_sharded: null shard");
+    const int H = shard->H_full;
+    if (int e = check_common(CLb, H, W, D)) return e;
+    MCCNN_REQUIRE(CRb && SLb && SRb && imageL && imageR && dispLb && dispRb && params && workspace, MCCNN_EINVAL,
+                  "mccnn_sgm_fused_sharded: null argument");
+    MCCNN_REQUIRE(workspace_bytes >= mccnn_sgm_workspace_bytes(H, W, D), MCCNN_EWORKSPACE, "mccnn_sgm_fused_sharded: workspace too small");
+    MCCNN_REQUIRE(aligned16(CLb) && aligned16(CRb) && aligned16(SLb) && aligned16(SRb) && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+                  MCCNN_EALIGN, "mccnn_sgm_fused_sharded: volumes must be 16-byte, the workspace 256-byte aligned");
+    MCCNN_REQUIRE(shard->world >= 1 && shard->rank >= 0 && shard->rank < shard->world && shard->rows >= 1 && shard->row0 >= 0 &&
+                      shard->row0 + shard->rows <= H,
+                  MCCNN_EINVAL, "mccnn_sgm_fused_sharded: bad band rank=%d/%d rows [%d,+%d) of %d", shard->rank, shard->world,
+                  shard->row0, shard->rows, H);
+    MCCNN_REQUIRE((shard->rank == 0) == (shard->row0 == 0) && (shard->rank == shard->world - 1) == (shard->row0 + shard->rows == H),
+                  MCCNN_EINVAL, "mccnn_sgm_fused_sharded: the bands must tile the image in rank order");
+    MCCNN_REQUIRE(shard->world == 1 || (shard->xchg_local != nullptr && shard->epoch != 0), MCCNN_EINVAL,
+                  "mccnn_sgm_fused_sharded: exchange buffer and a non-zero epoch are required");
+    MCCNN_REQUIRE((shard->rank == 0 || shard->xchg_prev != nullptr) && (shard->rank == shard->world - 1 || shard->xchg_next != nullptr),
+                  MCCNN_EINVAL, "mccnn_sgm_fused_sharded: missing peer exchange pointer");
+    MCCNN_REQUIRE(params->P1 >= 0 && params->P1_red >= 0, MCCNN_EINVAL, "mccnn_sgm_fused_sharded: negative P1");
+    return run_sgm_fused_band(CLb, CRb, imageL, imageR, SLb, SRb, dispLb, dispRb, workspace, W, D, params, keep_volumes, shard,
+                              sweep_mask & 15, stream);
 }
 
 extern "C" int mccnn_sgm_shard_status(const void* workspace, int* status_host, void* stream_) {

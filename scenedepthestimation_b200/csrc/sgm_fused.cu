@@ -34,6 +34,7 @@ namespace {
 constexpr int FW_MAX = 12;  // warps per CTA of the chain kernel (10 for rows of 1024 floats: shared memory)
 constexpr int RING = 2;     // hand-over slots between warps of one CTA (shared memory)
 constexpr int GRING = 8;    // hand-over slots between neighbouring CTAs (global memory)
+constexpr int XPUB = 4;    // a band's last unit publishes its rows to the neighbour rank every XPUB steps, XPUB steps late
 constexpr int INR = 4;      // rows of the global input link prefetched into shared memory (per CTA)
 constexpr int FSTAGES = 2;  // rows in flight per warp and stream
 constexpr int FLAG_STRIDE = 32;  // unsigned words between two flags (one 128-byte line each)
@@ -58,6 +59,20 @@ struct FusedArgs {
     int slot_floats;  // 32 * NPL + 4
     unsigned* counter;  // sweep 3: scanline counter
     int debug;          // development only (MCCNN_FUSED_DEBUG): bit 0 = never wait for a hand-over (wrong results, timing only)
+    // ---- row-band sharding (BAND kernels; one pair split over several GPUs, mccnn_sgm_fused_sharded): this launch owns image rows
+    // [row0, row0 + Hb) of H; the volumes and maps it is given hold only those rows, the u8 images are whole. What crosses a
+    // band boundary travels through the neighbours' exchange buffers (peer memory): see the layout in fused_xchg_layout().
+    int row0, Hb;
+    unsigned epoch;
+    const float* ent_in;  const unsigned* ent_flag_in;     // sweep 0: states of row row0 - 1 per column, written by the rank above
+    float* ent_out;       unsigned* ent_flag_out;          //          ... of my last row, into the rank below
+    const float* ext_in;  const unsigned long long* ext_prod_in;   // sweeps 1, 2: the row FIFO feeding my first unit
+    float* ext_out;       unsigned long long* ext_prod_out;        //              ... fed by my last unit (neighbour's memory)
+    const float* hand_in; const unsigned* hand_flag_in;    // sweep 3: state of a scanline entering from the rank below
+    float* hand_out;      unsigned* hand_flag_out;         //          ... leaving into the rank above
+    const int* go;                 // all ranks agreed to launch (0 = return at once); may be null
+    unsigned* status;              // set to 1 when a cross-rank wait hit the deadline (results invalid)
+    unsigned long long timeout_ns;
 };
 
 // ------------------------------------------------------------------------------------------------ small device helpers
@@ -89,6 +104,45 @@ __device__ __forceinline__ void bulk_wait_all_elect() {   // full completion (wr
         "}" ::"n"(N)
         : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Wait (lane 0 polls, the warp follows) until a flag written by ANOTHER GPU equals `want`; gives up at the deadline, or at once
+// when some warp has already given up: a rank that died or never launched cannot wedge this one (the results are then invalid
+// and *status says so).
+__device__ __forceinline__ void wait_peer_flag(const unsigned* flag, unsigned want, unsigned* status, unsigned long long timeout_ns, int lane) {
+    if (lane == 0) {
+        const unsigned long long t0 = timer_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys_u32(flag) != want) {
+            __nanosleep(64);
+            if ((++spins & 63u) == 0) {
+                if (*reinterpret_cast<volatile unsigned*>(status) != 0u) break;
+                if (timer_ns() - t0 > timeout_ns) { atomicExch(status, 1u); break; }
+            }
+        }
+    }
+    __syncwarp();
+}
+
 __device__ __forceinline__ unsigned ld_acquire_cta_smem(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
@@ -270,8 +324,11 @@ struct ChainSmem {
     static constexpr size_t BYTES = (size_t)FW * PER_WARP * 4 + (size_t)INR * SLOTF * 4 + (size_t)2 * FW * 4 + (size_t)(FW * STG + INR) * 8;
 };
 
-template <int NPL, bool READS>
+template <int NPL, bool READS, bool BAND>
 __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kernel(const FusedArgs a) {
+    if constexpr (BAND) {
+        if (a.go != nullptr && *reinterpret_cast<const volatile int*>(a.go) == 0) return;   // some rank will not launch: nobody waits
+    }
     using L = ChainSmem<NPL, READS>;
     constexpr int FW = L::FW;
     constexpr int FSTAGES = L::STG;   // (shadows the file-level default)
@@ -307,8 +364,9 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
     __syncthreads();
 
     const int side = blockIdx.x / a.ctas, cta = blockIdx.x - side * a.ctas;
-    const int n = a.ctas * FW;                 // warps of this chain
-    const int w = cta * FW + warp;             // position in the chain
+    const int fw = (int)(blockDim.x >> 5);     // warps this launch runs per CTA (<= FW; the shared-memory layout is FW's)
+    const int n = a.ctas * fw;                 // warps of this chain
+    const int w = cta * fw + warp;             // position in the chain
     const float* __restrict__ Cv = a.C[side];
     float* __restrict__ Sv = a.S[side];
     const unsigned char* __restrict__ img = a.img[side];
@@ -319,7 +377,7 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
     // links. The one that leaves CTA c for CTA c + 1 is global link c; link ctas - 1 closes the ring (T slots).
     // A global link is a FIFO of rows: the producer pushes one row per step of every unit it hands over (T per unit, payload
     // or not), the consumer pops T rows per unit; row index = round * T + step.
-    const bool in_local = warp > 0, out_local = warp < FW - 1;
+    const bool in_local = warp > 0, out_local = warp < fw - 1;
     const int lin = cta == 0 ? a.ctas - 1 : cta - 1, lout = cta;
     const size_t side_floats = ((size_t)a.ctas * GRING + (size_t)T) * SLOTF;
     auto link_base = [&](int l) { return a.glink + (size_t)side * side_floats + (size_t)l * GRING * SLOTF; };
@@ -340,6 +398,12 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
     uint32_t gstep = 0;      // rows consumed by this warp so far (stage ring position / mbarrier phase)
     // global input link (warp 0 only): rows [popped, fetched) sit in inring or are on their way; rows < avail are in global memory
     unsigned fetched = 0, avail = 0;
+    unsigned ring_fetched = 0, ring_popped = 0;   // rows ever requested into / popped from inring: slot and mbarrier phase
+    // the input FIFO currently read by warp 0: the chain's own closing / neighbour link, or (BAND, first unit of the band) the
+    // FIFO the neighbour rank writes into this rank's exchange buffer
+    const float* cur_gin = nullptr;
+    unsigned cur_depth = 1;
+    bool cur_ext = false;
     // global output link (warp FW - 1 only): rows < pushed have been handed to the copy engine, rows < published are visible
     unsigned cons_seen = 0;
     bool pending_pub = false;
@@ -352,40 +416,87 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
     // gpu-scope acquire / release fence sits in the step: measured, a fence per step in the two boundary warps of every CTA
     // is what the whole chain then waits for. fence.proxy.async orders the generic-proxy counter access against the
     // async-proxy copies of the same thread.
+    // rows < the returned count have been pushed onto the current input FIFO (lane 0 reads, the value is broadcast by the caller)
+    auto read_avail = [&]() -> unsigned {
+        if constexpr (BAND) {
+            if (cur_ext) {   // epoch-tagged 64-bit counter in this rank's exchange buffer, written by the neighbour GPU
+                const unsigned long long v = ld_acquire_sys_u64(a.ext_prod_in + side * 16);
+                return (unsigned)(v >> 32) == a.epoch ? (unsigned)v : 0u;
+            }
+        }
+        return ld_relaxed_gpu(gprod_in);
+    };
     auto fetch_rows = [&](unsigned popped) {
         if (fetched < avail && fetched < popped + INR) fence_proxy_async_global();
         while (fetched < avail && fetched < popped + INR) {
-            const unsigned sl = fetched % INR;
+            const unsigned sl = ring_fetched % INR;
             mbar_expect_tx_elect(&inbars[sl], SLOT_BYTES);
-            bulk_g2s_elect(inring + (size_t)sl * SLOTF, gin + (size_t)(fetched % depth_in) * SLOTF, SLOT_BYTES, &inbars[sl]);
+            bulk_g2s_elect(inring + (size_t)sl * SLOTF, cur_gin + (size_t)(fetched % cur_depth) * SLOTF, SLOT_BYTES, &inbars[sl]);
             fetched++;
+            ring_fetched++;
         }
     };
     // pop row q (it must be the next one): make sure it has been fetched, wait for it, free its global slot
     auto pop_row = [&](unsigned q) -> const float* {
         if (fetched <= q) {   // not even requested yet: the producer was late when we last looked
+            unsigned long long t0 = 0;
+            unsigned spins = 0;
             while (avail <= q) {
                 unsigned v = 0;
-                if (lane == 0) v = ld_relaxed_gpu(gprod_in);
+                if (lane == 0) v = read_avail();
                 avail = __shfl_sync(0xffffffffu, v, 0);
-                if (avail <= q) __nanosleep(100);
+                if (avail <= q) {
+                    __nanosleep(100);
+                    if constexpr (BAND) {
+                        if (cur_ext && (++spins & 63u) == 0) {   // another GPU feeds this FIFO: the wait is bounded
+                            int stop = 0;
+                            if (lane == 0) {
+                                if (t0 == 0) t0 = timer_ns();
+                                if (*reinterpret_cast<volatile unsigned*>(a.status) != 0u) stop = 1;
+                                else if (timer_ns() - t0 > a.timeout_ns) { atomicExch(a.status, 1u); stop = 1; }
+                            }
+                            if (__shfl_sync(0xffffffffu, stop, 0)) avail = q + 1;   // stop waiting; the row read is whatever is there
+                        }
+                    }
+                }
             }
             fetch_rows(q);
         }
-        mbar_wait(&inbars[q % INR], (q / INR) & 1u);
-        return inring + (size_t)(q % INR) * SLOTF;
+        const unsigned k = ring_popped++;
+        mbar_wait(&inbars[k % INR], (k / INR) & 1u);
+        return inring + (size_t)(k % INR) * SLOTF;
     };
+
+    // BAND: local rows are [0, Hb) of the volumes, image rows [row0, row0 + Hb); ug = the unit's index in the WHOLE image's chain
+    const int row0 = BAND ? a.row0 : 0;
+    const int Hloc = BAND ? a.Hb : H;       // rows of the volumes this launch works on
+    const int ubase = !BAND ? 0 : (a.sweep == 1 ? row0 : (a.sweep == 2 ? H - (row0 + Hloc) : 0));
 
     int round = 0;
     for (int u = w; u < a.U; u += n, round++) {
-        const long long pix0 = a.sweep == 0 ? (long long)u : (a.sweep == 1 ? (long long)u * W + (W - 1) : (long long)(H - 1 - u) * W);
-        const bool has_up = u >= 1;
-        const bool diag_unit = a.sweep == 0 ? true : (u <= a.U - 2);
+        const int ug = ubase + u;
+        // first pixel of the unit in the (band-local) volumes and in the (whole) image
+        const long long pix0 = a.sweep == 0 ? (long long)u : (a.sweep == 1 ? (long long)u * W + (W - 1) : (long long)(Hloc - 1 - u) * W);
+        const long long ipix0 = pix0 + (long long)row0 * W;
+        const bool has_up = ug >= 1;
+        const bool diag_unit = a.sweep == 0 ? true : (ug <= H - 2);
+        // BAND: the band's first unit is fed by the neighbour rank's last unit, the band's last unit feeds the neighbour's first
+        const bool ext_in_unit = BAND && a.sweep != 0 && a.ext_in != nullptr && u == 0;
+        const bool ext_out_unit = BAND && a.sweep != 0 && a.ext_out != nullptr && u == a.U - 1;
         // the producer of my input link works on unit u - 1: same round, or the previous one across the closing link
-        const unsigned qbase_in = (unsigned)((w == 0 ? round - 1 : round)) * (unsigned)T;   // only used when has_up
+        const unsigned qbase_in = ext_in_unit ? 0u : (unsigned)((w == 0 ? round - 1 : round)) * (unsigned)T;   // only used when has_up
         const unsigned qbase_out = (unsigned)round * (unsigned)T;
-        const bool gin_active = !in_local && has_up && !(a.debug & 2);      // this unit pops T rows from the global input link
-        const bool gout_active = !out_local && diag_unit && !(a.debug & 2);  // this unit pushes T rows onto the global output link
+        const bool gin_active = !in_local && has_up && (u >= 1 || ext_in_unit) && !(a.debug & 2);   // this unit pops T rows from a global FIFO
+        const bool gout_active = !out_local && diag_unit && !ext_out_unit && !(a.debug & 2);      // ... pushes T rows onto the chain's global link
+        if (gin_active) {
+            if (ext_in_unit) {
+                cur_gin = a.ext_in + (size_t)side * T * SLOTF; cur_depth = (unsigned)T; cur_ext = true;
+                fetched = 0; avail = 0;
+            } else {
+                if (cur_ext) { fetched = 0; avail = 0; }   // back to the chain's own link, whose numbering starts at 0
+                cur_gin = gin; cur_depth = depth_in; cur_ext = false;
+            }
+        }
 
         long long lpix = pix0;  // pixel of the next row to prefetch
         auto issue_load = [&](uint32_t g) {
@@ -402,11 +513,20 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
             for (int k = 0; k < pre; k++) issue_load(gstep + k);
         }
         // image values of the next 32 steps of this unit and of the neighbouring unit (lane l: step tb + l)
-        auto img_own = [&](int t) -> int { return (int)img[pix0 + (long long)min(t, T - 1) * dpix]; };
-        auto img_up = [&](int t) -> int { return has_up ? (int)img[pix0 + upoff + (long long)min(t, T - 1) * dpix] : 0; };
+        auto img_own = [&](int t) -> int { return (int)img[ipix0 + (long long)min(t, T - 1) * dpix]; };
+        auto img_up = [&](int t) -> int { return has_up ? (int)img[ipix0 + upoff + (long long)min(t, T - 1) * dpix] : 0; };
         int blk_own = img_own(lane), blk_up = img_up(lane);
         int nblk_own = img_own(32 + lane), nblk_up = img_up(32 + lane);
         int i_prev_own = 0, i_prev_up = 0;
+        // BAND, sweep 0, not the image's first rows: the paths continue from the rank above (entry states, written into this
+        // rank's exchange buffer per column: row 0 = the down path's state, row 1 = the down-right path's state, each + minimum)
+        const bool entry = BAND && a.sweep == 0 && a.ent_in != nullptr;
+        if constexpr (BAND) {
+            if (entry) {
+                i_prev_own = (int)img[ipix0 - W];
+                i_prev_up = has_up ? (int)img[ipix0 - W - 1] : 0;
+            }
+        }
 
         float Lo[NPL];   // state of the path that runs along this unit
         float mo = 0.f;
@@ -418,7 +538,7 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
             // the counters of the global links are read at the top of the step and used further down: their L2 latency
             // hides behind the own path
             unsigned avail_new = 0, cons_new = 0;
-            if (gin_active && lane == 0) avail_new = ld_relaxed_gpu(gprod_in);
+            if (gin_active && lane == 0) avail_new = read_avail();
             if (gout_active && lane == 0) cons_new = ld_relaxed_gpu(gcons_out);
 
             const int st = gstep % FSTAGES;
@@ -435,12 +555,26 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
             const int i_cur = __shfl_sync(0xffffffffu, blk_own, t & 31);
             const int i_upcur = __shfl_sync(0xffffffffu, blk_up, t & 31);
 
-            const bool own_active = t <= T - 2;
-            const bool diag_active = diag_unit && (a.sweep != 0 || t <= T - 2);
+            // sweep 0 steps down the image rows (global row yg); sweeps 1 and 2 step along a row (all rows are visited)
+            const int yg = row0 + t;
+            const bool own_active = a.sweep == 0 ? (yg <= H - 2) : (t <= T - 2);
+            const bool diag_active = diag_unit && (a.sweep != 0 || yg <= H - 2);
+            const bool own_first = a.sweep == 0 ? (yg == 0) : (t == 0);            // first pixel of the own path: raw cost
+            const bool diag_first = a.sweep == 0 ? (yg == 0 || u == 0) : (t == 0 || ug == 0);
+            const bool from_entry = entry && t == 0;                                // continue the rank above's paths
 
             // ---- the path along the unit
+            if constexpr (BAND) {
+                if (from_entry) {
+                    const size_t slot = (size_t)side * W + u;
+                    wait_peer_flag(a.ent_flag_in + slot, a.epoch, a.status, a.timeout_ns, lane);
+                    const float* src = a.ent_in + slot * (2 * SLOTF);
+                    load_row_cg<NPL>(src, lane, Lo);
+                    mo = __ldcg(src + ROWF);
+                }
+            }
             if (own_active) {
-                if (t == 0) {
+                if (own_first) {
 #pragma unroll
                     for (int j = 0; j < NPL; j++) Lo[j] = cf[j];
                 } else {
@@ -478,11 +612,17 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
             float md = 0.f;
             if (diag_active) {
                 float Ld[NPL];
-                if (t == 0 || !has_up || ((a.debug & 2) && !in_local)) {
+                if (diag_first || ((a.debug & 2) && !in_local)) {
 #pragma unroll
                     for (int j = 0; j < NPL; j++) Ld[j] = cf[j];
                 } else {
-                    if (in_local) {
+                    if (BAND && from_entry) {
+                        const size_t slot = (size_t)side * W + (u - 1);
+                        wait_peer_flag(a.ent_flag_in + slot, a.epoch, a.status, a.timeout_ns, lane);
+                        const float* src = a.ent_in + slot * (2 * SLOTF) + SLOTF;
+                        load_row_cg<NPL>(src, lane, Ld);
+                        md = __ldcg(src + ROWF);
+                    } else if (in_local) {
                         const unsigned q = qbase_in + (unsigned)(t - 1);   // index of the row I need on my input link
                         if (lane == 0 && !(a.debug & 1))
                             while (ld_acquire_cta_smem(&prodc[warp - 1]) < q + 1u) __nanosleep(20);
@@ -515,12 +655,28 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
                     if (lane == 0) dst[ROWF] = md;
                     __syncwarp();
                     if (lane == 0) st_release_cta_smem(&prodc[warp], qo + 1u);
-                } else if (gout_active) {
+                } else if (gout_active || ext_out_unit) {
                     // stage the row in my (otherwise unused) ring; the copy that last read this slot was committed two steps ago
                     // and is waited for below, before the row of the previous step is published
                     float* dst = ring + (size_t)(qo % RING) * SLOTF;
                     store_row<NPL>(dst, lane, Ld);
                     if (lane == 0) dst[ROWF] = md;
+                }
+                if constexpr (BAND) {
+                    // sweep 0, last row of the band: the rank below continues both paths from here (peer memory)
+                    if (a.sweep == 0 && a.ent_out != nullptr && t == T - 1) {
+                        const size_t slot = (size_t)side * W + u;
+                        float* dst = a.ent_out + slot * (2 * SLOTF);
+                        store_row_cg<NPL>(dst, lane, Lo);
+                        store_row_cg<NPL>(dst + SLOTF, lane, Ld);
+                        if (lane == 0) {
+                            __stcg(dst + ROWF, mo);
+                            __stcg(dst + SLOTF + ROWF, md);
+                        }
+                        __threadfence_system();
+                        __syncwarp();
+                        if (lane == 0) st_release_sys_u32(a.ent_flag_out + slot, a.epoch);
+                    }
                 }
             }
             // my input link inside the CTA: everything up to the row of step t - 1 is consumed (whether it was needed or not)
@@ -528,9 +684,9 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
                 __syncwarp();
                 if (lane == 0) st_release_cta_smem(&consc[warp - 1], qbase_in + (unsigned)t);
             }
-            if (gin_active && t >= 1) {
+            if (gin_active && !ext_in_unit && t >= 1) {
                 // the row's copy out of global memory completed before pop_row returned and its shared copy has been read in
-                // arithmetic: both slots are free
+                // arithmetic: both slots are free (the neighbour rank's FIFO is T deep and needs no such counter)
                 __syncwarp();
                 if (lane == 0) st_relaxed_gpu(gcons_in, qbase_in + (unsigned)t);
             }
@@ -560,10 +716,32 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
                 pending_pub = true;
                 pending_q = qo;
             }
+            if constexpr (BAND) {
+                if (ext_out_unit && diag_unit) {
+                    // the same push, into the neighbour rank's exchange buffer (T slots: no slot is reused inside a pair). A copy
+                    // over NVLink takes several steps to complete, and waiting for the previous one in every step would make this
+                    // unit (and with it the whole neighbour rank, which follows it in lock step) run at the link's latency: the
+                    // counter (it carries the pair's epoch) is written every XPUB steps for the rows whose copies were committed
+                    // at least XPUB steps ago. Groups committed since the copy of step t - XPUB: its S row, then a copy and an S
+                    // row per step = 2 * XPUB - 1.
+                    if (t >= XPUB && (t % XPUB) == 0) {
+                        bulk_wait_all_elect<2 * XPUB - 1>();
+                        fence_proxy_async_global();
+                        __syncwarp();
+                        if (lane == 0)
+                            st_release_sys_u64(a.ext_prod_out + side * 16, ((unsigned long long)a.epoch << 32) | (unsigned long long)(t - XPUB + 1));
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    bulk_s2g_commit_elect(a.ext_out + ((size_t)side * T + t) * SLOTF, ring + (size_t)((qbase_out + (unsigned)t) % RING) * SLOTF, SLOT_BYTES);
+                    pending_pub = true;
+                    pending_q = (unsigned)t;
+                }
+            }
 
             // ---- the "up" path adds the raw cost on rows >= 1 (its penalties are never written, sgm.cu); sweep 0 only
             if constexpr (!READS) {
-                if (t >= 1) {  // sweep 0: y = t
+                if (yg >= 1) {  // sweep 0: image row yg
 #pragma unroll
                     for (int j = 0; j < NPL; j++) so[j] = so[j] + cf[j];
                 }
@@ -571,7 +749,7 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
 
             // ---- S row out: staged, one bulk store per row. The store of the previous step has left the staging row (the
             // hand-over copy committed a moment ago may still be reading ITS row).
-            if (gout_active) bulk_wait_read_elect<1>(); else bulk_wait_read_elect<0>();
+            if (gout_active || (BAND && ext_out_unit && diag_unit)) bulk_wait_read_elect<1>(); else bulk_wait_read_elect<0>();
             __syncwarp();
             store_row<NPL>(outbuf, lane, so);
             fence_proxy_async_smem();
@@ -590,7 +768,17 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
         if (gin_active) {           // FIFO: pop the row of the producer's last step too
             pop_row(qbase_in + (unsigned)(T - 1));
             __syncwarp();
-            if (lane == 0) st_relaxed_gpu(gcons_in, qbase_in + (unsigned)T);
+            if (lane == 0 && !ext_in_unit) st_relaxed_gpu(gcons_in, qbase_in + (unsigned)T);
+        }
+        if constexpr (BAND) {
+            if (ext_out_unit && diag_unit && pending_pub) {   // publish the last row of the band's last unit
+                bulk_wait_all_elect<0>();
+                fence_proxy_async_global();
+                __syncwarp();
+                if (lane == 0)
+                    st_release_sys_u64(a.ext_prod_out + side * 16, ((unsigned long long)a.epoch << 32) | (unsigned long long)T);
+                pending_pub = false;
+            }
         }
         if (gout_active && pending_pub) {   // publish the last row of the unit
             bulk_wait_all_elect<0>();
@@ -610,7 +798,7 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
     }
     // rows requested from the global link but never popped must have landed before the CTA's shared memory goes away
     if (!in_local) {
-        for (unsigned q = (fetched > INR ? fetched - INR : 0u); q < fetched; q++) mbar_wait(&inbars[q % INR], (q / INR) & 1u);
+        for (unsigned k = ring_popped; k < ring_fetched; k++) mbar_wait(&inbars[k % INR], (k / INR) & 1u);
     }
     asm volatile(
         "{\n\t"
@@ -625,9 +813,13 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
 // wrapping modulo W with a restart), S is read, the sum goes to the WTA and, if asked for, back to S.
 constexpr int LW = 4;  // warps per CTA
 
-template <int NPL, bool STORE>
+template <int NPL, bool STORE, bool BAND>
 __global__ void __launch_bounds__(LW * 32) sgm_fused_last_kernel(const FusedArgs a) {
+    if constexpr (BAND) {
+        if (a.go != nullptr && *reinterpret_cast<const volatile int*>(a.go) == 0) return;
+    }
     constexpr int ROWF = 32 * NPL;
+    constexpr int SLOTF = ROWF + 4;
     constexpr int PER_WARP = ROWF * (FSTAGES * 2 + (STORE ? 1 : 0));
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -647,6 +839,9 @@ __global__ void __launch_bounds__(LW * 32) sgm_fused_last_kernel(const FusedArgs
     const int W = a.W, H = a.H;
     const uint32_t copy_bytes = (uint32_t)a.Dp * 4u;
     const size_t pitch = (size_t)a.Dp;
+    // BAND: this launch owns image rows [row0, row0 + Hb), i.e. the steps [tb, te) of every scanline (step t is row H - 1 - t)
+    const int row0 = BAND ? a.row0 : 0;
+    const int tb = BAND ? H - (a.row0 + a.Hb) : 0, te = BAND ? H - a.row0 : H;
     uint32_t gstep = 0;
     for (;;) {
         unsigned q = 0;
@@ -661,9 +856,9 @@ __global__ void __launch_bounds__(LW * 32) sgm_fused_last_kernel(const FusedArgs
             int c = (line - t) % W;
             return c < 0 ? c + W : c;
         };
-        int lrow = H - 1, lcol = line;
+        int lrow = H - 1 - tb, lcol = col_at(tb);
         auto issue_load = [&](uint32_t g) {
-            const size_t off = ((size_t)lrow * W + lcol) * pitch;
+            const size_t off = ((size_t)(lrow - row0) * W + lcol) * pitch;
             const int st = g % FSTAGES;
             float* dst = inbuf + (size_t)st * 2 * ROWF;
             mbar_expect_tx_elect(&bars[st], copy_bytes * 2);
@@ -673,32 +868,42 @@ __global__ void __launch_bounds__(LW * 32) sgm_fused_last_kernel(const FusedArgs
             lcol = lcol == 0 ? W - 1 : lcol - 1;
         };
         {
-            const int pre = min(FSTAGES, H);
+            const int pre = min(FSTAGES, te - tb);
             for (int k = 0; k < pre; k++) issue_load(gstep + k);
         }
         auto image_at = [&](int t) -> int {
             const int tt = min(t, H - 1);
             return (int)img[(size_t)(H - 1 - tt) * W + col_at(tt)];
         };
-        int blk = image_at(lane), nblk = image_at(32 + lane);
+        int blk = image_at(tb + lane), nblk = image_at(tb + 32 + lane);
         int i_prev = 0;
         float L[NPL];
         float mL = 0.f;
 #pragma unroll
         for (int j = 0; j < NPL; j++) L[j] = 0.f;
-        int row = H - 1, col = line;
-        for (int t = 0; t < H; t++) {
+        if constexpr (BAND) {
+            if (tb > 0 && tb <= H - 2) {   // the scanline enters from the rank below: continue from its state
+                const size_t slot = (size_t)side * W + line;
+                wait_peer_flag(a.hand_flag_in + slot, a.epoch, a.status, a.timeout_ns, lane);
+                const float* src = a.hand_in + slot * SLOTF;
+                load_row_cg<NPL>(src, lane, L);
+                mL = __ldcg(src + ROWF);
+                i_prev = image_at(tb - 1);
+            }
+        }
+        int row = H - 1 - tb, col = col_at(tb);
+        for (int t = tb; t < te; t++) {
             const int st = gstep % FSTAGES;
             mbar_wait(&bars[st], (gstep / FSTAGES) & 1u);
             float cf[NPL], so[NPL];
             const float* ib = inbuf + (size_t)st * 2 * ROWF;
             load_row<NPL>(ib, lane, cf);
             load_row<NPL>(ib + ROWF, lane, so);
-            if ((t & 31) == 0 && t > 0) {
+            if (((t - tb) & 31) == 0 && t > tb) {
                 blk = nblk;
                 nblk = image_at(t + 32 + lane);
             }
-            const int i_cur = __shfl_sync(0xffffffffu, blk, t & 31);
+            const int i_cur = __shfl_sync(0xffffffffu, blk, (t - tb) & 31);
             if (t <= H - 2) {
                 if (t == 0 || col == W - 1) {   // first pixel, or the scanline has just wrapped around the image
 #pragma unroll
@@ -719,15 +924,26 @@ __global__ void __launch_bounds__(LW * 32) sgm_fused_last_kernel(const FusedArgs
                 store_row<NPL>(outbuf, lane, so);
                 fence_proxy_async_smem();
                 __syncwarp();
-                bulk_s2g_commit_elect(Sv + ((size_t)row * W + col) * pitch, outbuf, copy_bytes);
+                bulk_s2g_commit_elect(Sv + ((size_t)(row - row0) * W + col) * pitch, outbuf, copy_bytes);
             }
             const float outv = warp_wta<NPL>(so, lane, a.D, a.subpixel);
-            if (lane == 0) a.disp[side][(size_t)row * W + col] = outv;
+            if (lane == 0) a.disp[side][(size_t)(row - row0) * W + col] = outv;
             __syncwarp();
-            if (t + FSTAGES < H) issue_load(gstep + FSTAGES);
+            if (t + FSTAGES < te) issue_load(gstep + FSTAGES);
             gstep++;
             row -= 1;
             col = col == 0 ? W - 1 : col - 1;
+        }
+        if constexpr (BAND) {
+            if (a.hand_out != nullptr && te <= H - 2) {   // the path goes on in the rank above (peer memory)
+                const size_t slot = (size_t)side * W + line;
+                float* dst = a.hand_out + slot * SLOTF;
+                store_row_cg<NPL>(dst, lane, L);
+                if (lane == 0) __stcg(dst + ROWF, mL);
+                __threadfence_system();
+                __syncwarp();
+                if (lane == 0) st_release_sys_u32(a.hand_flag_out + slot, a.epoch);
+            }
         }
     }
     asm volatile(
@@ -764,39 +980,43 @@ FusedLayout fused_layout(int H, int W, int D) {
     return l;
 }
 
-template <int NPL, bool READS>
+template <int NPL, bool READS, bool BAND>
 int launch_chain(FusedArgs a, cudaStream_t stream) {
     constexpr int FW = ChainSmem<NPL, READS>::FW;
     const size_t smem = ChainSmem<NPL, READS>::BYTES;
     int per_sm = 0;
-    if (int e = kernel_setup<sgm_chain_kernel<NPL, READS>>(FW * 32, smem, &per_sm)) return e;
+    if (int e = kernel_setup<sgm_chain_kernel<NPL, READS, BAND>>(FW * 32, smem, &per_sm)) return e;
     MCCNN_REQUIRE(per_sm >= 1, MCCNN_EINVAL, "sgm_chain_kernel<%d>: does not fit on an SM (smem %zu)", NPL, smem);
     int ctas = (sm_count() * per_sm) / 2;   // one chain per side; every CTA must be resident (cooperative launch)
     if (ctas > MAX_CHAIN_CTAS) ctas = MAX_CHAIN_CTAS;
-    const int need = ceil_div(a.U, FW);
-    if (ctas > need) ctas = need;
-    // full rounds: the units of a side are dealt to ctas * FW warps; keep the last round as full as the others
-    const int rounds = ceil_div(a.U, ctas * FW);
-    ctas = ceil_div(ceil_div(a.U, rounds), FW);
     MCCNN_REQUIRE(ctas >= 1, MCCNN_EINVAL, "sgm_chain_kernel: no resident CTA available");
+    // full rounds: the units of a side are dealt to ctas * fw warps; keep the last round as full as the others, and spread
+    // its units over every SM (fewer warps per CTA) rather than filling some SMs with FW warps and leaving the others idle
+    const int rounds = ceil_div(a.U, ctas * FW);
+    const int per_round = ceil_div(a.U, rounds);
+    int fw = ceil_div(per_round, ctas);
+    static const int env_fw = [] { const char* e = getenv("MCCNN_FUSED_FW"); return e ? atoi(e) : 0; }();
+    if (env_fw > 0) fw = env_fw;
+    if (fw > FW) fw = FW;
+    ctas = ceil_div(per_round, fw);
     a.ctas = ctas;
     void* params[] = {&a};
-    MCCNN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sgm_chain_kernel<NPL, READS>), dim3(2 * ctas), dim3(FW * 32), params,
+    MCCNN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sgm_chain_kernel<NPL, READS, BAND>), dim3(2 * ctas), dim3(fw * 32), params,
                                            smem, stream));
     return 0;
 }
 
-template <int NPL, bool STORE>
+template <int NPL, bool STORE, bool BAND>
 int launch_last(const FusedArgs& a, cudaStream_t stream) {
     constexpr int ROWF = 32 * NPL;
     const size_t smem = (size_t)LW * ROWF * (FSTAGES * 2 + (STORE ? 1 : 0)) * sizeof(float) + (size_t)LW * FSTAGES * sizeof(uint64_t);
     int per_sm = 0;
-    if (int e = kernel_setup<sgm_fused_last_kernel<NPL, STORE>>(LW * 32, smem, &per_sm)) return e;
+    if (int e = kernel_setup<sgm_fused_last_kernel<NPL, STORE, BAND>>(LW * 32, smem, &per_sm)) return e;
     MCCNN_REQUIRE(per_sm >= 1, MCCNN_EINVAL, "sgm_fused_last_kernel<%d>: does not fit on an SM (smem %zu)", NPL, smem);
     int grid = sm_count() * per_sm;
     const int need = ceil_div(2 * a.W, LW);
     if (grid > need) grid = need;
-    sgm_fused_last_kernel<NPL, STORE><<<grid, LW * 32, smem, stream>>>(a);
+    sgm_fused_last_kernel<NPL, STORE, BAND><<<grid, LW * 32, smem, stream>>>(a);
     MCCNN_LAUNCH_CHECK("sgm_fused_last_kernel");
     return 0;
 }
@@ -813,14 +1033,136 @@ int run_fused_npl(FusedArgs a, int keep_volumes, cudaStream_t stream, unsigned* 
         a.U = sweep == 0 ? a.W : a.H;
         a.T = sweep == 0 ? a.H : a.W;
         a.gflags = flags + (size_t)sweep * 2 * MAX_CHAIN_CTAS * 2 * FLAG_STRIDE;
-        if (int e = (sweep == 0 ? launch_chain<NPL, false>(a, stream) : launch_chain<NPL, true>(a, stream))) return e;
+        if (int e = (sweep == 0 ? launch_chain<NPL, false, false>(a, stream) : launch_chain<NPL, true, false>(a, stream))) return e;
     }
     a.store_s = keep_volumes;
     if (!(mask & 8)) return 0;
-    return keep_volumes ? launch_last<NPL, true>(a, stream) : launch_last<NPL, false>(a, stream);
+    return keep_volumes ? launch_last<NPL, true, false>(a, stream) : launch_last<NPL, false, false>(a, stream);
+}
+
+// ---- one pair split over several GPUs by image rows (mccnn_sgm_fused_sharded)
+// Exchange buffer of a rank = everything its neighbours write INTO it (peer memory), one section per sweep:
+//   ent   [2 sides][W][2 slots]   sweep 0: states of the down / down-right paths after the last row of the rank above (+ flags)
+//   fifo1 [2][W steps][slot]      sweep 1: the down-left states of the rank above's last row, one per step (+ counter)
+//   fifo2 [2][W steps][slot]      sweep 2: the up-right states of the rank below's first row (+ counter)
+//   hand  [2][W][slot]            sweep 3: state of every up-left scanline leaving the rank below (+ flags)
+// Flags carry the pair's epoch and are never reset; the counters are (epoch << 32 | rows pushed).
+struct XchgLayout {
+    size_t ent, ent_flag, fifo[2], prod, hand, hand_flag, end;
+};
+
+XchgLayout fused_xchg_layout(int W, int D) {
+    XchgLayout l{};
+    const int npl = npl_for(D);
+    const size_t slot = (size_t)(32 * (npl ? npl : 32) + 4) * sizeof(float);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o = 0;
+    l.ent = o; o += up((size_t)2 * W * 2 * slot);
+    l.ent_flag = o; o += up((size_t)2 * W * sizeof(unsigned));
+    for (int k = 0; k < 2; k++) { l.fifo[k] = o; o += up((size_t)2 * W * slot); }
+    l.prod = o; o += up((size_t)2 * 2 * 16 * sizeof(unsigned long long));
+    l.hand = o; o += up((size_t)2 * W * slot);
+    l.hand_flag = o; o += up((size_t)2 * W * sizeof(unsigned));
+    l.end = o;
+    return l;
+}
+
+template <int NPL>
+int run_fused_band_npl(FusedArgs a, int keep_volumes, cudaStream_t stream, unsigned* flags, const mccnn_shard* sh, int sweep_mask) {
+    const XchgLayout x = fused_xchg_layout(a.W, a.D);
+    char* mine = reinterpret_cast<char*>(sh->xchg_local);
+    char* prev = reinterpret_cast<char*>(sh->xchg_prev);
+    char* next = reinterpret_cast<char*>(sh->xchg_next);
+    const bool has_prev = sh->rank > 0, has_next = sh->rank < sh->world - 1;
+    for (int sweep = 0; sweep < 3; sweep++) {
+        if (!(sweep_mask & (1 << sweep))) continue;
+        a.sweep = sweep;
+        a.U = sweep == 0 ? a.W : a.Hb;
+        a.T = sweep == 0 ? a.Hb : a.W;
+        a.gflags = flags + (size_t)sweep * 2 * MAX_CHAIN_CTAS * 2 * FLAG_STRIDE;
+        a.ent_in = nullptr; a.ent_out = nullptr; a.ext_in = nullptr; a.ext_out = nullptr;
+        if (sweep == 0) {
+            if (has_prev) {
+                a.ent_in = reinterpret_cast<const float*>(mine + x.ent);
+                a.ent_flag_in = reinterpret_cast<const unsigned*>(mine + x.ent_flag);
+            }
+            if (has_next) {
+                a.ent_out = reinterpret_cast<float*>(next + x.ent);
+                a.ent_flag_out = reinterpret_cast<unsigned*>(next + x.ent_flag);
+            }
+        } else {
+            // sweep 1 runs down the rows (fed by the rank above, feeds the rank below), sweep 2 up
+            char* from = sweep == 1 ? (has_prev ? mine : nullptr) : (has_next ? mine : nullptr);
+            char* to = sweep == 1 ? (has_next ? next : nullptr) : (has_prev ? prev : nullptr);
+            const size_t prod_off = x.prod + (size_t)(sweep - 1) * 2 * 16 * sizeof(unsigned long long);
+            if (from) {
+                a.ext_in = reinterpret_cast<const float*>(from + x.fifo[sweep - 1]);
+                a.ext_prod_in = reinterpret_cast<const unsigned long long*>(from + prod_off);
+            }
+            if (to) {
+                a.ext_out = reinterpret_cast<float*>(to + x.fifo[sweep - 1]);
+                a.ext_prod_out = reinterpret_cast<unsigned long long*>(to + prod_off);
+            }
+        }
+        if (int e = (sweep == 0 ? launch_chain<NPL, false, true>(a, stream) : launch_chain<NPL, true, true>(a, stream))) return e;
+    }
+    if (!(sweep_mask & 8)) return 0;
+    a.store_s = keep_volumes;
+    a.hand_in = nullptr; a.hand_out = nullptr;
+    if (has_next) {
+        a.hand_in = reinterpret_cast<const float*>(mine + x.hand);
+        a.hand_flag_in = reinterpret_cast<const unsigned*>(mine + x.hand_flag);
+    }
+    if (has_prev) {
+        a.hand_out = reinterpret_cast<float*>(prev + x.hand);
+        a.hand_flag_out = reinterpret_cast<unsigned*>(prev + x.hand_flag);
+    }
+    return keep_volumes ? launch_last<NPL, true, true>(a, stream) : launch_last<NPL, false, true>(a, stream);
 }
 
 }  // namespace
+
+size_t sgm_fused_xchg_bytes(int W, int D) { return fused_xchg_layout(W, D).end; }
+
+// workspace: the caller's SGM workspace (first 256 bytes = the exact mode's words incl. the status word at index 32, then the fused
+// mode's flags and rings)
+int run_sgm_fused_band(const float* CLb, const float* CRb, const uint8_t* imageL, const uint8_t* imageR, float* SLb, float* SRb,
+                       float* dispLb, float* dispRb, void* workspace, int W, int D, const mccnn_sgm_params* p, int keep_volumes,
+                       const mccnn_shard* sh, int sweep_mask, cudaStream_t stream) {
+    const int H = sh->H_full;
+    const FusedLayout l = fused_layout(H, W, D);
+    char* base = reinterpret_cast<char*>(workspace);
+    char* ws = base + 256;
+    if (sweep_mask & 1) MCCNN_CUDA(cudaMemsetAsync(base, 0, 256, stream));
+    MCCNN_CUDA(cudaMemsetAsync(ws + l.flags, 0, l.links - l.flags, stream));
+    FusedArgs a{};
+    a.C[0] = CLb; a.C[1] = CRb;
+    a.S[0] = SLb; a.S[1] = SRb;
+    a.img[0] = imageL; a.img[1] = imageR;
+    a.disp[0] = dispLb; a.disp[1] = dispRb;
+    a.H = H; a.W = W; a.D = D; a.Dp = disp_pitch(D);
+    a.P1 = p->P1; a.P2 = p->P2; a.P1r = p->P1_red; a.P2r = p->P2_red;
+    a.threshold = p->threshold;
+    a.subpixel = p->subpixel;
+    a.glink = reinterpret_cast<float*>(ws + l.links);
+    a.slot_floats = l.slot_floats;
+    a.counter = reinterpret_cast<unsigned*>(ws + l.counter);
+    a.row0 = sh->row0; a.Hb = sh->rows; a.epoch = sh->epoch;
+    a.go = sh->go_flag;
+    a.status = reinterpret_cast<unsigned*>(base) + 32;
+    a.timeout_ns = (unsigned long long)(sh->timeout_ms ? sh->timeout_ms : 2000u) * 1000000ull;
+    unsigned* flags = reinterpret_cast<unsigned*>(ws + l.flags);
+    switch (npl_for(D)) {
+#define MCCNN_FUSED_BAND_CASE(N) \
+    case N: return run_fused_band_npl<N>(a, keep_volumes, stream, flags, sh, sweep_mask);
+        MCCNN_FUSED_BAND_CASE(1) MCCNN_FUSED_BAND_CASE(2) MCCNN_FUSED_BAND_CASE(3) MCCNN_FUSED_BAND_CASE(4) MCCNN_FUSED_BAND_CASE(5)
+        MCCNN_FUSED_BAND_CASE(6) MCCNN_FUSED_BAND_CASE(7) MCCNN_FUSED_BAND_CASE(8) MCCNN_FUSED_BAND_CASE(10) MCCNN_FUSED_BAND_CASE(13)
+        MCCNN_FUSED_BAND_CASE(16) MCCNN_FUSED_BAND_CASE(20) MCCNN_FUSED_BAND_CASE(25) MCCNN_FUSED_BAND_CASE(32)
+#undef MCCNN_FUSED_BAND_CASE
+    }
+    set_error("sgm (fused, sharded): D=%d exceeds the supported maximum of 1024", D);
+    return MCCNN_EINVAL;
+}
 
 size_t sgm_fused_workspace_bytes(int H, int W, int D) { return fused_layout(H, W, D).end; }
 

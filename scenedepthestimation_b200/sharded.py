@@ -10,6 +10,10 @@ Rank r owns rows [row0, row0 + rows). What crosses NVLink:
   * the two raw WTA bands are all-gathered (23 MB each) and the cheap L-R check / fill / median run on the whole map.
 The result is bit-identical to the single-GPU path.
 
+mode="fused" (opt-in, csrc/sgm_fused.cu): the 4 sweeps of the fused SGM on the bands. The two row sweeps advance in lock step
+on all ranks (the last row of a band streams one fp32 state per step into its neighbour over NVLink), the column and the
+diagonal sweep hand their states over per column / scanline. Value-identical to the single-GPU fused mode.
+
 torch.distributed provides the process group and torch's symmetric memory the peer-mapped exchange buffers.
 `emulate_bands` runs the same band kernels for several "ranks" on ONE GPU in dependency order (tests).
 """
@@ -61,6 +65,53 @@ def sgm_band(CLb, CRb, il_full, ir_full, D, shard: _lib.Shard, pass_mask=0x7F, k
     return out
 
 
+FUSED_SWEEP_DOWNWARD = (True, True, False, False)   # sweep -> runs through the bands top-down / bottom-up
+
+
+def sgm_fused_band(CLb, CRb, il_full, ir_full, D, shard: _lib.Shard, ws, sweep_mask=15, keep_volumes=True, out=None, params=None):
+    """mccnn_sgm_fused_sharded on this rank's band -> (SLb, SRb, dispLb, dispRb). `ws`: mccnn_sgm_workspace_bytes(H, W, D) bytes."""
+    lib = _lib.load()
+    rows, W, _ = CLb.shape
+    params = params or _lib.default_sgm_params()
+    if out is None:
+        out = (torch.empty_like(CLb), torch.empty_like(CRb),
+               torch.empty((rows, W), dtype=torch.float32, device="cuda"), torch.empty((rows, W), dtype=torch.float32, device="cuda"))
+    SLb, SRb, dl, dr = out
+    _lib.check(lib.mccnn_sgm_fused_sharded(CLb.data_ptr(), CRb.data_ptr(), il_full.data_ptr(), ir_full.data_ptr(), SLb.data_ptr(),
+                                           SRb.data_ptr(), dl.data_ptr(), dr.data_ptr(), ws.data_ptr(), ws.numel(), W, D,
+                                           C.byref(params), 1 if keep_volumes else 0, C.byref(shard), sweep_mask,
+                                           torch.cuda.current_stream().cuda_stream), "mccnn_sgm_fused_sharded")
+    return out
+
+
+def emulate_fused_bands(CL, CR, il, ir, D, world: int, epoch: int = 1, keep_volumes: bool = True, params=None):
+    """The fused mode's `world` row bands of one pair on ONE GPU, sweep by sweep in dependency order."""
+    lib = _lib.load()
+    H, W, _ = CL.shape
+    bands = band_rows(H, world)
+    nx = lib.mccnn_sgm_fused_shard_exchange_bytes(W, D)
+    xchg = [torch.zeros(nx, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    ws = [torch.zeros(lib.mccnn_sgm_workspace_bytes(H, W, D), dtype=torch.uint8, device="cuda") for _ in range(world)]
+    # the fused sweeps accumulate into the S volumes in place, starting from a copy of the cost volumes made by sweep 0
+    SL, SR = torch.empty_like(CL), torch.empty_like(CR)
+    dl = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    dr = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    shards = []
+    for r, (r0, n) in enumerate(bands):
+        shards.append(_shard(r, world, H, r0, n, xchg[r].data_ptr(), xchg[r - 1].data_ptr() if r > 0 else None,
+                             xchg[r + 1].data_ptr() if r < world - 1 else None, epoch))
+    for s in range(4):
+        order = range(world) if FUSED_SWEEP_DOWNWARD[s] else range(world - 1, -1, -1)
+        for r in order:
+            r0, n = bands[r]
+            sgm_fused_band(CL[r0:r0 + n], CR[r0:r0 + n], il, ir, D, shards[r], ws[r], sweep_mask=1 << s, keep_volumes=keep_volumes,
+                           out=(SL[r0:r0 + n], SR[r0:r0 + n], dl[r0:r0 + n], dr[r0:r0 + n]), params=params)
+    for w in ws:
+        if band_status(w):
+            raise RuntimeError(lib.mccnn_last_error().decode(errors="replace"))
+    return SL, SR, dl, dr
+
+
 def band_status(ws) -> int:
     """Synchronises the stream; 0 = every scanline of the last mccnn_sgm_sharded launch got its hand-over, 1 = a wait hit the
     deadline (a neighbour rank died / never launched): the outputs are invalid."""
@@ -97,7 +148,8 @@ def emulate_bands(CL, CR, il, ir, D, world: int, epoch: int = 1):
 class ShardedMatcher:
     """One pair per call, split by rows over the ranks of `group` (one process per GPU, NCCL)."""
 
-    def __init__(self, H: int, W: int, D: int, weights: dict, num_layers: int = 5, group=None, timeout_ms: int = 2000):
+    def __init__(self, H: int, W: int, D: int, weights: dict, num_layers: int = 5, group=None, timeout_ms: int = 2000,
+                 mode: str = "exact"):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
 
@@ -110,7 +162,8 @@ class ShardedMatcher:
         self.max_rows = max(n for _, n in self.bands)  # bands may differ by one row: gathers are padded to this
         self.packed = eng.pack_weights(weights, num_layers)
         lib = _lib.load()
-        nx = lib.mccnn_sgm_shard_exchange_bytes(W)
+        self.fused = eng._mode(mode) == eng.FUSED
+        nx = lib.mccnn_sgm_fused_shard_exchange_bytes(W, D) if self.fused else lib.mccnn_sgm_shard_exchange_bytes(W)
         self.xchg = symm_mem.empty(nx, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
         self.xchg.zero_()
         self.handle = symm_mem.rendezvous(self.xchg, self.group)
@@ -120,9 +173,11 @@ class ShardedMatcher:
         self.epoch = 0
         self.timeout_ms = int(timeout_ms)
         self.go = torch.ones(1, dtype=torch.int32, device="cuda")       # all-reduced (MIN) before every SGM launch
-        self.sgm_ws = torch.zeros(256, dtype=torch.uint8, device="cuda")
+        self.sgm_ws = torch.zeros(lib.mccnn_sgm_workspace_bytes(H, W, D) if self.fused else 256, dtype=torch.uint8, device="cuda")
         self.tc_ws = None
-        if D >= 512:   # the cost-volume variant mccnn_disparity_pipeline picks for wide bands (pipeline.cu)
+        if self.fused:
+            self.tc_ws = torch.empty(lib.mccnn_cost_volume_fast_tc_workspace_bytes(self.max_rows, W), dtype=torch.uint8, device="cuda")
+        elif D >= 512:   # the cost-volume variant mccnn_disparity_pipeline picks for wide bands (pipeline.cu)
             self.tc_ws = torch.empty(lib.mccnn_cost_volume_tc_workspace_bytes(self.max_rows, W), dtype=torch.uint8, device="cuda")
         Dp = eng.disp_pitch(D)
         self.S = (torch.empty((self.rows, W, Dp), dtype=torch.float32, device="cuda"),
@@ -152,6 +207,11 @@ class ShardedMatcher:
         Dp = eng.disp_pitch(self.D)
         CL = torch.empty((n, W, Dp), dtype=torch.float32, device="cuda")
         CR = torch.empty((n, W, Dp), dtype=torch.float32, device="cuda")
+        if self.fused:
+            _lib.check(lib.mccnn_cost_volume_fast_tc(fl.data_ptr(), fr.data_ptr(), CL.data_ptr(), CR.data_ptr(), self.tc_ws.data_ptr(),
+                                                     self.tc_ws.numel(), n, W, self.D, 1.0, torch.cuda.current_stream().cuda_stream),
+                       "mccnn_cost_volume_fast_tc")
+            return CL, CR
         _lib.check(lib.mccnn_cost_volume_tc(fl.data_ptr(), fr.data_ptr(), CL.data_ptr(), CR.data_ptr(), self.tc_ws.data_ptr(),
                                             self.tc_ws.numel(), n, W, self.D, 1.0, torch.cuda.current_stream().cuda_stream),
                    "mccnn_cost_volume_tc")
@@ -185,8 +245,11 @@ class ShardedMatcher:
         self.epoch += 1
         shard = _shard(self.rank, self.world, self.H, r0, n, self.xchg.data_ptr(), self.prev, self.next, self.epoch,
                        self.go.data_ptr(), self.timeout_ms)
-        sgm_band(CL, CR, self.il, self.ir, self.D, shard, keep_volumes=False,
-                 out=(self.S[0], self.S[1], self.f_send[0, :n], self.f_send[1, :n]), ws=self.sgm_ws)
+        out = (self.S[0], self.S[1], self.f_send[0, :n], self.f_send[1, :n])
+        if self.fused:
+            sgm_fused_band(CL, CR, self.il, self.ir, self.D, shard, self.sgm_ws, keep_volumes=False, out=out)
+        else:
+            sgm_band(CL, CR, self.il, self.ir, self.D, shard, keep_volumes=False, out=out, ws=self.sgm_ws)
         self._gather(self.f_send, self.f_recv, self.dl, self.dr)
         fl, _ = eng.lr_flags(self.dl, self.dr, right=False)
         filled = eng.lrc_fill(self.dl, fl)

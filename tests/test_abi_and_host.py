@@ -200,3 +200,26 @@ def test_output_dtype_contract():
     d = np.array([[0.0, 3.75, 254.0, 399.5]], np.float32)
     assert np.array_equal(ms.encode_disparity(d, 128, 2), np.array([[0, 6, 252, 30]], np.uint8))   # the reference's wrap, kept
     assert np.array_equal(ms.encode_disparity(d, 400, 2), np.array([[0, 6, 508, 798]], np.uint16))
+
+
+def test_fused_sharded_argument_errors_without_gpu(lib):
+    """mccnn_sgm_fused_sharded rejects bad bands before any CUDA call."""
+    import ctypes as C
+    from scenedepthestimation_b200 import _lib
+
+    assert lib.mccnn_sgm_fused_shard_exchange_bytes(0, 16) == 0 and lib.mccnn_sgm_fused_shard_exchange_bytes(64, 2000) == 0
+    n64, n1000 = lib.mccnn_sgm_fused_shard_exchange_bytes(100, 64), lib.mccnn_sgm_fused_shard_exchange_bytes(100, 1000)
+    assert 0 < n64 < n1000 and n64 % 256 == 0
+    prm = _lib.default_sgm_params()
+    p, big = 1 << 20, 1 << 40
+
+    def call(shard):
+        return lib.mccnn_sgm_fused_sharded(p, p, p, p, p, p, p, p, p, big, 64, 16, C.byref(prm), 0, shard, 15, None)
+
+    assert call(None) == -1 and b"null shard" in lib.mccnn_last_error()
+    bad_order = _lib.Shard(1, 2, 32, 0, 16, p, p, None, 1, None, 0)           # rank 1 must not start at row 0
+    assert call(C.byref(bad_order)) == -1 and b"tile the image" in lib.mccnn_last_error()
+    no_epoch = _lib.Shard(0, 2, 32, 0, 16, p, None, p, 0, None, 0)
+    assert call(C.byref(no_epoch)) == -1 and b"epoch" in lib.mccnn_last_error()
+    no_peer = _lib.Shard(0, 2, 32, 0, 16, p, None, None, 1, None, 0)
+    assert call(C.byref(no_peer)) == -1 and b"peer" in lib.mccnn_last_error()

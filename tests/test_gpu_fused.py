@@ -180,3 +180,25 @@ def test_fused_mode_through_the_drop_ins_and_optional_stages(eng, tmp_path, monk
     match_single.main(["-i", "0", "-f", "f", "--weights", "random", "--ndisp", str(D), "--mode", "fused"])
     got = cv2.imread("result/f/ld0.png", cv2.IMREAD_UNCHANGED)
     assert np.array_equal(got, match_single.match_images(pairs[0][0], pairs[0][1], w, D, 1, mode="fused"))
+
+
+# ---- the fused mode's row bands (one pair over several GPUs), several "ranks" on one GPU in dependency order
+BANDS = [(37, 45, 16, "noise", 2), (64, 80, 70, "tex", 3), (61, 50, 33, "noise", 4), (100, 300, 228, "tex", 2), (9, 40, 20, "noise", 8),
+         (30, 1300, 40, "tex", 2), (1300, 11, 24, "noise", 3), (3, 30, 9, "noise", 3), (40, 33, 1000, "noise", 3)]
+
+
+@pytest.mark.parametrize("H,W,D,kind,world", BANDS)
+def test_fused_bands_equal_the_unsharded_fused_mode(eng, H, W, D, kind, world):
+    """mccnn_sgm_fused_sharded, bands of uneven height down to one row, entry / exit states of the column sweep, the row sweeps'
+    FIFOs between bands, the diagonal sweep's hand-over: value for value the unsharded fused mode."""
+    from scenedepthestimation_b200 import sharded
+
+    il, ir, fl, fr = _inputs(H, W, D, kind, H * 5 + W + world)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    SL, SR, dl, dr = eng.sgm(CL, CR, dev(il), dev(ir), D, keep_volumes=True, mode="fused")
+    for keep in (True, False):
+        bSL, bSR, bdl, bdr = sharded.emulate_fused_bands(CL, CR, dev(il), dev(ir), D, world, epoch=3, keep_volumes=keep)
+        torch.cuda.synchronize()
+        assert torch.equal(bdl, dl) and torch.equal(bdr, dr)
+        if keep:
+            assert torch.equal(bSL[..., :D], SL[..., :D]) and torch.equal(bSR[..., :D], SR[..., :D])

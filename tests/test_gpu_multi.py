@@ -33,6 +33,23 @@ def test_two_rank_sharded_pair_is_bit_identical(cfg):
     assert "bit-identical to single GPU: True" in r.stdout
 
 
+@pytest.mark.parametrize("cfg", ["c1", "c5"])
+def test_two_rank_sharded_pair_fused_mode_equals_single_gpu_fused(cfg):
+    """mccnn_sgm_fused_sharded over real NVLink peer memory: the row sweeps' step-by-step FIFOs between the ranks, the column /
+    diagonal hand-overs. Value for value the single-GPU fused mode."""
+    _need(2)
+    r = _torchrun(2, cfg, "fused")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "fused: bit-identical to single GPU: True" in r.stdout
+
+
+def test_two_rank_fault_fused_mode():
+    _need(2)
+    r = _torchrun(2, "c1", "fused", "fault", timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("abandoned pair raised") == 2 and "bit-identical to single GPU: True" in r.stdout
+
+
 def test_two_rank_fault_is_loud_not_a_hang():
     _need(2)
     r = _torchrun(2, "c1", "fault", timeout=300)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """torchrun entry: one pair split by rows over the ranks (ShardedMatcher) vs the single-GPU path; parity + timing.
-   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/run_sharded.py [cfg]"""
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/run_sharded.py [cfg] [fused] [fault]"""
 import os, sys, time
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,10 +14,12 @@ def main():
     W, H, D = syn.CONFIGS[cfg]
     il, ir, _ = syn.textured_pair(H, W, D, 77)
     weights = syn.glorot_weights()
-    m = sharded.ShardedMatcher(H, W, D, weights)
+    opts = sys.argv[2:]
+    mode = "fused" if "fused" in opts else "exact"
+    m = sharded.ShardedMatcher(H, W, D, weights, mode=mode)
     r0, n = m.row0, m.rows
     bl, br = torch.from_numpy(il[r0:r0 + n]).cuda(), torch.from_numpy(ir[r0:r0 + n]).cuda()
-    if len(sys.argv) > 2 and sys.argv[2] == "fault":
+    if "fault" in opts:
         # one rank hands in a band of the wrong shape: EVERY rank must raise for this pair (nobody waits in a kernel), and the
         # next, well-formed pair must work again
         raised = False
@@ -35,13 +37,13 @@ def main():
     torch.cuda.synchronize()
     ok = True
     if rank == 0:
-        ref_l, ref_r = eng.match_pair(torch.from_numpy(il).cuda(), torch.from_numpy(ir).cuda(), m.packed, D, 5)
+        ref_l, ref_r = eng.match_pair(torch.from_numpy(il).cuda(), torch.from_numpy(ir).cuda(), m.packed, D, 5, mode=mode)
         ok = bool(torch.equal(ref_l, dl) and torch.equal(ref_r, dr))
-        print(f"[sharded x{world}] {cfg} {W}x{H} D={D}: bit-identical to single GPU: {ok}", flush=True)
+        print(f"[sharded x{world}] {cfg} {W}x{H} D={D} {mode}: bit-identical to single GPU: {ok}", flush=True)
         t = []
         for _ in range(3):
             torch.cuda.synchronize(); t0 = time.perf_counter()
-            eng.match_pair(torch.from_numpy(il).cuda(), torch.from_numpy(ir).cuda(), m.packed, D, 5)
+            eng.match_pair(torch.from_numpy(il).cuda(), torch.from_numpy(ir).cuda(), m.packed, D, 5, mode=mode)
             torch.cuda.synchronize(); t.append(time.perf_counter() - t0)
         print(f"[single] {min(t) * 1e3:.2f} ms", flush=True)
         eng._ws.clear()
