@@ -315,7 +315,7 @@ __device__ __forceinline__ float warp_wta(const float (&so)[NPL], int lane, int 
 // flight x latency, not by the 8 warps' instruction rate).
 template <int NPL, bool READS>
 struct ChainSmem {
-    static constexpr int FW = NPL > 25 ? 10 : FW_MAX;
+    static constexpr int FW = NPL > 25 ? 10 : FW_MAX;   // (a 13th warp for sweep 0 = 3 instead of 4 rounds of columns at c4, but 128 registers: measured slower, 68.1 vs 66.1 ms)
     static constexpr int STG = READS ? 1 : 2;
     static constexpr int NIN = READS ? 2 : 1;
     static constexpr int ROWF = 32 * NPL;
@@ -996,7 +996,7 @@ int launch_chain(FusedArgs a, cudaStream_t stream) {
     const int per_round = ceil_div(a.U, rounds);
     int fw = ceil_div(per_round, ctas);
     static const int env_fw = [] { const char* e = getenv("MCCNN_FUSED_FW"); return e ? atoi(e) : 0; }();
-    if (env_fw > 0) fw = env_fw;
+    if (env_fw > 0 && env_fw <= FW && ceil_div(per_round, env_fw) <= ctas) fw = env_fw;
     if (fw > FW) fw = FW;
     ctas = ceil_div(per_round, fw);
     a.ctas = ctas;

@@ -202,3 +202,33 @@ def test_fused_bands_equal_the_unsharded_fused_mode(eng, H, W, D, kind, world):
         assert torch.equal(bdl, dl) and torch.equal(bdr, dr)
         if keep:
             assert torch.equal(bSL[..., :D], SL[..., :D]) and torch.equal(bSR[..., :D], SR[..., :D])
+
+
+def test_fused_band_waits_are_bounded(eng):
+    """mccnn_sgm_fused_sharded with nobody on the other side: the column sweep's entry states, the row sweeps' FIFO and the
+    diagonal sweep's hand-over never arrive. Every wait must end at the deadline and the status word must say so; with the go
+    flag at 0 the kernels return at once and leave the status alone."""
+    import time
+
+    from scenedepthestimation_b200 import _lib, sharded as sh
+
+    H, W, D = 24, 40, 16
+    il, ir, fl, fr = _inputs(H, W, D, "noise", 3)
+    CL, CR = eng.cost_volume(dev(fl), dev(fr), D)
+    lib = _lib.load()
+    xchg = [torch.zeros(lib.mccnn_sgm_fused_shard_exchange_bytes(W, D), dtype=torch.uint8, device="cuda") for _ in range(3)]
+    ws = torch.zeros(lib.mccnn_sgm_workspace_bytes(H, W, D), dtype=torch.uint8, device="cuda")
+    # rank 1 of 3 (rows 8..15): waits on the rank above in sweeps 0 and 1, on the rank below in sweeps 2 and 3
+    for mask in (1, 2, 4, 8, 15):
+        for go_value, want in ((1, 1), (0, 0)):
+            go = torch.full((1,), go_value, dtype=torch.int32, device="cuda")
+            shard = sh._shard(1, 3, H, 8, 8, xchg[1].data_ptr(), xchg[0].data_ptr(), xchg[2].data_ptr(), 9, go.data_ptr(), 40)
+            ws.zero_()
+            for x in xchg:
+                x.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sh.sgm_fused_band(CL[8:16], CR[8:16], dev(il), dev(ir), D, shard, ws, sweep_mask=mask)
+            st = sh.band_status(ws)
+            dt = time.perf_counter() - t0
+            assert st == want and dt < 5.0, (mask, go_value, st, dt)
