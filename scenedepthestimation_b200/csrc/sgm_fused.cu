@@ -42,6 +42,7 @@ constexpr int MAX_CHAIN_CTAS = 512;
 constexpr float kInf = __builtin_huge_valf();
 
 struct FusedArgs {
+    int side_base;   // first side (0 = left volume, 1 = right) of a chain launch; a launch covers gridDim.x / ctas sides
     const float* C[2];
     float* S[2];
     const unsigned char* img[2];
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
     fence_proxy_async_smem();
     __syncthreads();
 
-    const int side = blockIdx.x / a.ctas, cta = blockIdx.x - side * a.ctas;
+    const int side = a.side_base + blockIdx.x / a.ctas, cta = blockIdx.x % a.ctas;
     const int fw = (int)(blockDim.x >> 5);     // warps this launch runs per CTA (<= FW; the shared-memory layout is FW's)
     const int n = a.ctas * fw;                 // warps of this chain
     const int w = cta * fw + warp;             // position in the chain
@@ -980,14 +981,27 @@ FusedLayout fused_layout(int H, int W, int D) {
     return l;
 }
 
+// rounds a chain of `units` needs when `sides` chains share the GPU
 template <int NPL, bool READS, bool BAND>
-int launch_chain(FusedArgs a, cudaStream_t stream) {
+int chain_rounds(int units, int sides, int* rounds) {
+    constexpr int FW = ChainSmem<NPL, READS>::FW;
+    int per_sm = 0;
+    if (int e = kernel_setup<sgm_chain_kernel<NPL, READS, BAND>>(FW * 32, ChainSmem<NPL, READS>::BYTES, &per_sm)) return e;
+    int ctas = (sm_count() * per_sm) / sides;
+    if (ctas > MAX_CHAIN_CTAS) ctas = MAX_CHAIN_CTAS;
+    *rounds = ctas >= 1 ? ceil_div(units, ctas * FW) : (1 << 20);
+    return 0;
+}
+
+// sides = 2: both volumes in one launch (one chain each, half the GPU each); sides = 1: the chain of side a.side_base alone
+template <int NPL, bool READS, bool BAND>
+int launch_chain(FusedArgs a, cudaStream_t stream, int sides = 2) {
     constexpr int FW = ChainSmem<NPL, READS>::FW;
     const size_t smem = ChainSmem<NPL, READS>::BYTES;
     int per_sm = 0;
     if (int e = kernel_setup<sgm_chain_kernel<NPL, READS, BAND>>(FW * 32, smem, &per_sm)) return e;
     MCCNN_REQUIRE(per_sm >= 1, MCCNN_EINVAL, "sgm_chain_kernel<%d>: does not fit on an SM (smem %zu)", NPL, smem);
-    int ctas = (sm_count() * per_sm) / 2;   // one chain per side; every CTA must be resident (cooperative launch)
+    int ctas = (sm_count() * per_sm) / sides;   // one chain per side; every CTA must be resident (cooperative launch)
     if (ctas > MAX_CHAIN_CTAS) ctas = MAX_CHAIN_CTAS;
     MCCNN_REQUIRE(ctas >= 1, MCCNN_EINVAL, "sgm_chain_kernel: no resident CTA available");
     // full rounds: the units of a side are dealt to ctas * fw warps; keep the last round as full as the others, and spread
@@ -1001,7 +1015,7 @@ int launch_chain(FusedArgs a, cudaStream_t stream) {
     ctas = ceil_div(per_round, fw);
     a.ctas = ctas;
     void* params[] = {&a};
-    MCCNN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sgm_chain_kernel<NPL, READS, BAND>), dim3(2 * ctas), dim3(fw * 32), params,
+    MCCNN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sgm_chain_kernel<NPL, READS, BAND>), dim3(sides * ctas), dim3(fw * 32), params,
                                            smem, stream));
     return 0;
 }
@@ -1104,7 +1118,29 @@ int run_fused_band_npl(FusedArgs a, int keep_volumes, cudaStream_t stream, unsig
                 a.ext_prod_out = reinterpret_cast<unsigned long long*>(to + prod_off);
             }
         }
-        if (int e = (sweep == 0 ? launch_chain<NPL, false, true>(a, stream) : launch_chain<NPL, true, true>(a, stream))) return e;
+        a.side_base = 0;
+        if (sweep == 0) {
+            if (int e = launch_chain<NPL, false, true>(a, stream)) return e;
+            continue;
+        }
+        // Row sweeps: rank r can start when the rank it follows starts its LAST round, so with R rounds per rank the sweep
+        // takes (world - 1)(R - 1) + R round times. When a band has more rows than half the GPU holds warps but not more than
+        // the whole GPU does (c4 on 2 GPUs: 994 rows, 888 / 1776 warps), one side after the other on the whole GPU is faster:
+        // 2 x 1 round in lock step with the neighbour instead of 3.
+        int r2 = 0, r1 = 0;
+        if (int e = chain_rounds<NPL, true, true>(a.U, 2, &r2)) return e;
+        if (int e = chain_rounds<NPL, true, true>(a.U, 1, &r1)) return e;
+        const int hops = sh->world - 1;
+        static const int env_seq = [] { const char* e = getenv("MCCNN_FUSED_SIDES_SEQ"); return e ? atoi(e) : -1; }();
+        const bool seq = env_seq >= 0 ? env_seq != 0 : 2 * (hops * (r1 - 1) + r1) < hops * (r2 - 1) + r2;
+        if (!seq) {
+            if (int e = launch_chain<NPL, true, true>(a, stream)) return e;
+        } else {
+            for (int side = 0; side < 2; side++) {
+                a.side_base = side;
+                if (int e = launch_chain<NPL, true, true>(a, stream, 1)) return e;
+            }
+        }
     }
     if (!(sweep_mask & 8)) return 0;
     a.store_s = keep_volumes;

@@ -232,3 +232,18 @@ def test_fused_band_waits_are_bounded(eng):
             st = sh.band_status(ws)
             dt = time.perf_counter() - t0
             assert st == want and dt < 5.0, (mask, go_value, st, dt)
+
+
+def test_fused_bands_one_side_after_the_other():
+    """The row sweeps of a band launch one chain per volume side on the whole GPU when that saves rounds (c4 on 2 GPUs); forced
+    here through the development switch on every band shape above, in a child process (the switch is read once)."""
+    import os
+    import subprocess
+    import sys
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    env = dict(os.environ, MCCNN_FUSED_SIDES_SEQ="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "bands_equal"], env=env,
+                       capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and f"{len(BANDS)} passed" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
