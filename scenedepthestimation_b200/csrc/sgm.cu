@@ -705,6 +705,7 @@ extern "C" int mccnn_sgm(const float* CL, const float* CR, const uint8_t* imageL
     MCCNN_REQUIRE(params->P1 >= 0 && params->P1_red >= 0, MCCNN_EINVAL, "mccnn_sgm: negative P1");
     if (mode == MCCNN_SGM_FUSED) {
         MCCNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, MCCNN_EALIGN, "mccnn_sgm: workspace must be 256-byte aligned");
+        MCCNN_REQUIRE(params->P2 >= 0 && params->P2_red >= 0, MCCNN_EINVAL, "mccnn_sgm: the fused mode needs penalties >= 0");
         return run_sgm_fused(CL, CR, imageL, imageR, SL, SR, dispL, dispR, reinterpret_cast<char*>(workspace) + 256, H, W, D, params,
                              keep_volumes, stream);
     }
@@ -771,7 +772,8 @@ extern "C" int mccnn_sgm_fused_sharded(const float* CLb, const float* CRb, const
                   "mccnn_sgm_fused_sharded: exchange buffer and a non-zero epoch are required");
     MCCNN_REQUIRE((shard->rank == 0 || shard->xchg_prev != nullptr) && (shard->rank == shard->world - 1 || shard->xchg_next != nullptr),
                   MCCNN_EINVAL, "mccnn_sgm_fused_sharded: missing peer exchange pointer");
-    MCCNN_REQUIRE(params->P1 >= 0 && params->P1_red >= 0, MCCNN_EINVAL, "mccnn_sgm_fused_sharded: negative P1");
+    MCCNN_REQUIRE(params->P1 >= 0 && params->P1_red >= 0 && params->P2 >= 0 && params->P2_red >= 0, MCCNN_EINVAL,
+                  "mccnn_sgm_fused_sharded: negative penalty");
     return run_sgm_fused_band(CLb, CRb, imageL, imageR, SLb, SRb, dispLb, dispRb, workspace, W, D, params, keep_volumes, shard,
                               sweep_mask & 15, stream);
 }

@@ -31,7 +31,7 @@
 namespace mccnn {
 namespace {
 
-constexpr int FW_MAX = 12;  // warps per CTA of the chain kernel (10 for rows of 1024 floats: shared memory)
+constexpr int FW_MAX = 11;  // compute warps per CTA of the chain kernel (10 for rows of 1024 floats: shared memory); + 1 link warp
 constexpr int RING = 2;     // hand-over slots between warps of one CTA (shared memory)
 constexpr int GRING = 8;    // hand-over slots between neighbouring CTAs (global memory)
 constexpr int XPUB = 4;    // a band's last unit publishes its rows to the neighbour rank every XPUB steps, XPUB steps late
@@ -59,7 +59,6 @@ struct FusedArgs {
     unsigned* gflags; // [side][ctas][2][FLAG_STRIDE]: produced / consumed counters of the link leaving CTA c
     int slot_floats;  // 32 * NPL + 4
     unsigned* counter;  // sweep 3: scanline counter
-    int debug;          // development only (MCCNN_FUSED_DEBUG): bit 0 = never wait for a hand-over (wrong results, timing only)
     // ---- row-band sharding (BAND kernels; one pair split over several GPUs, mccnn_sgm_fused_sharded): this launch owns image rows
     // [row0, row0 + Hb) of H; the volumes and maps it is given hold only those rows, the u8 images are whole. What crosses a
     // band boundary travels through the neighbours' exchange buffers (peer memory): see the layout in fused_xchg_layout().
@@ -307,26 +306,33 @@ __device__ __forceinline__ float warp_wta(const float (&so)[NPL], int lane, int 
 
 // ------------------------------------------------------------------------------------------------ sweeps 0, 1, 2
 // Shared-memory layout of the chain kernel (floats unless noted):
-//   per warp : inbuf [FSTAGES][NIN][ROWF] | outbuf [ROWF] | ring [RING][SLOTF]   (SLOTF = ROWF + 4: the row and, at [ROWF], its minimum)
+//   per compute warp : inbuf [FSTAGES][NIN][ROWF] | outbuf [ROWF] | ring [RING][SLOTF]   (SLOTF = ROWF + 4: the row and, at [ROWF], its minimum)
 //   per CTA  : inring [INR][SLOTF]  rows prefetched from the previous CTA's global ring (read by warp 0 only)
-//              prodc [FW], consc [FW] (unsigned)   counters of the links between the warps of the CTA
+//              prodc [FW], consc [FW] (unsigned)   counters of the links leaving the compute warps
+//              inpop, incons (unsigned)            warp 0 -> link warp: rows popped from inring (running total / link numbering)
+//              xcons (unsigned)                    link warp -> the warp of a band's last unit: rows of that unit forwarded
 //              mbarriers: FSTAGES per warp, then INR for inring
-// Rows in flight per warp: a sweep that reads S as well has 2 x (cost + S) rows under way per warp; the first sweep (cost
-// only) needs 4 stages to keep as many bytes in flight (measured on c4: 20.5 -> see profiles, the sweep is bound by bytes in
-// flight x latency, not by the 8 warps' instruction rate).
+// Warps: fw <= FW compute warps (one unit each at a time) and ONE LINK WARP (the last warp of the CTA) that moves the rows of
+// the two global links of the CTA: it prefetches the rows the previous CTA published into inring for warp 0 and forwards the
+// rows warp fw - 1 leaves in its ring to the next CTA (or, BAND, to the neighbour GPU). Every compute warp therefore sees the
+// same thing on both sides -- a shared-memory ring with a counter -- and runs the same step. (Before, warp 0 and warp fw - 1 did
+// the global polling, fencing and copying themselves; ncu showed the interior warps polling their predecessor 27 times per
+// step on average: the whole chain ran at the pace of those two warps.)
+// Rows in flight per warp: a sweep that reads S as well has one (cost + S) row pair under way per warp, refilled right after its
+// consumption; the first sweep (cost only) has two stages.
 template <int NPL, bool READS>
 struct ChainSmem {
-    static constexpr int FW = NPL > 25 ? 10 : FW_MAX;   // (a 13th warp for sweep 0 = 3 instead of 4 rounds of columns at c4, but 128 registers: measured slower, 68.1 vs 66.1 ms)
+    static constexpr int FW = NPL > 25 ? 10 : FW_MAX;   // compute warps (the block has one more warp)
     static constexpr int STG = READS ? 1 : 2;
     static constexpr int NIN = READS ? 2 : 1;
     static constexpr int ROWF = 32 * NPL;
     static constexpr int SLOTF = ROWF + 4;
     static constexpr int PER_WARP = ROWF * (STG * NIN + 1) + RING * SLOTF;
-    static constexpr size_t BYTES = (size_t)FW * PER_WARP * 4 + (size_t)INR * SLOTF * 4 + (size_t)2 * FW * 4 + (size_t)(FW * STG + INR) * 8;
+    static constexpr size_t BYTES = (size_t)FW * PER_WARP * 4 + (size_t)INR * SLOTF * 4 + (size_t)(2 * FW + 4) * 4 + (size_t)(FW * STG + INR) * 8;
 };
 
 template <int NPL, bool READS, bool BAND>
-__global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kernel(const FusedArgs a) {
+__global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 1) * 32) sgm_chain_kernel(const FusedArgs a) {
     if constexpr (BAND) {
         if (a.go != nullptr && *reinterpret_cast<const volatile int*>(a.go) == 0) return;   // some rank will not launch: nobody waits
     }
@@ -339,57 +345,240 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
     constexpr uint32_t SLOT_BYTES = SLOTF * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* wbase = reinterpret_cast<float*>(smem_raw) + (size_t)warp * PER_WARP;
+    const int fw = (int)(blockDim.x >> 5) - 1;   // compute warps of this launch (<= FW; the shared-memory layout is FW's); warp fw = link warp
+    float* smem_f = reinterpret_cast<float*>(smem_raw);
+    float* wbase = smem_f + (size_t)(warp < fw ? warp : 0) * PER_WARP;
     float* inbuf = wbase;                            // [FSTAGES][NIN][ROWF]
     float* outbuf = wbase + ROWF * FSTAGES * NIN;    // [ROWF]
-    float* ring = outbuf + ROWF;                     // [RING][SLOTF]: the link warp -> warp + 1 (or the staging rows of the global link)
-    float* inring = reinterpret_cast<float*>(smem_raw) + (size_t)FW * PER_WARP;   // [INR][SLOTF]
+    float* ring = outbuf + ROWF;                     // [RING][SLOTF]: the link warp -> warp + 1 (the last compute warp's is drained by the link warp)
+    float* inring = smem_f + (size_t)FW * PER_WARP;                              // [INR][SLOTF]
     unsigned* prodc = reinterpret_cast<unsigned*>(inring + INR * SLOTF);         // [FW] rows published on the link leaving warp w
     unsigned* consc = prodc + FW;                                                // [FW] rows the reader of that link is done with
-    uint64_t* bars_all = reinterpret_cast<uint64_t*>(consc + FW);
-    uint64_t* bars = bars_all + warp * FSTAGES;
+    unsigned* inpop = consc + FW;                                                // rows warp 0 has popped from inring, running total
+    unsigned* incons = inpop + 1;                                                // ... in the numbering of the chain's global link
+    unsigned* xcons = inpop + 2;                                                 // BAND: rows of the band's last unit the link warp has taken
+    uint64_t* bars_all = reinterpret_cast<uint64_t*>(inpop + 4);
+    uint64_t* bars = bars_all + (warp < fw ? warp : 0) * FSTAGES;
     uint64_t* inbars = bars_all + FW * FSTAGES;                                  // [INR]
 
-    if (lane == 0) {
+    if (lane == 0 && warp < fw) {
 #pragma unroll
         for (int s = 0; s < FSTAGES; s++) mbar_init(&bars[s], 1);
-        if (warp == 0)
+        if (warp == 0) {
             for (int s = 0; s < INR; s++) mbar_init(&inbars[s], 1);
+            *inpop = 0u;
+            *incons = 0u;
+            *xcons = 0u;
+        }
         mbar_fence_init();
         prodc[warp] = 0u;
         consc[warp] = 0u;
     }
     // tails [Dp, 32 * NPL) of the row buffers stay +INF for ever (the bulk copies bring Dp floats): those disparities never win
-    for (int i = lane; i < ROWF * FSTAGES * NIN; i += 32) inbuf[i] = kInf;
+    if (warp < fw)
+        for (int i = lane; i < ROWF * FSTAGES * NIN; i += 32) inbuf[i] = kInf;
     fence_proxy_async_smem();
     __syncthreads();
 
     const int side = a.side_base + blockIdx.x / a.ctas, cta = blockIdx.x % a.ctas;
-    const int fw = (int)(blockDim.x >> 5);     // warps this launch runs per CTA (<= FW; the shared-memory layout is FW's)
-    const int n = a.ctas * fw;                 // warps of this chain
-    const int w = cta * fw + warp;             // position in the chain
-    const float* __restrict__ Cv = a.C[side];
-    float* __restrict__ Sv = a.S[side];
-    const unsigned char* __restrict__ img = a.img[side];
+    const int n = a.ctas * fw;                 // compute warps of this chain
     const int W = a.W, H = a.H, T = a.T;
-    const uint32_t copy_bytes = (uint32_t)a.Dp * 4u;
-    const size_t pitch = (size_t)a.Dp;
 
     // links. The one that leaves CTA c for CTA c + 1 is global link c; link ctas - 1 closes the ring (T slots).
-    // A global link is a FIFO of rows: the producer pushes one row per step of every unit it hands over (T per unit, payload
-    // or not), the consumer pops T rows per unit; row index = round * T + step.
-    const bool in_local = warp > 0, out_local = warp < fw - 1;
+    // A global link is a FIFO of rows: the producer side pushes one row per step of every unit it hands over (T per unit,
+    // payload or not), the consumer pops T rows per unit; row index = round * T + step.
     const int lin = cta == 0 ? a.ctas - 1 : cta - 1, lout = cta;
     const size_t side_floats = ((size_t)a.ctas * GRING + (size_t)T) * SLOTF;
     auto link_base = [&](int l) { return a.glink + (size_t)side * side_floats + (size_t)l * GRING * SLOTF; };
     const unsigned depth_in = lin == a.ctas - 1 ? (unsigned)T : (unsigned)GRING;
     const unsigned depth_out = lout == a.ctas - 1 ? (unsigned)T : (unsigned)GRING;
-    const float* gin = link_base(lin);
-    float* gout = link_base(lout);
-    unsigned* gprod_in = a.gflags + ((size_t)(side * a.ctas + lin) * 2 + 0) * FLAG_STRIDE;
-    unsigned* gcons_in = a.gflags + ((size_t)(side * a.ctas + lin) * 2 + 1) * FLAG_STRIDE;
-    unsigned* gprod_out = a.gflags + ((size_t)(side * a.ctas + lout) * 2 + 0) * FLAG_STRIDE;
-    unsigned* gcons_out = a.gflags + ((size_t)(side * a.ctas + lout) * 2 + 1) * FLAG_STRIDE;
+
+    // BAND: local rows are [0, Hb) of the volumes, image rows [row0, row0 + Hb); ug = the unit's index in the WHOLE image's chain
+    const int row0 = BAND ? a.row0 : 0;
+    const int Hloc = BAND ? a.Hb : H;       // rows of the volumes this launch works on
+    const int ubase = !BAND ? 0 : (a.sweep == 1 ? row0 : (a.sweep == 2 ? H - (row0 + Hloc) : 0));
+    // which units take rows from / hand rows to a global link (both warps of a link and the link warps use these)
+    auto unit_ext_in = [&](int u) -> bool { return BAND && a.sweep != 0 && a.ext_in != nullptr && u == 0; };
+    auto unit_ext_out = [&](int u) -> bool { return BAND && a.sweep != 0 && a.ext_out != nullptr && u == a.U - 1; };
+    auto unit_pops = [&](int u) -> bool { return ubase + u >= 1 && (u >= 1 || unit_ext_in(u)); };       // unit of a warp 0
+    auto unit_pushes = [&](int u) -> bool { return a.sweep == 0 ? true : (ubase + u <= H - 2); };       // unit of a warp fw - 1
+
+    // ================================================================================================ the link warp
+    if (warp == fw) {
+        if (lane != 0) return;
+        const float* gin = link_base(lin);
+        float* gout = link_base(lout);
+        unsigned* gprod_in = a.gflags + ((size_t)(side * a.ctas + lin) * 2 + 0) * FLAG_STRIDE;
+        unsigned* gcons_in = a.gflags + ((size_t)(side * a.ctas + lin) * 2 + 1) * FLAG_STRIDE;
+        unsigned* gprod_out = a.gflags + ((size_t)(side * a.ctas + lout) * 2 + 0) * FLAG_STRIDE;
+        unsigned* gcons_out = a.gflags + ((size_t)(side * a.ctas + lout) * 2 + 1) * FLAG_STRIDE;
+        // the rows to forward come from the ring of warp fw - 1; BAND: the band's last unit feeds the neighbour GPU from whatever
+        // warp it runs on (it is the last unit of the chain, so it comes after everything else this warp forwards)
+        int osrc = fw - 1;
+        bool ext_tail = BAND && a.sweep != 0 && a.ext_out != nullptr && ((a.U - 1) % n) / fw == cta && ((a.U - 1) % n) % fw != fw - 1 &&
+                        unit_pushes(a.U - 1);
+        // Ordering on the global links. The rows reach L2 through the copy engine and the counter is written only after
+        // cp.async.bulk.wait_group has reported them complete; the consumer side reads the counter from L2 (relaxed.gpu bypasses
+        // L1) and only then lets the copy engine read the rows from L2, the copy being control-dependent on the counter's value.
+        // fence.proxy.async orders the generic-proxy counter access against the async-proxy copies of the same thread.
+        // ---- input side: the units of warp 0
+        int iu = cta * fw, iround = 0;
+        unsigned it = 0;            // rows of the current unit requested so far
+        unsigned in_req = 0;        // rows ever requested into inring: slot and mbarrier phase
+        unsigned avail = 0;         // rows published on the current source
+        unsigned cons_pub = 0;      // last value forwarded to the producer of the chain link
+        unsigned long long wait_t0 = 0;
+        while (iu < a.U && !unit_pops(iu)) { iu += n; iround++; }
+        // ---- output side: the units of warp fw - 1
+        int ou = cta * fw + fw - 1, oround = 0;
+        unsigned ot = 0;            // rows of the current unit forwarded so far
+        unsigned cons_seen = 0;     // rows the next CTA has popped from the chain link
+        bool unpublished = false;   // the copy of the latest row has been committed but the row is not announced yet
+        bool in_closed = false;
+        while (ou < a.U && !unit_pushes(ou)) { ou += n; oround++; }
+        auto next_out_unit = [&]() {
+            do { ou += n; oround++; } while (ou < a.U && !unit_pushes(ou));
+            if (ou >= a.U && ext_tail) {
+                ext_tail = false;
+                ou = a.U - 1; oround = (a.U - 1) / n; osrc = ((a.U - 1) % n) % fw;
+            }
+        };
+        if (ou >= a.U && ext_tail) { ou -= n; oround--; next_out_unit(); }
+
+        while (iu < a.U || ou < a.U) {
+            bool progress = false;
+            if (ou < a.U) {
+                const unsigned qo = (unsigned)oround * (unsigned)T + ot;        // the row's index on the link leaving warp fw - 1
+                if (ld_acquire_cta_smem(&prodc[osrc]) >= qo + 1u) {
+                    const bool ext = unit_ext_out(ou);
+                    bool slot_free = ext || qo + 1u <= depth_out || cons_seen >= qo + 1u - depth_out;
+                    if (!slot_free) {
+                        cons_seen = ld_relaxed_gpu(gcons_out);
+                        slot_free = cons_seen >= qo + 1u - depth_out;
+                    }
+                    if (slot_free) {
+                        fence_proxy_async_smem();
+                        float* dst = gout + (size_t)(qo % depth_out) * SLOTF;
+                        if constexpr (BAND) {
+                            if (ext) dst = a.ext_out + ((size_t)side * T + ot) * SLOTF;   // T slots: none is reused inside a pair
+                        }
+                        const float* src_ring = smem_f + (size_t)osrc * PER_WARP + ROWF * (FSTAGES * NIN + 1);
+                        bulk_s2g(dst, src_ring + (size_t)(qo % RING) * SLOTF, SLOT_BYTES);
+                        bulk_commit();
+                        bulk_wait_read<0>();                                   // the ring slot has been read: its warp may reuse it
+                        ot++;
+                        if (osrc == fw - 1) st_release_cta_smem(&consc[fw - 1], qo + 1u);
+                        else st_release_cta_smem(xcons, ot);
+                        const bool unit_done = ot == (unsigned)T;
+                        // Publication runs behind the copies: a row is announced once its copy is COMPLETE, and waiting for the
+                        // copy just committed would put the write latency of L2 (or of NVLink) into every step.
+                        unpublished = !unit_done;
+                        if (!ext) {
+                            if (unit_done) bulk_wait_all<0>(); else bulk_wait_all<1>();
+                            fence_proxy_async_global();
+                            st_relaxed_gpu(gprod_out, unit_done ? qo + 1u : qo);
+                        } else if constexpr (BAND) {
+                            // the neighbour GPU: the counter carries the pair's epoch; every XPUB rows, XPUB rows late
+                            if (unit_done) {
+                                bulk_wait_all<0>();
+                                fence_proxy_async_global();
+                                st_release_sys_u64(a.ext_prod_out + side * 16, ((unsigned long long)a.epoch << 32) | (unsigned long long)T);
+                            } else if (ot >= 2u * XPUB && (ot % XPUB) == 0u) {
+                                bulk_wait_all<XPUB>();
+                                fence_proxy_async_global();
+                                st_release_sys_u64(a.ext_prod_out + side * 16, ((unsigned long long)a.epoch << 32) | (unsigned long long)(ot - XPUB));
+                            }
+                        }
+                        if (unit_done) {
+                            ot = 0;
+                            next_out_unit();
+                        }
+                        progress = true;
+                    }
+                }
+            }
+            if (iu < a.U) {
+                const bool ext = unit_ext_in(iu);
+                if (!ext) {   // tell the producer which slots of the chain link are free again
+                    const unsigned cv = ld_acquire_cta_smem(incons);
+                    if (cv != cons_pub) {
+                        st_relaxed_gpu(gcons_in, cv);
+                        cons_pub = cv;
+                    }
+                }
+                if (in_req < ld_acquire_cta_smem(inpop) + (unsigned)INR) {   // a free inring slot
+                    const unsigned qbase = ext ? 0u : (unsigned)(cta == 0 ? iround - 1 : iround) * (unsigned)T;
+                    const unsigned q = qbase + it;
+                    if (avail <= q) {
+                        if constexpr (BAND) {
+                            if (ext) {   // epoch-tagged 64-bit counter in this rank's exchange buffer, written by the neighbour GPU
+                                const unsigned long long v = ld_acquire_sys_u64(a.ext_prod_in + side * 16);
+                                avail = (unsigned)(v >> 32) == a.epoch ? (unsigned)v : 0u;
+                                if (avail <= q) {   // another GPU feeds this FIFO: the wait is bounded
+                                    if (wait_t0 == 0) wait_t0 = timer_ns();
+                                    if (*reinterpret_cast<volatile unsigned*>(a.status) != 0u) avail = (unsigned)T;
+                                    else if (timer_ns() - wait_t0 > a.timeout_ns) { atomicExch(a.status, 1u); avail = (unsigned)T; }
+                                } else {
+                                    wait_t0 = 0;
+                                }
+                            } else {
+                                avail = ld_relaxed_gpu(gprod_in);
+                            }
+                        } else {
+                            avail = ld_relaxed_gpu(gprod_in);
+                        }
+                    }
+                    if (avail > q) {
+                        const unsigned sl = in_req % INR;
+                        const float* src = gin + (size_t)(q % depth_in) * SLOTF;
+                        if constexpr (BAND) {
+                            if (ext) src = a.ext_in + ((size_t)side * T + it) * SLOTF;
+                        }
+                        fence_proxy_async_global();
+                        mbar_expect_tx(&inbars[sl], SLOT_BYTES);
+                        bulk_g2s(inring + (size_t)sl * SLOTF, src, SLOT_BYTES, &inbars[sl]);
+                        in_req++;
+                        it++;
+                        if (it == (unsigned)T) {
+                            it = 0;
+                            if (ext) avail = 0;   // back to the chain's own link, whose numbering starts at 0
+                            do { iu += n; iround++; } while (iu < a.U && !unit_pops(iu));
+                        }
+                        progress = true;
+                    }
+                }
+            }
+            if (iu >= a.U && !in_closed) {
+                // no more units for warp 0: whatever still arrives on the input link is not needed (its rows are all in shared
+                // memory); the producer must not wait for free slots any more
+                st_relaxed_gpu(gcons_in, 0xffffffffu);
+                in_closed = true;
+            }
+            if (!progress) {
+                if (unpublished && ou < a.U) {   // nothing else to do: announce the latest row now instead of with the next one
+                    bulk_wait_all<0>();
+                    fence_proxy_async_global();
+                    if (!unit_ext_out(ou)) st_relaxed_gpu(gprod_out, (unsigned)oround * (unsigned)T + ot);
+                    else if constexpr (BAND) st_release_sys_u64(a.ext_prod_out + side * 16, ((unsigned long long)a.epoch << 32) | (unsigned long long)ot);
+                    unpublished = false;
+                } else {
+                    __nanosleep(40);
+                }
+            }
+        }
+        if (!in_closed) st_relaxed_gpu(gcons_in, 0xffffffffu);
+        bulk_wait_all<0>();
+        return;
+    }
+
+    // ================================================================================================ the compute warps
+    const int w = cta * fw + warp;             // position in the chain
+    const float* __restrict__ Cv = a.C[side];
+    float* __restrict__ Sv = a.S[side];
+    const unsigned char* __restrict__ img = a.img[side];
+    const uint32_t copy_bytes = (uint32_t)a.Dp * 4u;
+    const size_t pitch = (size_t)a.Dp;
+    const bool in_local = warp > 0, out_local = warp < fw - 1;
     const float* lring_in = ring - PER_WARP;   // the previous warp's ring (only dereferenced when in_local)
 
     // geometry of the sweep: pixel(u, t), the step along the unit and the offset to the neighbouring unit's pixel
@@ -397,81 +586,7 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
     const int upoff = a.sweep == 0 ? -1 : (a.sweep == 1 ? -W : W);
 
     uint32_t gstep = 0;      // rows consumed by this warp so far (stage ring position / mbarrier phase)
-    // global input link (warp 0 only): rows [popped, fetched) sit in inring or are on their way; rows < avail are in global memory
-    unsigned fetched = 0, avail = 0;
-    unsigned ring_fetched = 0, ring_popped = 0;   // rows ever requested into / popped from inring: slot and mbarrier phase
-    // the input FIFO currently read by warp 0: the chain's own closing / neighbour link, or (BAND, first unit of the band) the
-    // FIFO the neighbour rank writes into this rank's exchange buffer
-    const float* cur_gin = nullptr;
-    unsigned cur_depth = 1;
-    bool cur_ext = false;
-    // global output link (warp FW - 1 only): rows < pushed have been handed to the copy engine, rows < published are visible
-    unsigned cons_seen = 0;
-    bool pending_pub = false;
-    unsigned pending_q = 0;
-
-    // copy every row that is available and fits into inring: global slot -> shared slot, completion on the slot's mbarrier
-    // Ordering on the global links. The producer's rows reach L2 through the copy engine and it writes the counter only after
-    // cp.async.bulk.wait_group has reported them complete; the consumer reads the counter from L2 (relaxed.gpu bypasses L1) and
-    // only then lets the copy engine read the rows from L2, the copy being control-dependent on the counter's value. No
-    // gpu-scope acquire / release fence sits in the step: measured, a fence per step in the two boundary warps of every CTA
-    // is what the whole chain then waits for. fence.proxy.async orders the generic-proxy counter access against the
-    // async-proxy copies of the same thread.
-    // rows < the returned count have been pushed onto the current input FIFO (lane 0 reads, the value is broadcast by the caller)
-    auto read_avail = [&]() -> unsigned {
-        if constexpr (BAND) {
-            if (cur_ext) {   // epoch-tagged 64-bit counter in this rank's exchange buffer, written by the neighbour GPU
-                const unsigned long long v = ld_acquire_sys_u64(a.ext_prod_in + side * 16);
-                return (unsigned)(v >> 32) == a.epoch ? (unsigned)v : 0u;
-            }
-        }
-        return ld_relaxed_gpu(gprod_in);
-    };
-    auto fetch_rows = [&](unsigned popped) {
-        if (fetched < avail && fetched < popped + INR) fence_proxy_async_global();
-        while (fetched < avail && fetched < popped + INR) {
-            const unsigned sl = ring_fetched % INR;
-            mbar_expect_tx_elect(&inbars[sl], SLOT_BYTES);
-            bulk_g2s_elect(inring + (size_t)sl * SLOTF, cur_gin + (size_t)(fetched % cur_depth) * SLOTF, SLOT_BYTES, &inbars[sl]);
-            fetched++;
-            ring_fetched++;
-        }
-    };
-    // pop row q (it must be the next one): make sure it has been fetched, wait for it, free its global slot
-    auto pop_row = [&](unsigned q) -> const float* {
-        if (fetched <= q) {   // not even requested yet: the producer was late when we last looked
-            unsigned long long t0 = 0;
-            unsigned spins = 0;
-            while (avail <= q) {
-                unsigned v = 0;
-                if (lane == 0) v = read_avail();
-                avail = __shfl_sync(0xffffffffu, v, 0);
-                if (avail <= q) {
-                    __nanosleep(100);
-                    if constexpr (BAND) {
-                        if (cur_ext && (++spins & 63u) == 0) {   // another GPU feeds this FIFO: the wait is bounded
-                            int stop = 0;
-                            if (lane == 0) {
-                                if (t0 == 0) t0 = timer_ns();
-                                if (*reinterpret_cast<volatile unsigned*>(a.status) != 0u) stop = 1;
-                                else if (timer_ns() - t0 > a.timeout_ns) { atomicExch(a.status, 1u); stop = 1; }
-                            }
-                            if (__shfl_sync(0xffffffffu, stop, 0)) avail = q + 1;   // stop waiting; the row read is whatever is there
-                        }
-                    }
-                }
-            }
-            fetch_rows(q);
-        }
-        const unsigned k = ring_popped++;
-        mbar_wait(&inbars[k % INR], (k / INR) & 1u);
-        return inring + (size_t)(k % INR) * SLOTF;
-    };
-
-    // BAND: local rows are [0, Hb) of the volumes, image rows [row0, row0 + Hb); ug = the unit's index in the WHOLE image's chain
-    const int row0 = BAND ? a.row0 : 0;
-    const int Hloc = BAND ? a.Hb : H;       // rows of the volumes this launch works on
-    const int ubase = !BAND ? 0 : (a.sweep == 1 ? row0 : (a.sweep == 2 ? H - (row0 + Hloc) : 0));
+    unsigned ring_popped = 0;   // warp 0: rows ever popped from inring (slot and mbarrier phase)
 
     int round = 0;
     for (int u = w; u < a.U; u += n, round++) {
@@ -480,34 +595,26 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
         const long long pix0 = a.sweep == 0 ? (long long)u : (a.sweep == 1 ? (long long)u * W + (W - 1) : (long long)(Hloc - 1 - u) * W);
         const long long ipix0 = pix0 + (long long)row0 * W;
         const bool has_up = ug >= 1;
-        const bool diag_unit = a.sweep == 0 ? true : (ug <= H - 2);
-        // BAND: the band's first unit is fed by the neighbour rank's last unit, the band's last unit feeds the neighbour's first
-        const bool ext_in_unit = BAND && a.sweep != 0 && a.ext_in != nullptr && u == 0;
-        const bool ext_out_unit = BAND && a.sweep != 0 && a.ext_out != nullptr && u == a.U - 1;
+        const bool diag_unit = unit_pushes(u);
         // the producer of my input link works on unit u - 1: same round, or the previous one across the closing link
-        const unsigned qbase_in = ext_in_unit ? 0u : (unsigned)((w == 0 ? round - 1 : round)) * (unsigned)T;   // only used when has_up
+        const unsigned qbase_in = unit_ext_in(u) ? 0u : (unsigned)((w == 0 ? round - 1 : round)) * (unsigned)T;   // only used when has_up
         const unsigned qbase_out = (unsigned)round * (unsigned)T;
-        const bool gin_active = !in_local && has_up && (u >= 1 || ext_in_unit) && !(a.debug & 2);   // this unit pops T rows from a global FIFO
-        const bool gout_active = !out_local && diag_unit && !ext_out_unit && !(a.debug & 2);      // ... pushes T rows onto the chain's global link
-        if (gin_active) {
-            if (ext_in_unit) {
-                cur_gin = a.ext_in + (size_t)side * T * SLOTF; cur_depth = (unsigned)T; cur_ext = true;
-                fetched = 0; avail = 0;
-            } else {
-                if (cur_ext) { fetched = 0; avail = 0; }   // back to the chain's own link, whose numbering starts at 0
-                cur_gin = gin; cur_depth = depth_in; cur_ext = false;
-            }
-        }
+        const bool gin_active = !in_local && unit_pops(u);       // this unit pops T rows from inring (filled by the link warp)
+        const bool ext_tail_unit = out_local && unit_ext_out(u);  // BAND: the band's last unit on a warp other than the CTA's last
+        const bool gout_push = (!out_local || ext_tail_unit) && diag_unit;   // ... leaves T rows in its ring for the link warp
+        const bool gin_counts = gin_active && !unit_ext_in(u);   // pops are reported in the chain link's numbering
 
-        long long lpix = pix0;  // pixel of the next row to prefetch
+        const long long dstep = (long long)dpix * (long long)pitch;   // floats from one step's row to the next
+        long long loff = pix0 * (long long)pitch;                        // row to prefetch next
+        long long soff = loff;                                          // row of the current step
         auto issue_load = [&](uint32_t g) {
-            const size_t off = (size_t)lpix * pitch;
+            const long long off = loff;
             const int st = g % FSTAGES;
             float* dst = inbuf + (size_t)st * NIN * ROWF;
             mbar_expect_tx_elect(&bars[st], copy_bytes * NIN);
             bulk_g2s_elect(dst, Cv + off, copy_bytes, &bars[st]);
             if constexpr (READS) bulk_g2s_elect(dst + ROWF, Sv + off, copy_bytes, &bars[st]);
-            lpix += dpix;
+            loff += dstep;
         };
         {
             const int pre = min(FSTAGES, T);
@@ -528,20 +635,27 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
                 i_prev_up = has_up ? (int)img[ipix0 - W - 1] : 0;
             }
         }
+        // pop the next row of inring (warp 0): wait for the link warp's copy to land
+        auto pop_row = [&]() -> const float* {
+            const unsigned k = ring_popped++;
+            mbar_wait(&inbars[k % INR], (k / INR) & 1u);
+            return inring + (size_t)(k % INR) * SLOTF;
+        };
+        // ... and give the slot back once the row has been read in arithmetic (rows_done = pops of this unit so far)
+        auto popped_done = [&](unsigned rows_done) {
+            __syncwarp();
+            if (lane == 0) {
+                if (gin_counts) st_release_cta_smem(incons, qbase_in + rows_done);
+                st_release_cta_smem(inpop, ring_popped);
+            }
+        };
 
         float Lo[NPL];   // state of the path that runs along this unit
         float mo = 0.f;
 #pragma unroll
         for (int j = 0; j < NPL; j++) Lo[j] = 0.f;
 
-        long long pix = pix0;
-        for (int t = 0; t < T; t++, pix += dpix) {
-            // the counters of the global links are read at the top of the step and used further down: their L2 latency
-            // hides behind the own path
-            unsigned avail_new = 0, cons_new = 0;
-            if (gin_active && lane == 0) avail_new = read_avail();
-            if (gout_active && lane == 0) cons_new = ld_relaxed_gpu(gcons_out);
-
+        for (int t = 0; t < T; t++, soff += dstep) {
             const int st = gstep % FSTAGES;
             mbar_wait(&bars[st], (gstep / FSTAGES) & 1u);
             float cf[NPL], so[NPL];
@@ -560,7 +674,6 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
             const int yg = row0 + t;
             const bool own_active = a.sweep == 0 ? (yg <= H - 2) : (t <= T - 2);
             const bool diag_active = diag_unit && (a.sweep != 0 || yg <= H - 2);
-            const bool own_first = a.sweep == 0 ? (yg == 0) : (t == 0);            // first pixel of the own path: raw cost
             const bool diag_first = a.sweep == 0 ? (yg == 0 || u == 0) : (t == 0 || ug == 0);
             const bool from_entry = entry && t == 0;                                // continue the rank above's paths
 
@@ -575,14 +688,11 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
                 }
             }
             if (own_active) {
-                if (own_first) {
-#pragma unroll
-                    for (int j = 0; j < NPL; j++) Lo[j] = cf[j];
-                } else {
-                    const int dn = i_cur - i_prev_own;
-                    const bool full = (dn >= 0) && (dn <= a.threshold);
-                    dp_step<NPL>(Lo, cf, mo, full ? a.P1 : a.P1r, full ? a.P2 : a.P2r, lane);
-                }
+                // The first pixel of a path takes the raw cost. No branch for it: the state starts as Lo = 0, mo = 0, and with
+                // penalties >= 0 (checked on the host) the step gives min(0 + P1, 0, 0 + P2) - 0 = 0, i.e. Lo = cf + 0.
+                const int dn = i_cur - i_prev_own;
+                const bool full = (dn >= 0) && (dn <= a.threshold);
+                dp_step<NPL>(Lo, cf, mo, full ? a.P1 : a.P1r, full ? a.P2 : a.P2r, lane);
                 mo = warp_min_f32(tree_min_f32<NPL>(Lo));
             }
             if constexpr (READS) {
@@ -600,22 +710,30 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
             __syncwarp();
             if (t + FSTAGES < T) issue_load(gstep + FSTAGES);
 
-            // ---- global input link: request every row that has become available (they are used one or more steps later)
-            if (gin_active) {
-                avail = max(avail, __shfl_sync(0xffffffffu, avail_new, 0));
-                fetch_rows(qbase_in + (unsigned)max(t - 1, 0));
-            }
-            if (gout_active) cons_seen = max(cons_seen, __shfl_sync(0xffffffffu, cons_new, 0));
-
             // ---- the diagonal path: predecessor = step t - 1 of unit u - 1
             const float* grow = nullptr;
-            if (gin_active && t >= 1) grow = pop_row(qbase_in + (unsigned)(t - 1));   // popped whether it is needed or not (FIFO)
+            if (gin_active && t >= 1) grow = pop_row();   // popped whether it is needed or not (FIFO)
+            // the row this step hands to unit u + 1 (row qo of my output link); the last compute warp leaves one per step for
+            // the link warp, payload or not (FIFO). Its slot must have been read by the consumer (0xffffffff = reader gone).
+            const bool push = gout_push || (out_local && diag_active);
+            const unsigned qo = qbase_out + (unsigned)t;
+            if (ext_tail_unit) {   // the link warp counts this unit's rows from 0
+                if (push && t + 1 > RING) {
+                    if (lane == 0)
+                        while (ld_acquire_cta_smem(xcons) < (unsigned)(t + 1 - RING)) __nanosleep(20);
+                    __syncwarp();
+                }
+            } else if (push && qo + 1u > RING) {
+                if (lane == 0)
+                    while (ld_acquire_cta_smem(&consc[warp]) < qo + 1u - RING) __nanosleep(20);
+                __syncwarp();
+            }
             float md = 0.f;
             if (diag_active) {
                 float Ld[NPL];
-                if (diag_first || ((a.debug & 2) && !in_local)) {
+                if (diag_first) {   // first pixel of the path: zero state, the step below then yields the raw cost (see the own path)
 #pragma unroll
-                    for (int j = 0; j < NPL; j++) Ld[j] = cf[j];
+                    for (int j = 0; j < NPL; j++) Ld[j] = 0.f;
                 } else {
                     if (BAND && from_entry) {
                         const size_t slot = (size_t)side * W + (u - 1);
@@ -625,7 +743,7 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
                         md = __ldcg(src + ROWF);
                     } else if (in_local) {
                         const unsigned q = qbase_in + (unsigned)(t - 1);   // index of the row I need on my input link
-                        if (lane == 0 && !(a.debug & 1))
+                        if (lane == 0)
                             while (ld_acquire_cta_smem(&prodc[warp - 1]) < q + 1u) __nanosleep(20);
                         __syncwarp();
                         const float* src = lring_in + (size_t)(q % RING) * SLOTF;
@@ -635,6 +753,8 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
                         load_row<NPL>(grow, lane, Ld);
                         md = grow[ROWF];
                     }
+                }
+                {
                     const int dn = i_cur - i_prev_up;
                     const bool full = (dn >= 0) && (dn <= a.threshold);
                     dp_step<NPL>(Ld, cf, md, full ? a.P1 : a.P1r, full ? a.P2 : a.P2r, lane);
@@ -643,22 +763,7 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
 #pragma unroll
                 for (int j = 0; j < NPL; j++) so[j] = so[j] + Ld[j];
 
-                // hand the new state to unit u + 1 (row qo of my output link)
-                const unsigned qo = qbase_out + (unsigned)t;
-                if (out_local) {
-                    if (qo + 1u > RING && !(a.debug & 1)) {   // once its reader is done with the slot (0xffffffff = reader gone)
-                        if (lane == 0)
-                            while (ld_acquire_cta_smem(&consc[warp]) < qo + 1u - RING) __nanosleep(20);
-                        __syncwarp();
-                    }
-                    float* dst = ring + (size_t)(qo % RING) * SLOTF;
-                    store_row<NPL>(dst, lane, Ld);
-                    if (lane == 0) dst[ROWF] = md;
-                    __syncwarp();
-                    if (lane == 0) st_release_cta_smem(&prodc[warp], qo + 1u);
-                } else if (gout_active || ext_out_unit) {
-                    // stage the row in my (otherwise unused) ring; the copy that last read this slot was committed two steps ago
-                    // and is waited for below, before the row of the previous step is published
+                if (push) {
                     float* dst = ring + (size_t)(qo % RING) * SLOTF;
                     store_row<NPL>(dst, lane, Ld);
                     if (lane == 0) dst[ROWF] = md;
@@ -680,65 +785,16 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
                     }
                 }
             }
-            // my input link inside the CTA: everything up to the row of step t - 1 is consumed (whether it was needed or not)
+            if (push) {
+                __syncwarp();
+                if (lane == 0) st_release_cta_smem(&prodc[warp], qo + 1u);
+            }
+            // my input link: everything up to the row of step t - 1 is consumed (whether it was needed or not)
             if (in_local && has_up && t >= 1) {
                 __syncwarp();
                 if (lane == 0) st_release_cta_smem(&consc[warp - 1], qbase_in + (unsigned)t);
             }
-            if (gin_active && !ext_in_unit && t >= 1) {
-                // the row's copy out of global memory completed before pop_row returned and its shared copy has been read in
-                // arithmetic: both slots are free (the neighbour rank's FIFO is T deep and needs no such counter)
-                __syncwarp();
-                if (lane == 0) st_relaxed_gpu(gcons_in, qbase_in + (unsigned)t);
-            }
-            if (gout_active) {
-                // FIFO push of row qo = qbase_out + t, one bulk copy shared -> global per step (payload or not).
-                // 1. publish the previous row: its copy was committed a step ago
-                if (pending_pub) {
-                    bulk_wait_all_elect<1>();   // all but the latest group (the S row of the previous step) are complete
-                    fence_proxy_async_global();
-                    __syncwarp();
-                    if (lane == 0) st_relaxed_gpu(gprod_out, pending_q + 1u);
-                }
-                // 2. the global slot must have been popped by the reader
-                const unsigned qo = qbase_out + (unsigned)t;
-                if (qo + 1u > depth_out && !(a.debug & 1)) {
-                    while (cons_seen < qo + 1u - depth_out) {
-                        unsigned v = 0;
-                        if (lane == 0) v = ld_relaxed_gpu(gcons_out);
-                        cons_seen = __shfl_sync(0xffffffffu, v, 0);
-                        if (cons_seen < qo + 1u - depth_out) __nanosleep(100);
-                    }
-                }
-                // 3. shared -> global
-                fence_proxy_async_smem();
-                __syncwarp();
-                bulk_s2g_commit_elect(gout + (size_t)(qo % depth_out) * SLOTF, ring + (size_t)(qo % RING) * SLOTF, SLOT_BYTES);
-                pending_pub = true;
-                pending_q = qo;
-            }
-            if constexpr (BAND) {
-                if (ext_out_unit && diag_unit) {
-                    // the same push, into the neighbour rank's exchange buffer (T slots: no slot is reused inside a pair). A copy
-                    // over NVLink takes several steps to complete, and waiting for the previous one in every step would make this
-                    // unit (and with it the whole neighbour rank, which follows it in lock step) run at the link's latency: the
-                    // counter (it carries the pair's epoch) is written every XPUB steps for the rows whose copies were committed
-                    // at least XPUB steps ago. Groups committed since the copy of step t - XPUB: its S row, then a copy and an S
-                    // row per step = 2 * XPUB - 1.
-                    if (t >= XPUB && (t % XPUB) == 0) {
-                        bulk_wait_all_elect<2 * XPUB - 1>();
-                        fence_proxy_async_global();
-                        __syncwarp();
-                        if (lane == 0)
-                            st_release_sys_u64(a.ext_prod_out + side * 16, ((unsigned long long)a.epoch << 32) | (unsigned long long)(t - XPUB + 1));
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    bulk_s2g_commit_elect(a.ext_out + ((size_t)side * T + t) * SLOTF, ring + (size_t)((qbase_out + (unsigned)t) % RING) * SLOTF, SLOT_BYTES);
-                    pending_pub = true;
-                    pending_q = (unsigned)t;
-                }
-            }
+            if (gin_active && t >= 1) popped_done((unsigned)t);
 
             // ---- the "up" path adds the raw cost on rows >= 1 (its penalties are never written, sgm.cu); sweep 0 only
             if constexpr (!READS) {
@@ -748,14 +804,13 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
                 }
             }
 
-            // ---- S row out: staged, one bulk store per row. The store of the previous step has left the staging row (the
-            // hand-over copy committed a moment ago may still be reading ITS row).
-            if (gout_active || (BAND && ext_out_unit && diag_unit)) bulk_wait_read_elect<1>(); else bulk_wait_read_elect<0>();
+            // ---- S row out: staged, one bulk store per row. The store of the previous step has left the staging row.
+            bulk_wait_read_elect<0>();
             __syncwarp();
             store_row<NPL>(outbuf, lane, so);
             fence_proxy_async_smem();
             __syncwarp();
-            bulk_s2g_commit_elect(Sv + (size_t)pix * pitch, outbuf, copy_bytes);
+            bulk_s2g_commit_elect(Sv + soff, outbuf, copy_bytes);
 
             i_prev_own = i_cur;
             i_prev_up = i_upcur;
@@ -767,40 +822,13 @@ __global__ void __launch_bounds__(ChainSmem<NPL, READS>::FW * 32) sgm_chain_kern
             if (lane == 0) st_release_cta_smem(&consc[warp - 1], qbase_in + (unsigned)T);
         }
         if (gin_active) {           // FIFO: pop the row of the producer's last step too
-            pop_row(qbase_in + (unsigned)(T - 1));
-            __syncwarp();
-            if (lane == 0 && !ext_in_unit) st_relaxed_gpu(gcons_in, qbase_in + (unsigned)T);
-        }
-        if constexpr (BAND) {
-            if (ext_out_unit && diag_unit && pending_pub) {   // publish the last row of the band's last unit
-                bulk_wait_all_elect<0>();
-                fence_proxy_async_global();
-                __syncwarp();
-                if (lane == 0)
-                    st_release_sys_u64(a.ext_prod_out + side * 16, ((unsigned long long)a.epoch << 32) | (unsigned long long)T);
-                pending_pub = false;
-            }
-        }
-        if (gout_active && pending_pub) {   // publish the last row of the unit
-            bulk_wait_all_elect<0>();
-            fence_proxy_async_global();
-            __syncwarp();
-            if (lane == 0) st_relaxed_gpu(gprod_out, pending_q + 1u);
-            pending_pub = false;
+            pop_row();
+            popped_done((unsigned)T);
         }
     }
     // no more units for this warp: whatever still arrives on its input link is not needed
     __syncwarp();
-    if (lane == 0) {
-        if (in_local)
-            st_release_cta_smem(&consc[warp - 1], 0xffffffffu);
-        else
-            st_relaxed_gpu(gcons_in, 0xffffffffu);
-    }
-    // rows requested from the global link but never popped must have landed before the CTA's shared memory goes away
-    if (!in_local) {
-        for (unsigned k = ring_popped; k < ring_fetched; k++) mbar_wait(&inbars[k % INR], (k / INR) & 1u);
-    }
+    if (lane == 0 && in_local) st_release_cta_smem(&consc[warp - 1], 0xffffffffu);
     asm volatile(
         "{\n\t"
         ".reg .pred q;\n\t"
@@ -986,7 +1014,7 @@ template <int NPL, bool READS, bool BAND>
 int chain_rounds(int units, int sides, int* rounds) {
     constexpr int FW = ChainSmem<NPL, READS>::FW;
     int per_sm = 0;
-    if (int e = kernel_setup<sgm_chain_kernel<NPL, READS, BAND>>(FW * 32, ChainSmem<NPL, READS>::BYTES, &per_sm)) return e;
+    if (int e = kernel_setup<sgm_chain_kernel<NPL, READS, BAND>>((FW + 1) * 32, ChainSmem<NPL, READS>::BYTES, &per_sm)) return e;
     int ctas = (sm_count() * per_sm) / sides;
     if (ctas > MAX_CHAIN_CTAS) ctas = MAX_CHAIN_CTAS;
     *rounds = ctas >= 1 ? ceil_div(units, ctas * FW) : (1 << 20);
@@ -999,7 +1027,7 @@ int launch_chain(FusedArgs a, cudaStream_t stream, int sides = 2) {
     constexpr int FW = ChainSmem<NPL, READS>::FW;
     const size_t smem = ChainSmem<NPL, READS>::BYTES;
     int per_sm = 0;
-    if (int e = kernel_setup<sgm_chain_kernel<NPL, READS, BAND>>(FW * 32, smem, &per_sm)) return e;
+    if (int e = kernel_setup<sgm_chain_kernel<NPL, READS, BAND>>((FW + 1) * 32, smem, &per_sm)) return e;
     MCCNN_REQUIRE(per_sm >= 1, MCCNN_EINVAL, "sgm_chain_kernel<%d>: does not fit on an SM (smem %zu)", NPL, smem);
     int ctas = (sm_count() * per_sm) / sides;   // one chain per side; every CTA must be resident (cooperative launch)
     if (ctas > MAX_CHAIN_CTAS) ctas = MAX_CHAIN_CTAS;
@@ -1015,7 +1043,7 @@ int launch_chain(FusedArgs a, cudaStream_t stream, int sides = 2) {
     ctas = ceil_div(per_round, fw);
     a.ctas = ctas;
     void* params[] = {&a};
-    MCCNN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sgm_chain_kernel<NPL, READS, BAND>), dim3(sides * ctas), dim3(fw * 32), params,
+    MCCNN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sgm_chain_kernel<NPL, READS, BAND>), dim3(sides * ctas), dim3((fw + 1) * 32), params,
                                            smem, stream));
     return 0;
 }
@@ -1039,8 +1067,6 @@ template <int NPL>
 int run_fused_npl(FusedArgs a, int keep_volumes, cudaStream_t stream, unsigned* flags) {
     const char* env_mask = getenv("MCCNN_FUSED_SWEEPS");
     const int mask = env_mask ? atoi(env_mask) : 15;
-    const char* env_dbg = getenv("MCCNN_FUSED_DEBUG");
-    a.debug = env_dbg ? atoi(env_dbg) : 0;
     for (int sweep = 0; sweep < 3; sweep++) {
         if (!(mask & (1 << sweep))) continue;
         a.sweep = sweep;
