@@ -31,7 +31,7 @@
 namespace mccnn {
 namespace {
 
-constexpr int FW_MAX = 11;  // compute warps per CTA of the chain kernel (10 for rows of 1024 floats: shared memory); + 1 link warp
+constexpr int FW_MAX = 10;  // compute warps per CTA of the chain kernel (9 for rows of 1024 floats: shared memory); + 2 link warps
 constexpr int RING = 2;     // hand-over slots between warps of one CTA (shared memory)
 constexpr int GRING = 8;    // hand-over slots between neighbouring CTAs (global memory)
 constexpr int XPUB = 4;    // a band's last unit publishes its rows to the neighbour rank every XPUB steps, XPUB steps late
@@ -59,6 +59,7 @@ struct FusedArgs {
     unsigned* gflags; // [side][ctas][2][FLAG_STRIDE]: produced / consumed counters of the link leaving CTA c
     int slot_floats;  // 32 * NPL + 4
     unsigned* counter;  // sweep 3: scanline counter
+    int strict;         // MCCNN_FUSED_STRICT=1: gpu-scope release on the producer side of the global links as well (see the link warps)
     // ---- row-band sharding (BAND kernels; one pair split over several GPUs, mccnn_sgm_fused_sharded): this launch owns image rows
     // [row0, row0 + Hb) of H; the volumes and maps it is given hold only those rows, the u8 images are whole. What crosses a
     // band boundary travels through the neighbours' exchange buffers (peer memory): see the layout in fused_xchg_layout().
@@ -322,30 +323,32 @@ __device__ __forceinline__ float warp_wta(const float (&so)[NPL], int lane, int 
 // consumption; the first sweep (cost only) has two stages.
 template <int NPL, bool READS>
 struct ChainSmem {
-    static constexpr int FW = NPL > 25 ? 10 : FW_MAX;   // compute warps (the block has one more warp)
+    static constexpr int FW = NPL > 25 ? 9 : FW_MAX;   // compute warps (the block has two more warps)
     static constexpr int STG = READS ? 1 : 2;
     static constexpr int NIN = READS ? 2 : 1;
     static constexpr int ROWF = 32 * NPL;
     static constexpr int SLOTF = ROWF + 4;
-    static constexpr int PER_WARP = ROWF * (STG * NIN + 1) + RING * SLOTF;
+    static constexpr int RG = RING;   // hand-over slots between the warps of a CTA (3 measured: no gain, c4 63.3 vs 64.0 ms)
+    static constexpr int PER_WARP = ROWF * (STG * NIN + 1) + RG * SLOTF;
     static constexpr size_t BYTES = (size_t)FW * PER_WARP * 4 + (size_t)INR * SLOTF * 4 + (size_t)(2 * FW + 4) * 4 + (size_t)(FW * STG + INR) * 8;
 };
 
 template <int NPL, bool READS, bool BAND>
-__global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 1) * 32) sgm_chain_kernel(const FusedArgs a) {
+__global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 2) * 32) sgm_chain_kernel(const FusedArgs a) {
     if constexpr (BAND) {
         if (a.go != nullptr && *reinterpret_cast<const volatile int*>(a.go) == 0) return;   // some rank will not launch: nobody waits
     }
     using L = ChainSmem<NPL, READS>;
     constexpr int FW = L::FW;
     constexpr int FSTAGES = L::STG;   // (shadows the file-level default)
+    constexpr int RING = L::RG;       // (likewise)
     constexpr int ROWF = L::ROWF, SLOTF = L::SLOTF;
     constexpr int NIN = L::NIN;
     constexpr int PER_WARP = L::PER_WARP;
     constexpr uint32_t SLOT_BYTES = SLOTF * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int fw = (int)(blockDim.x >> 5) - 1;   // compute warps of this launch (<= FW; the shared-memory layout is FW's); warp fw = link warp
+    const int fw = (int)(blockDim.x >> 5) - 2;   // compute warps of this launch (<= FW; the shared-memory layout is FW's); warps fw, fw + 1 = link warps
     float* smem_f = reinterpret_cast<float*>(smem_raw);
     float* wbase = smem_f + (size_t)(warp < fw ? warp : 0) * PER_WARP;
     float* inbuf = wbase;                            // [FSTAGES][NIN][ROWF]
@@ -404,8 +407,9 @@ __global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 1) * 32) sgm_chai
     auto unit_pushes = [&](int u) -> bool { return a.sweep == 0 ? true : (ubase + u <= H - 2); };       // unit of a warp fw - 1
 
     // ================================================================================================ the link warp
-    if (warp == fw) {
+    if (warp >= fw) {
         if (lane != 0) return;
+        const bool do_out = warp == fw, do_in = warp == fw + 1;   // one warp per direction: a gpu-scope release / acquire per row each
         const float* gin = link_base(lin);
         float* gout = link_base(lout);
         unsigned* gprod_in = a.gflags + ((size_t)(side * a.ctas + lin) * 2 + 0) * FLAG_STRIDE;
@@ -417,10 +421,18 @@ __global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 1) * 32) sgm_chai
         int osrc = fw - 1;
         bool ext_tail = BAND && a.sweep != 0 && a.ext_out != nullptr && ((a.U - 1) % n) / fw == cta && ((a.U - 1) % n) % fw != fw - 1 &&
                         unit_pushes(a.U - 1);
-        // Ordering on the global links. The rows reach L2 through the copy engine and the counter is written only after
-        // cp.async.bulk.wait_group has reported them complete; the consumer side reads the counter from L2 (relaxed.gpu bypasses
-        // L1) and only then lets the copy engine read the rows from L2, the copy being control-dependent on the counter's value.
-        // fence.proxy.async orders the generic-proxy counter access against the async-proxy copies of the same thread.
+        // Ordering on the global links. The rows reach L2 through the copy engine. Producer side: cp.async.bulk.wait_group (the
+        // copy is complete), fence.proxy.async.global, counter store. Consumer side: counter load, fence.acq_rel.gpu,
+        // fence.proxy.async.global, and only then the copy engine reads the rows.
+        // The consumer's gpu-scope fence is NOT optional. Measured at c4 (tools/check_race_c4.py): announcing a row right after
+        // wait_group and fetching it without that fence corrupts thousands of rows per sweep (the global slots are reused every
+        // GRING rows, and the reading SM's copy engine can still be served the slot's previous contents); announcing it a step
+        // later (what round 1 / 2 did from the compute warps, never observed to fail) only makes that window improbable. With
+        // the fence: 0 differing rows in 24 / 24 repeated c4 sweeps, and the announcement no longer has to lag.
+        // A gpu-scope RELEASE on the producer side as well (what the PTX memory model asks for on paper: completion of a bulk
+        // copy is defined for the issuing thread only) costs 62.5 -> 73 ms at c4 -- a MEMBAR.GPU under 6 TB/s of traffic takes
+        // microseconds -- and changed nothing observable; it is available as MCCNN_FUSED_STRICT=1 and off by default.
+        // None of this is in the step of a compute warp: one link warp per direction.
         // ---- input side: the units of warp 0
         int iu = cta * fw, iround = 0;
         unsigned it = 0;            // rows of the current unit requested so far
@@ -433,7 +445,9 @@ __global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 1) * 32) sgm_chai
         int ou = cta * fw + fw - 1, oround = 0;
         unsigned ot = 0;            // rows of the current unit forwarded so far
         unsigned cons_seen = 0;     // rows the next CTA has popped from the chain link
-        bool unpublished = false;   // the copy of the latest row has been committed but the row is not announced yet
+        bool unpublished = false;   // copies have been committed whose rows are not announced yet
+        unsigned idle = 0;          // polls without progress
+        auto publish = [&](unsigned v) { if (a.strict) st_release_gpu(gprod_out, v); else st_relaxed_gpu(gprod_out, v); };
         bool in_closed = false;
         while (ou < a.U && !unit_pushes(ou)) { ou += n; oround++; }
         auto next_out_unit = [&]() {
@@ -445,6 +459,8 @@ __global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 1) * 32) sgm_chai
         };
         if (ou >= a.U && ext_tail) { ou -= n; oround--; next_out_unit(); }
 
+        if (!do_in) iu = a.U;
+        if (!do_out) ou = a.U;
         while (iu < a.U || ou < a.U) {
             bool progress = false;
             if (ou < a.U) {
@@ -455,6 +471,7 @@ __global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 1) * 32) sgm_chai
                     if (!slot_free) {
                         cons_seen = ld_relaxed_gpu(gcons_out);
                         slot_free = cons_seen >= qo + 1u - depth_out;
+                        if (slot_free && a.strict) fence_acq_rel_gpu();   // the consumer's reads of the slot happened before what we write now
                     }
                     if (slot_free) {
                         fence_proxy_async_smem();
@@ -472,12 +489,12 @@ __global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 1) * 32) sgm_chai
                         const bool unit_done = ot == (unsigned)T;
                         // Publication runs behind the copies: a row is announced once its copy is COMPLETE, and waiting for the
                         // copy just committed would put the write latency of L2 (or of NVLink) into every step.
-                        unpublished = !unit_done;
-                        if (!ext) {
-                            if (unit_done) bulk_wait_all<0>(); else bulk_wait_all<1>();
+                        if (!ext) {   // the next CTA: announce the row as soon as its copy is complete
+                            bulk_wait_all<0>();
                             fence_proxy_async_global();
-                            st_relaxed_gpu(gprod_out, unit_done ? qo + 1u : qo);
+                            publish(qo + 1u);
                         } else if constexpr (BAND) {
+                            unpublished = !unit_done;
                             // the neighbour GPU: the counter carries the pair's epoch; every XPUB rows, XPUB rows late
                             if (unit_done) {
                                 bulk_wait_all<0>();
@@ -501,8 +518,8 @@ __global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 1) * 32) sgm_chai
                 const bool ext = unit_ext_in(iu);
                 if (!ext) {   // tell the producer which slots of the chain link are free again
                     const unsigned cv = ld_acquire_cta_smem(incons);
-                    if (cv != cons_pub) {
-                        st_relaxed_gpu(gcons_in, cv);
+                    if (cv - cons_pub >= (unsigned)(GRING / 2)) {   // (a release per row is not needed: the ring is GRING deep)
+                        if (a.strict) st_release_gpu(gcons_in, cv); else st_relaxed_gpu(gcons_in, cv);
                         cons_pub = cv;
                     }
                 }
@@ -527,6 +544,7 @@ __global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 1) * 32) sgm_chai
                         } else {
                             avail = ld_relaxed_gpu(gprod_in);
                         }
+                        if (avail > q) fence_acq_rel_gpu();   // acquire: the rows below `avail` are complete in L2
                     }
                     if (avail > q) {
                         const unsigned sl = in_req % INR;
@@ -548,25 +566,27 @@ __global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 1) * 32) sgm_chai
                     }
                 }
             }
-            if (iu >= a.U && !in_closed) {
+            if (do_in && iu >= a.U && !in_closed) {
                 // no more units for warp 0: whatever still arrives on the input link is not needed (its rows are all in shared
                 // memory); the producer must not wait for free slots any more
                 st_relaxed_gpu(gcons_in, 0xffffffffu);
                 in_closed = true;
             }
-            if (!progress) {
-                if (unpublished && ou < a.U) {   // nothing else to do: announce the latest row now instead of with the next one
+            if (progress) {
+                idle = 0;
+            } else {
+                if (BAND && unpublished && ou < a.U && ++idle >= 8u) {   // neighbour GPU: nothing else to do, announce the latest rows now
                     bulk_wait_all<0>();
                     fence_proxy_async_global();
-                    if (!unit_ext_out(ou)) st_relaxed_gpu(gprod_out, (unsigned)oround * (unsigned)T + ot);
-                    else if constexpr (BAND) st_release_sys_u64(a.ext_prod_out + side * 16, ((unsigned long long)a.epoch << 32) | (unsigned long long)ot);
+                    st_release_sys_u64(a.ext_prod_out + side * 16, ((unsigned long long)a.epoch << 32) | (unsigned long long)ot);
                     unpublished = false;
+                    idle = 0;
                 } else {
                     __nanosleep(40);
                 }
             }
         }
-        if (!in_closed) st_relaxed_gpu(gcons_in, 0xffffffffu);
+        if (do_in && !in_closed) st_relaxed_gpu(gcons_in, 0xffffffffu);
         bulk_wait_all<0>();
         return;
     }
@@ -767,6 +787,9 @@ __global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 1) * 32) sgm_chai
                     float* dst = ring + (size_t)(qo % RING) * SLOTF;
                     store_row<NPL>(dst, lane, Ld);
                     if (lane == 0) dst[ROWF] = md;
+                    // the link warp hands this slot to the copy engine: the WRITING lanes order their generic-proxy stores
+                    // before the async proxy's read (a fence on the reading side alone does not)
+                    if (gout_push) fence_proxy_async_smem();
                 }
                 if constexpr (BAND) {
                     // sweep 0, last row of the band: the rank below continues both paths from here (peer memory)
@@ -1009,12 +1032,17 @@ FusedLayout fused_layout(int H, int W, int D) {
     return l;
 }
 
+inline int fused_strict() {
+    static const int v = [] { const char* e = getenv("MCCNN_FUSED_STRICT"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 // rounds a chain of `units` needs when `sides` chains share the GPU
 template <int NPL, bool READS, bool BAND>
 int chain_rounds(int units, int sides, int* rounds) {
     constexpr int FW = ChainSmem<NPL, READS>::FW;
     int per_sm = 0;
-    if (int e = kernel_setup<sgm_chain_kernel<NPL, READS, BAND>>((FW + 1) * 32, ChainSmem<NPL, READS>::BYTES, &per_sm)) return e;
+    if (int e = kernel_setup<sgm_chain_kernel<NPL, READS, BAND>>((FW + 2) * 32, ChainSmem<NPL, READS>::BYTES, &per_sm)) return e;
     int ctas = (sm_count() * per_sm) / sides;
     if (ctas > MAX_CHAIN_CTAS) ctas = MAX_CHAIN_CTAS;
     *rounds = ctas >= 1 ? ceil_div(units, ctas * FW) : (1 << 20);
@@ -1027,7 +1055,7 @@ int launch_chain(FusedArgs a, cudaStream_t stream, int sides = 2) {
     constexpr int FW = ChainSmem<NPL, READS>::FW;
     const size_t smem = ChainSmem<NPL, READS>::BYTES;
     int per_sm = 0;
-    if (int e = kernel_setup<sgm_chain_kernel<NPL, READS, BAND>>((FW + 1) * 32, smem, &per_sm)) return e;
+    if (int e = kernel_setup<sgm_chain_kernel<NPL, READS, BAND>>((FW + 2) * 32, smem, &per_sm)) return e;
     MCCNN_REQUIRE(per_sm >= 1, MCCNN_EINVAL, "sgm_chain_kernel<%d>: does not fit on an SM (smem %zu)", NPL, smem);
     int ctas = (sm_count() * per_sm) / sides;   // one chain per side; every CTA must be resident (cooperative launch)
     if (ctas > MAX_CHAIN_CTAS) ctas = MAX_CHAIN_CTAS;
@@ -1043,7 +1071,7 @@ int launch_chain(FusedArgs a, cudaStream_t stream, int sides = 2) {
     ctas = ceil_div(per_round, fw);
     a.ctas = ctas;
     void* params[] = {&a};
-    MCCNN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sgm_chain_kernel<NPL, READS, BAND>), dim3(sides * ctas), dim3((fw + 1) * 32), params,
+    MCCNN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sgm_chain_kernel<NPL, READS, BAND>), dim3(sides * ctas), dim3((fw + 2) * 32), params,
                                            smem, stream));
     return 0;
 }
@@ -1067,6 +1095,7 @@ template <int NPL>
 int run_fused_npl(FusedArgs a, int keep_volumes, cudaStream_t stream, unsigned* flags) {
     const char* env_mask = getenv("MCCNN_FUSED_SWEEPS");
     const int mask = env_mask ? atoi(env_mask) : 15;
+    a.strict = fused_strict();
     for (int sweep = 0; sweep < 3; sweep++) {
         if (!(mask & (1 << sweep))) continue;
         a.sweep = sweep;
@@ -1211,6 +1240,7 @@ int run_sgm_fused_band(const float* CLb, const float* CRb, const uint8_t* imageL
     a.counter = reinterpret_cast<unsigned*>(ws + l.counter);
     a.row0 = sh->row0; a.Hb = sh->rows; a.epoch = sh->epoch;
     a.go = sh->go_flag;
+    a.strict = fused_strict();
     a.status = reinterpret_cast<unsigned*>(base) + 32;
     a.timeout_ns = (unsigned long long)(sh->timeout_ms ? sh->timeout_ms : 2000u) * 1000000ull;
     unsigned* flags = reinterpret_cast<unsigned*>(ws + l.flags);
