@@ -17,8 +17,7 @@ E = 2.0 * H * W * D
 for _ in range(2):   # allocations, module load
     eng.sgm(CL, CR, il, ir, D, keep_volumes=False, mode="fused")
 torch.cuda.synchronize()
-for dbg in [int(v) for v in os.environ.get('DBG', '0,1,3').split(',')]:
-    os.environ["MCCNN_FUSED_DEBUG"] = str(dbg)
+for dbg in (0,):
     for mask, name, bpe in ((1, "sweep0 down+downright", 8), (2, "sweep1 left+downleft", 12), (4, "sweep2 right+upright", 12), (8, "sweep3 upleft+wta", 8), (15, "all", 40)):
         os.environ["MCCNN_FUSED_SWEEPS"] = str(mask)
         for _ in range(2):
