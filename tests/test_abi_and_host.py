@@ -73,6 +73,11 @@ def test_argument_errors_without_gpu(lib):
     assert lib.mccnn_sgm(1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, big,
                          8, 8, 16, C.byref(p), 7, 0, None) == -1
     assert b"mode" in lib.mccnn_last_error()
+    neg = _lib.default_sgm_params()
+    neg.P2_red = -1.0   # the fused mode starts a path from the zero state, which needs penalties >= 0
+    assert lib.mccnn_sgm(1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, big,
+                         8, 8, 16, C.byref(neg), 1, 0, None) == -1
+    assert b"penalties" in lib.mccnn_last_error()
     assert lib.mccnn_sgm(1 << 20, (1 << 20) + 4, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, big,
                          8, 8, 16, C.byref(p), 0, 0, None) == -2
     assert lib.mccnn_disparity_pipeline(1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 1 << 20, 16,
