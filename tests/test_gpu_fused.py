@@ -274,3 +274,30 @@ def test_fused_sgm_repeatable_at_full_size(eng, cfg):
     torch.cuda.empty_cache()
     _, _, el, er = eng.sgm(CL, CR, il, ir, D, keep_volumes=False, mode="exact")
     assert int((el != dl).sum()) <= 64 and int((er != dr).sum()) <= 64   # (measured: 8 and 6 of 5.7 M at c4; a lost row costs hundreds)
+
+
+def test_fused_pairs_in_flight_equal_sequential(eng):
+    """Several KITTI-shaped pairs in flight on their own streams (match.StreamedMatcher, fused mode): the chain kernels of
+    different pairs share the SMs and the L2, every pair has its own rings and counters. Every map must equal the one the same
+    pair gives alone, pass after pass."""
+    from scenedepthestimation_b200 import match as mt, synthetic as syn
+
+    W, H, D = syn.CONFIGS["c5"]
+    weights = syn.glorot_weights()
+    packed = eng.pack_weights(weights, 5)
+    pairs = [syn.textured_pair(H, W, D, 300 + k)[:2] for k in range(7)]
+    alone = []
+    for il, ir in pairs:
+        dl, _ = eng.match_pair(dev(il), dev(ir), packed, D, 5, mode="fused")
+        alone.append(eng.encode_u8(dl, 1).cpu().numpy())
+    m = mt.StreamedMatcher(H, W, weights, ndisp=D, scale=1, depth=3, mode="fused")
+    for rep in range(3):
+        got = []
+        for k, (il, ir) in enumerate(pairs):
+            r = m.submit(il, ir, k)
+            if r is not None:
+                got.append(r)
+        got += m.drain()
+        assert [t for t, _ in got] == list(range(len(pairs)))
+        for (t, img), ref in zip(got, alone):
+            assert np.array_equal(img, ref), (rep, t, int((img != ref).sum()))
