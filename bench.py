@@ -437,7 +437,7 @@ def main():
                      "cost_volume_hbm_frac": (2 * evals * 4 + 2 * H * W * 256) / (float(fstage[1]) * 1e-3) / 1e9 / peak,
                      "vs_exact_on_this_pair": {"left_map_pixels_differ": int((fl_ != ref_l).sum()), "right_wta_pixels_differ": int((fr_ != ref_r).sum()),
                                                "pixels": H * W, "left_max_abs_diff": float((fl_ - ref_l).abs().max())},
-                     "census": "profiles/r02_fused_census.json"}
+                     "census": "profiles/r02p_fused_census.json"}
         except Exception as exc:  # the headline line must be printed whatever happens here
             fused = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
