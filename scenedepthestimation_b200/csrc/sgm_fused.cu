@@ -22,9 +22,14 @@
 // wait when its neighbour is late. The state (one row of D floats + its minimum) travels through a 2-slot ring in shared
 // memory between warps of a CTA, through an 8-slot ring in global memory (L2-resident) between the last warp of a CTA and
 // the first warp of the next one, and through a T-slot global buffer from the last warp of the chain to the first one,
-// which by then works on the next round of units (unit u -> warp u mod n). The grid is launched cooperatively: every warp
-// of a chain must be resident.
+// which by then works on the next round of units (unit u -> warp u mod n). The global rings are served by two LINK WARPS
+// per CTA (one per direction: prefetch of announced rows into a shared-memory ring for warp 0, forwarding of the last compute
+// warp's ring), so every compute warp sees shared-memory rings on both sides and runs the same step. The grid is launched
+// cooperatively: every warp of a chain must be resident.
 // Cost and S rows stream through shared memory with 1-D bulk copies + mbarriers, as in sgm.cu.
+// BAND kernels (mccnn_sgm_fused_sharded): the same sweeps on a band of image rows, the neighbour GPUs' bands reached through
+// peer memory (entry / exit states per column in sweep 0, a row FIFO per step in sweeps 1 and 2, a state per scanline in
+// sweep 3); value-identical to the unsharded sweeps.
 #include "common.cuh"
 #include <cstdlib>
 
