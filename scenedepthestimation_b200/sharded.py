@@ -145,6 +145,17 @@ def emulate_bands(CL, CR, il, ir, D, world: int, epoch: int = 1):
     return SL, SR, dl, dr
 
 
+def gather_bands(send, recv, bands, left_full, right_full, group=None):
+    """One all_gather of every rank's (padded) [left | right] band `send` [2, max_rows, W] into `recv` [world, 2, max_rows, W],
+    then the valid rows of each band are laid out as whole maps. Bands may differ by one row, hence the padding."""
+    import torch.distributed as dist
+
+    dist.all_gather_into_tensor(recv.view(-1, *send.shape[1:]), send, group=group)   # (concatenated along dim 0: any backend)
+    for r, (r0, n) in enumerate(bands):
+        left_full[r0:r0 + n].copy_(recv[r, 0, :n])
+        right_full[r0:r0 + n].copy_(recv[r, 1, :n])
+
+
 class ShardedMatcher:
     """One pair per call, split by rows over the ranks of `group` (one process per GPU, NCCL)."""
 
@@ -193,11 +204,7 @@ class ShardedMatcher:
         self.f_recv = torch.empty((self.world, 2, self.max_rows, W), dtype=torch.float32, device="cuda")
 
     def _gather(self, send, recv, left_full, right_full):
-        """One all_gather of the (padded) [left | right] bands, then the valid rows are laid out as whole maps."""
-        self.dist.all_gather_into_tensor(recv, send, group=self.group)
-        for r, (r0, n) in enumerate(self.bands):
-            left_full[r0:r0 + n].copy_(recv[r, 0, :n])
-            right_full[r0:r0 + n].copy_(recv[r, 1, :n])
+        gather_bands(send, recv, self.bands, left_full, right_full, self.group)
 
     def _cost_volume(self, fl, fr):
         if self.tc_ws is None:
