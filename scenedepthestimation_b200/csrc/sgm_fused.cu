@@ -64,7 +64,7 @@ struct FusedArgs {
     unsigned* gflags; // [side][ctas][2][FLAG_STRIDE]: produced / consumed counters of the link leaving CTA c
     int slot_floats;  // 32 * NPL + 4
     unsigned* counter;  // sweep 3: scanline counter
-    int strict;         // MCCNN_FUSED_STRICT=1: gpu-scope release on the producer side of the global links as well (see the link warps)
+    int strict;         // 1 (default): gpu-scope release on the producer side of the global links; MCCNN_FUSED_STRICT=0 drops it (measurement only)
     // ---- row-band sharding (BAND kernels; one pair split over several GPUs, mccnn_sgm_fused_sharded): this launch owns image rows
     // [row0, row0 + Hb) of H; the volumes and maps it is given hold only those rows, the u8 images are whole. What crosses a
     // band boundary travels through the neighbours' exchange buffers (peer memory): see the layout in fused_xchg_layout().
@@ -434,9 +434,11 @@ __global__ void __launch_bounds__((ChainSmem<NPL, READS>::FW + 2) * 32) sgm_chai
         // GRING rows, and the reading SM's copy engine can still be served the slot's previous contents); announcing it a step
         // later (what round 1 / 2 did from the compute warps, never observed to fail) only makes that window improbable. With
         // the fence: 0 differing rows in 24 / 24 repeated c4 sweeps, and the announcement no longer has to lag.
-        // A gpu-scope RELEASE on the producer side as well (what the PTX memory model asks for on paper: completion of a bulk
-        // copy is defined for the issuing thread only) costs 62.5 -> 73 ms at c4 -- a MEMBAR.GPU under 6 TB/s of traffic takes
-        // microseconds -- and changed nothing observable; it is available as MCCNN_FUSED_STRICT=1 and off by default.
+        // The gpu-scope RELEASE on the producer side (the counter store is st.release.gpu; completion of a bulk copy is defined
+        // for the issuing thread only) is not optional either: without it a single pair at c4 came out right in 72 / 72 repeated
+        // sweeps, but with several pairs in flight on their own streams (test_fused_pairs_in_flight_equal_sequential) two runs
+        // in three lost a few rows; with it, none. It costs 62.5 -> 72.5 ms of SGM at c4 (a MEMBAR.GPU under 6 TB/s of traffic
+        // takes microseconds). MCCNN_FUSED_STRICT=0 drops it, for measurements only.
         // None of this is in the step of a compute warp: one link warp per direction.
         // ---- input side: the units of warp 0
         int iu = cta * fw, iround = 0;
@@ -1038,7 +1040,7 @@ FusedLayout fused_layout(int H, int W, int D) {
 }
 
 inline int fused_strict() {
-    static const int v = [] { const char* e = getenv("MCCNN_FUSED_STRICT"); return e ? atoi(e) : 0; }();
+    static const int v = [] { const char* e = getenv("MCCNN_FUSED_STRICT"); return e ? atoi(e) : 1; }();
     return v;
 }
 

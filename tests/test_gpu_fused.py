@@ -312,19 +312,3 @@ def test_fused_pairs_in_flight_equal_sequential(eng):
         assert [t for t, _ in got] == list(range(len(pairs)))
         for (t, img), ref in zip(got, alone):
             assert np.array_equal(img, ref), (rep, t, int((img != ref).sum()))
-
-
-def test_fused_strict_switch_same_results():
-    """MCCNN_FUSED_STRICT=1 (gpu-scope release on the producer side of every CTA-to-CTA hand-over as well) must give the same
-    values: the oracle comparisons and the band tests are rerun under it in a child process (the switch is read once)."""
-    import os
-    import subprocess
-    import sys
-
-    if not torch.cuda.is_available():
-        pytest.skip("no CUDA device")
-    env = dict(os.environ, MCCNN_FUSED_STRICT="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
-                        "equals_fused_oracle and not full_size or bands_equal"], env=env, capture_output=True, text=True, timeout=900,
-                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    assert r.returncode == 0 and f"{len(SHAPES) + len(BANDS)} passed" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
