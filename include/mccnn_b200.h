@@ -50,8 +50,9 @@ enum {
  *   recurrence, extents, wraps and penalties with fp32 path state, the 8 contributions added to S in the order down,
  *   down-right, up, left, down-left, right, up-right, up-left (4 sweeps over the volumes instead of 7, csrc/sgm_fused.cu),
  *   and, inside mccnn_disparity_pipeline / mccnn_match_pair, an fp32-accumulated cost volume. Needs all four penalties
- *   >= 0 (MCCNN_EINVAL otherwise; the exact mode only needs P1 >= 0). Environment: MCCNN_FUSED_STRICT=1 adds a gpu-scope
- *   release to every row hand-over between CTAs (see csrc/sgm_fused.cu, "link warps"); slower, same results. */
+ *   >= 0 (MCCNN_EINVAL otherwise; the exact mode only needs P1 >= 0). Environment: MCCNN_FUSED_STRICT=0 drops the gpu-scope
+ *   release of the row hand-over between CTAs (csrc/sgm_fused.cu, "link warps"): faster, measured to lose rows when several
+ *   pairs are in flight; for measurements only. */
 enum { MCCNN_SGM_EXACT = 0, MCCNN_SGM_FUSED = 1 };
 
 typedef struct {
